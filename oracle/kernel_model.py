@@ -1,0 +1,297 @@
+"""Bit-level numpy model of the CUDA kernels' arithmetic ("f32 mode"), batched over envs.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Two jobs:
+  * it is the specification of ``ipp_marl_b200/csrc`` — the belief maps written by
+    the kernels must equal this model BIT FOR BIT (only IEEE +,-,*,/,min,max in
+    float32 are used on the belief path, so numpy reproduces them exactly);
+  * it is checked against ``oracle.numpy_oracle`` (= the reference's arithmetic)
+    with the SURVEY.md section 8d gate ``allclose(rtol=1e-5, atol=1e-5)``, at batch
+    sizes the per-env oracle is too slow for.
+
+Arithmetic (DESIGN.md "belief update in odds space"): the reference's
+``1 - 1/(1 + exp(logit(x) + logit(y) - logit(prior)))`` (mapping/mappings.py:109-124)
+is algebraically ``o' = o * k`` on the odds ``o = x/(1-x)`` with
+``k = exp(logit(y) - logit(prior))``; ``k`` takes two values per altitude (cell seen
+as 1 / as 0) plus ``k_out`` for the 0.5 "not observed" cells of map2communicate.
+The clamp the reference applies before every pass is kept (in odds space), the
+state is rounded to float32 probability once per step exactly where the reference
+rounds (fuse entry), and the final ``o -> p`` uses the symmetric form so that
+probabilities near 1 keep their accuracy.
+"""
+import numpy as np
+
+from . import noise as hn
+from . import numpy_oracle as no
+
+F32 = np.float32
+
+
+class KernelTables:
+    """Host-side tables handed to the kernels (computed with the reference's own expressions)."""
+
+    def __init__(self, params):
+        geo = no.Geometry(params)
+        self.geo = geo
+        self.gx, self.gy = geo.gx, geo.gy
+        self.n_alt = geo.pz
+        self.rx = np.zeros(self.n_alt, np.int32)
+        self.ry = np.zeros(self.n_alt, np.int32)
+        for i, z in enumerate(geo.altitudes):
+            raw, _ = no.footprint(geo, np.array([0, 0, z]))
+            # raw = [yu, yd, xl, xr] around cell 0: radius = upper bound
+            self.ry[i] = raw[1]
+            self.rx[i] = raw[3]
+        # cameras.py:66: floor(position / res_x) for BOTH axes
+        self.cell_x = np.array([int(np.floor(i * geo.spacing / geo.res_x)) for i in range(geo.px)], np.int32)
+        self.cell_y = np.array([int(np.floor(i * geo.spacing / geo.res_x)) for i in range(geo.py)], np.int32)
+        prior = geo.prior
+        l_p = np.log(prior / (1 - prior))
+        self.k_hi = np.zeros(self.n_alt, F32)
+        self.k_lo = np.zeros(self.n_alt, F32)
+        self.thresh = np.zeros(self.n_alt, np.uint32)
+        for i, z in enumerate(geo.altitudes):
+            noise = no.NOISE_BY_ALTITUDE.get(int(z), 0)
+            acc = 1 - noise
+            y_hi = np.float32(np.round(acc, 3))
+            y_lo = np.float32(np.round(1 - acc, 3))
+            with np.errstate(divide="ignore"):
+                l_hi = np.log(y_hi / (1 - y_hi))  # float32, as mappings.py:113 evaluates it
+                l_lo = np.log(y_lo / (1 - y_lo))
+            self.k_hi[i] = F32(np.exp(np.float64(l_hi) - l_p))
+            self.k_lo[i] = F32(np.exp(np.float64(l_lo) - l_p))
+            self.thresh[i] = hn.flip_threshold(noise)
+        l_half = np.log(F32(0.5) / (1 - F32(0.5)))
+        self.k_out = F32(np.exp(np.float64(l_half) - l_p))
+        # clamps: float32 in probability space (first pass of the reference), and the loosest
+        # odds-space bounds covering both the float32 and the float64 clamp of later passes
+        self.p_min = F32(0.0001)
+        self.p_max = F32(0.9999)
+        o_lo32 = self.p_min / (F32(1) - self.p_min)
+        o_hi32 = self.p_max / (F32(1) - self.p_max)
+        self.o_min = min(F32(0.0001 / 0.9999), o_lo32)
+        self.o_max = max(F32(0.9999 / 0.0001), o_hi32)
+        # comm range: largest integer squared distance still within range (communication_log.py:49-53)
+        r = float(geo.comm_range)
+        d2 = int(np.floor(r * r)) + 2
+        while d2 > 0 and not (np.sqrt(np.float64(d2)) <= r):
+            d2 -= 1
+        self.comm_d2_max = d2 if r >= 0 else -1
+        fr = float(geo.failure_rate)
+        # r >= failure_rate with r = n / 2^24  <=>  n >= ceil(fr * 2^24)
+        n = int(np.ceil(fr * 16777216.0))
+        while n > 0 and (n - 1) / 16777216.0 >= fr:
+            n -= 1
+        while n / 16777216.0 < fr:
+            n += 1
+        self.fail_thresh24 = n
+
+
+def _rects(tab, pos):
+    """Clipped footprint [yu, yd, xl, xr] of positions [..., 3] (metres) via the tables."""
+    geo = tab.geo
+    ix = pos[..., 0] // geo.spacing
+    iy = pos[..., 1] // geo.spacing
+    iz = pos[..., 2] // geo.spacing - geo.min_altitude // geo.spacing
+    cx = tab.cell_x[ix]
+    cy = tab.cell_y[iy]
+    rx = tab.rx[iz]
+    ry = tab.ry[iz]
+    xl = np.clip(cx - rx, 0, tab.gx - 1)
+    xr = np.clip(cx + rx, 0, tab.gx - 1)
+    yu = np.clip(cy - ry, 0, tab.gy - 1)
+    yd = np.clip(cy + ry, 0, tab.gy - 1)
+    return np.stack([yu, yd, xl, xr], axis=-1), iz
+
+
+class KernelModelEnv:
+    """Batched env with the kernels' arithmetic.  State arrays mirror the device layout."""
+
+    def __init__(self, params, episodes, noiseless=False):
+        self.tab = KernelTables(params)
+        geo = self.tab.geo
+        self.geo = geo
+        self.episodes = np.asarray(episodes, dtype=np.int64)
+        B, A = len(self.episodes), geo.n_agents
+        self.B, self.A = B, A
+        self.noiseless = noiseless
+        gx, gy = self.tab.gx, self.tab.gy
+        self.gt = np.stack([no.ground_truth(geo, int(e)) for e in self.episodes]).astype(np.uint8)
+        self.local = np.full((B, A, gx, gy), F32(geo.prior), dtype=F32)
+        self.glob = np.full((B, gx, gy), F32(geo.prior), dtype=F32)
+        self.pos = np.stack(
+            [[no.start_position(geo, a, int(e)) for a in range(A)] for e in self.episodes]
+        ).astype(np.int64)
+        self.t = 0
+        self.flag_stuck = np.zeros(B, dtype=bool)
+        xs = np.arange(gx, dtype=np.int64)[:, None]
+        ys = np.arange(gy, dtype=np.int64)[None, :]
+        self._xs, self._ys = xs, ys
+        self._cell = (xs * gy + ys)[None]
+        # initial measurement at the start positions (agent/agent.py:44-49): own-update pass only
+        for a in range(A):
+            inr, k = self._k_of(self.pos[:, a], a, 0)
+            self.local[:, a] = self._apply(self.local[:, a], [(inr, k, False)])
+
+    # ---- measurement multipliers ---------------------------------------------------------
+    def _k_of(self, pos, agent, index):
+        """(in_rect [B,gx,gy] bool, k [B,gx,gy] f32) of the measurement (agent, index) taken at pos."""
+        tab = self.tab
+        rect, iz = _rects(tab, pos)
+        yu, yd, xl, xr = (rect[:, i][:, None, None] for i in range(4))
+        inr = (self._xs[None] >= xl) & (self._xs[None] < xr) & (self._ys[None] >= yu) & (self._ys[None] < yd)
+        key = hn.stream_key(self.geo.seed, self.episodes, agent, index, hn.PURPOSE_NOISE)
+        if self.noiseless:
+            wrong = np.zeros(inr.shape, dtype=bool)
+        else:
+            h = hn.cell_hash(key[:, None, None], self._cell)
+            wrong = h < tab.thresh[iz][:, None, None]
+        seen_one = (self.gt != 0) ^ wrong
+        k = np.where(seen_one, tab.k_hi[iz][:, None, None], tab.k_lo[iz][:, None, None]).astype(F32)
+        return inr, k
+
+    # ---- one map through a list of passes ------------------------------------------------
+    def _apply(self, p, passes):
+        """passes: list of (in_rect, k, is_fuse[, enabled[B]]).  Returns the new float32 map.
+
+        fuse pass : every cell is clamped, cells in the rect *= k, the others *= k_out
+        own update: only cells in the rect are clamped and *= k  (mappings.py:46-61)
+        """
+        tab = self.tab
+        p = p.astype(F32, copy=True)
+        B = p.shape[0]
+        touched = np.zeros(p.shape, dtype=bool)  # some pass multiplied by k != 1
+        clamped = np.zeros(p.shape, dtype=bool)  # some pass clamped the cell
+        kout_is_one = bool(tab.k_out == F32(1))
+        for ps in passes:
+            inr, k, is_fuse = ps[0], ps[1], ps[2]
+            en = ps[3][:, None, None] if len(ps) > 3 else np.ones((B, 1, 1), dtype=bool)
+            if is_fuse:
+                clamped |= en
+                touched |= en & (inr | (not kout_is_one))
+            else:
+                clamped |= en & inr
+                touched |= en & inr
+        pc = np.minimum(np.maximum(p, tab.p_min), tab.p_max)
+        with np.errstate(over="ignore", invalid="ignore"):
+            o = pc / (F32(1) - pc)
+            for ps in passes:
+                inr, k, is_fuse = ps[0], ps[1], ps[2]
+                en = ps[3][:, None, None] if len(ps) > 3 else np.ones((B, 1, 1), dtype=bool)
+                oc = np.minimum(np.maximum(o, tab.o_min), tab.o_max)
+                if is_fuse:
+                    kk = np.where(inr, k, tab.k_out).astype(F32)
+                    o = np.where(en, oc * kk, o)
+                else:
+                    o = np.where(en & inr, oc * k, o)
+            one = F32(1)
+            d = one + o
+            small = o / d
+            big = one - one / d
+            pn = np.where(o < one, small, big).astype(F32)
+        return np.where(touched, pn, np.where(clamped, pc, p)).astype(F32)
+
+    # ---- comm matrix ------------------------------------------------------------------------
+    def comm(self):
+        tab, A = self.tab, self.A
+        out = np.zeros((self.B, A, A), dtype=bool)
+        for i in range(A):
+            key = hn.stream_key(self.geo.seed, self.episodes, i, self.t, hn.PURPOSE_COMM)
+            for j in range(A):
+                d = self.pos[:, i] - self.pos[:, j]
+                d2 = (d * d).sum(-1)
+                n24 = hn.cell_hash(key, j) >> np.uint32(8)
+                out[:, i, j] = (d2 == 0) | ((d2 <= tab.comm_d2_max) & (n24 >= tab.fail_thresh24))
+        return out
+
+    # ---- masks / moves ------------------------------------------------------------------------
+    def _choose_and_move(self, actions):
+        geo, A, B = self.geo, self.A, self.B
+        sp = geo.spacing
+        new_pos = self.pos.copy()
+        masks = np.zeros((B, A, 6), dtype=np.uint8)
+        acts = np.zeros((B, A), dtype=np.int64)
+        for a in range(A):
+            p = self.pos[:, a]
+            m = np.ones((B, 6), dtype=bool)
+            m[:, 0] &= p[:, 2] != geo.max_altitude
+            m[:, 5] &= p[:, 2] != geo.min_altitude
+            m[:, 2] &= p[:, 1] != 0
+            m[:, 3] &= p[:, 1] != geo.y_dim_m
+            m[:, 1] &= p[:, 0] != 0
+            m[:, 4] &= p[:, 0] != geo.x_dim_m
+            for j in range(a):
+                q = new_pos[:, j]
+                dx = q[:, 0] // sp - p[:, 0] // sp
+                dy = q[:, 1] // sp - p[:, 1] // sp
+                for cond, idxs in (
+                    ((dx == 0) & (dy == 0), (0, 5)),
+                    ((dx == -1) & (dy == 0), (1,)),
+                    ((dx == 0) & (dy == -1), (2,)),
+                    ((dx == 0) & (dy == 1), (3,)),
+                    ((dx == 1) & (dy == 0), (4,)),
+                ):
+                    go = cond & (m.sum(1) > 1)
+                    for ix in idxs:
+                        m[go, ix] = False
+            cnt = m.sum(1)
+            if actions is None:
+                key = hn.stream_key(geo.seed, self.episodes, a, self.t, hn.PURPOSE_ACTION)
+                u = hn.uniform01(hn.cell_hash(key, 0))
+                kth = np.minimum((u * cnt.astype(F32)).astype(np.int64), np.maximum(cnt - 1, 0))
+                order = np.cumsum(m, axis=1) - 1
+                pick = (m & (order == kth[:, None])).argmax(1)
+                act = np.where(cnt > 0, pick, -1)
+            else:
+                act = np.asarray(actions)[:, a].astype(np.int64)
+            self.flag_stuck |= cnt == 0
+            off = np.zeros((B, 3), dtype=np.int64)
+            off[act == 0, 2] = sp
+            off[act == 1, 0] = -sp
+            off[act == 2, 1] = -sp
+            off[act == 3, 1] = sp
+            off[act == 4, 0] = sp
+            off[act == 5, 2] = -sp
+            new_pos[:, a] = p + off
+            masks[:, a] = m
+            acts[:, a] = act
+        return new_pos, masks, acts
+
+    # ---- reward -------------------------------------------------------------------------------
+    def _reward(self, last, nxt):
+        """utils/reward.py:68-82 with float32 per-cell terms and float64 sums."""
+        tab = self.tab
+
+        def H(p):
+            pc = np.minimum(np.maximum(p, tab.p_min), tab.p_max).astype(F32)
+            q = F32(1) - pc
+            return (-pc * np.log2(pc) - q * np.log2(q)).astype(F32)
+
+        w = np.where(nxt.astype(np.float64) > 0.501, F32(1), np.where(nxt.astype(np.float64) < 0.499, F32(0), F32(0.5)))
+        hl, hn_ = H(last), H(nxt)
+        s1 = (w * (hl - hn_)).astype(np.float64).sum(axis=(1, 2))
+        s2 = (w * hl).astype(np.float64).sum(axis=(1, 2))
+        n = float(self.tab.gx * self.tab.gy)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = 22.0 * (s1 / s2) - 0.5
+        ab = 10.0 * (s1 / n) - 0.17
+        return rel.astype(F32), ab.astype(F32)
+
+    # ---- one fused env step (ipp_step) ---------------------------------------------------------
+    def step(self, actions=None):
+        A = self.A
+        comm = self.comm()
+        prev = [self._k_of(self.pos[:, j], j, self.t) for j in range(A)]
+        new_pos, masks, acts = self._choose_and_move(actions)
+        new = [self._k_of(new_pos[:, i], i, self.t + 1) for i in range(A)]
+        last = self.glob
+        self.glob = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
+        rel, ab = self._reward(last, self.glob)
+        fused = np.empty_like(self.local)
+        for i in range(A):
+            passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
+            fused[:, i] = self._apply(self.local[:, i], passes)
+            self.local[:, i] = self._apply(self.local[:, i], passes + [(new[i][0], new[i][1], False)])
+        self.local_fused_model = fused  # what a separate observe kernel would have stored
+        self.pos = new_pos
+        self.t += 1
+        return dict(comm=comm, mask=masks, action=acts, reward_rel=rel, reward_abs=ab)

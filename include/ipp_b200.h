@@ -1,0 +1,163 @@
+/*
+ * ipp_b200.h — C ABI of the B200-native batched informative-path-planning environment.
+ *
+ * The reference (dmar-bonn/ipp-marl, Python/numpy) has no FFI; its "operator interface" for the
+ * per-timestep environment path is the Python surface listed in SURVEY.md section 8b.  This header is
+ * what a binding for that path would target (INTEGRATION.md shows the ctypes stub).  Each entry
+ * point cites the reference code it replaces (paths relative to marl_framework/).
+ *
+ * Conventions: every function returns 0 (IPP_OK) or a negative ipp_status; nothing throws; the
+ * caller owns every buffer; "device" pointers are CUDA device memory of the current device,
+ * "host" pointers are ordinary host memory; `stream` is a cudaStream_t passed as void* (NULL =
+ * the legacy default stream).  Distinct handles may be used from distinct threads.
+ *
+ * Layouts (all C-contiguous):
+ *   belief maps   float32 [..., map_stride], cell (x, y) at x * gy + y  — first array axis is
+ *                 world x exactly as in the reference (mapping/mappings.py:46-61); map_stride >=
+ *                 gx*gy is a multiple of 4 cells so every map starts 16-byte aligned.
+ *   ground truth  uint8   [n_envs, map_stride]   (mapping/ground_truths.py:42-56 half-plane field)
+ *   positions     int32   [n_envs, n_agents, 3]  metres (x, y, z), as agent/agent.py keeps them
+ *   episodes      uint32  [n_envs]               episode number of each env (seeds + random streams)
+ */
+#ifndef IPP_B200_H
+#define IPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPP_MAX_AGENTS 8
+#define IPP_MAX_ALT 8
+#define IPP_MAX_LATTICE 128
+#define IPP_N_ACTIONS 6
+
+typedef enum ipp_status {
+  IPP_OK = 0,
+  IPP_ERR_INVALID_ARG = -1,
+  IPP_ERR_UNSUPPORTED = -2,
+  IPP_ERR_CUDA = -3,
+  IPP_ERR_NO_DEVICE = -4,
+  IPP_ERR_ALLOC = -5
+} ipp_status;
+
+/*
+ * Static description of one batch of environments.  The geometric / arithmetic tables are
+ * computed ON THE HOST with the reference's own float64 expressions (ipp_marl_b200/geometry.py)
+ * because they sit on floating-point knife edges (SURVEY.md section 7 "exact geometry").
+ */
+typedef struct ipp_config {
+  int32_t gx, gy;          /* belief cells per side: mapping/grid_maps.py:16-50                    */
+  int32_t map_stride;      /* cells between consecutive maps, multiple of 4, >= gx*gy             */
+  int32_t px, py, n_alt;   /* agent lattice: agent/state_space.py:16-18                            */
+  int32_t n_agents;        /* 1..IPP_MAX_AGENTS                                                    */
+  int32_t n_envs;          /* envs owned by this handle (this GPU's shard)                         */
+  int32_t spacing;         /* metres between lattice points                                        */
+  int32_t min_altitude, max_altitude, x_dim_m, y_dim_m;
+  int32_t budget;          /* last timestep index: coma_wrapper.py:163-164                         */
+  uint32_t seed;           /* environment.seed                                                     */
+  int32_t comm_d2_max;     /* largest squared distance (m^2) with sqrt(d2) <= communication_range  */
+  uint32_t fail_thresh24;  /* message delivered iff (hash >> 8) >= fail_thresh24                   */
+  float prior;             /* mapping.prior                                                        */
+  float k_out;             /* odds multiplier of a 0.5 cell of map2communicate = exp(-logit prior) */
+  float p_min, p_max;      /* float32(0.0001), float32(0.9999): mapping/mappings.py:110-111        */
+  float o_min, o_max;      /* same clamp in odds space                                             */
+  int32_t radius_x[IPP_MAX_ALT], radius_y[IPP_MAX_ALT]; /* sensors/cameras.py:62-67 per altitude   */
+  float k_hi[IPP_MAX_ALT], k_lo[IPP_MAX_ALT]; /* odds multipliers of a cell seen as 1 / as 0       */
+  uint32_t flip_thresh[IPP_MAX_ALT];          /* cell measured wrongly iff hash < flip_thresh      */
+  int32_t cell_x[IPP_MAX_LATTICE], cell_y[IPP_MAX_LATTICE]; /* floor(pos/res_x): cameras.py:66     */
+} ipp_config;
+
+/* Device-resident state of the batch (struct-of-arrays form of agent/agent.py:13-38 per UAV and of
+ * the accumulated global map of missions/episode_generator.py:47,53). */
+typedef struct ipp_state {
+  float* local_maps;   /* [n_envs, n_agents, map_stride]  Agent.local_map                          */
+  float* global_map;   /* [n_envs, map_stride]            accumulated_map_knowledge                */
+  uint8_t* ground_truth; /* [n_envs, map_stride]          Mapping.simulated_map                    */
+  uint32_t* episodes;  /* [n_envs]                                                                  */
+} ipp_state;
+
+/* Per-step inputs / outputs (device pointers; any output may be NULL). */
+typedef struct ipp_step_io {
+  const int32_t* pos_in;    /* [n_envs, n_agents, 3] positions at the start of the step            */
+  int32_t* pos_out;         /* [n_envs, n_agents, 3] positions after the moves                     */
+  const int32_t* actions_in;/* [n_envs, n_agents] injected actions (-1 = stay) or NULL             */
+  const float* probs_in;    /* [n_envs, n_agents, 6] policy probabilities or NULL; with both NULL  */
+                            /* the policy is uniform over the unmasked actions                     */
+  int32_t greedy;           /* probs_in: 0 = sample like torch.multinomial(p*mask), 1 = argmax     */
+  int32_t* actions_out;     /* [n_envs, n_agents] chosen actions                                   */
+  uint8_t* mask_out;        /* [n_envs, n_agents] bit a = action a allowed (after collision mask)  */
+  uint8_t* comm_out;        /* [n_envs, n_agents] bit j = agent i received agent j's message       */
+  float* reward_rel;        /* [n_envs] 22*rel-0.5 : utils/reward.py:39-41                         */
+  float* reward_abs;        /* [n_envs] 10*abs-0.17: utils/reward.py:38                            */
+  uint8_t* stuck_out;       /* [n_envs] 1 if some agent had an all-zero mask (stayed in place)     */
+} ipp_step_io;
+
+typedef struct ipp_handle ipp_handle;
+
+const char* ipp_status_string(int status);
+/* Text of the last CUDA error seen by this handle ("" if none). */
+const char* ipp_last_error(const ipp_handle* h);
+int ipp_version(void);
+
+/* Validate the config, pick launch geometry, allocate the (small) per-handle scratch. */
+int ipp_create(const ipp_config* cfg, ipp_handle** out);
+int ipp_destroy(ipp_handle* h);
+/* Bytes of device scratch held by the handle (reward partials, reset parameters). */
+int64_t ipp_scratch_bytes(const ipp_handle* h);
+
+/*
+ * Episode reset for the whole batch.  Replaces, per env: Mapping.__init__ -> Simulation ->
+ * gaussian_random_field (mapping/ground_truths.py:42-56: MT19937 seeded with the episode number),
+ * Mapping.init_priors (mapping/mappings.py:126-132), AgentStateSpace.get_random_agent_state
+ * (agent/state_space.py:28-51: MT19937 seeded with seed*episode*agent) and the t == 0 measurement
+ * of Agent.communicate (agent/agent.py:44-49).  `pos_out` receives the start positions.
+ */
+int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream);
+
+/*
+ * One full environment timestep, fused (policy = injected actions, given probabilities or uniform):
+ * CommunicationLog.get_messages (agent/communication_log.py:39-58) -> Agent.receive_messages /
+ * Mapping.fuse_map "local" (agent/agent.py:62-71, mapping/mappings.py:82-89) -> fuse_map "global"
+ * (coma_wrapper.py:93-95) -> get_global_reward (utils/reward.py:11-53) -> per agent, in id order:
+ * get_action_mask / apply_collision_mask / action choice / action_to_position
+ * (agent/action_space.py:56-70,211-223,328-344) -> Mapping.update_grid_map at the new position
+ * (mapping/mappings.py:32-78).  t is the timestep index (0..budget).
+ */
+int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
+
+/* The same timestep split around the policy network: ipp_observe = everything before the actor
+ * forward (fuse local + global + reward; io->pos_in only), ipp_act = masks, action choice, move
+ * and the measurement update at the new positions. */
+int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
+int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
+
+/* ---- single-map entry points used by the drop-in facade (host pointers, synchronous) -------- */
+
+/* Camera.project_field_of_view (sensors/cameras.py:46-79): position[3] metres ->
+ * raw[4], clipped[4] = [yu, yd, xl, xr].  Pure host arithmetic on the config tables. */
+int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, int32_t* clipped);
+
+/* Mapping.update_cells / apply_update (mapping/mappings.py:106-124) on n cells:
+ * x is clamped IN PLACE like the reference; y is per cell (y_is_scalar == 0) or one value
+ * (IG_baseline.py:240-245 passes a Python float); out = updated probabilities. */
+int ipp_update_cells(ipp_handle* h, float* x_host, const float* y_host, int32_t y_is_scalar, int64_t n,
+                     float* out_host);
+
+/* get_shannon_entropy (utils/state.py:118-121): p clamped IN PLACE, H written to out. */
+int ipp_shannon_entropy(ipp_handle* h, float* p_host, int64_t n, float* out_host);
+
+/* Mapping.fuse_map (mapping/mappings.py:80-104): own [cells] fused with n_others dense maps
+ * (map2communicate arrays, [n_others, cells]) in order; result in out (own is not modified). */
+int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host, int32_t n_others,
+                 int64_t cells, float* out_host);
+
+/* get_utility_reward (utils/reward.py:68-82) on two dense maps: out[0] = absolute, out[1] = relative. */
+int ipp_utility_reward(ipp_handle* h, const float* last_host, const float* next_host, int64_t cells,
+                       double* out2_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPP_B200_H */

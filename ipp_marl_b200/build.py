@@ -1,0 +1,64 @@
+"""Build the CUDA library (nvcc, sm_100a) in-tree: ipp_marl_b200/_lib/libipp_b200.so.
+
+The built .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "_lib")
+LIB = os.path.join(LIBDIR, "libipp_b200.so")
+STAMP = os.path.join(LIBDIR, "libipp_b200.stamp")
+SOURCES = ["ipp_kernels.cu", "ipp_facade_kernels.cu", "ipp_abi.cu"]
+HEADERS = ["ipp_device.cuh", "ipp_launch.h", os.path.join("..", "..", "include", "ipp_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def nvcc_path():
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    return cand if os.path.exists(cand) else None
+
+
+def build(force=False, verbose=False):
+    """Compile if sources changed; returns the library path.  Raises if nvcc fails."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+        with open(STAMP) as f:
+            if f.read().strip() == digest:
+                return LIB
+    nvcc = nvcc_path()
+    if nvcc is None:
+        if os.path.exists(LIB):
+            return LIB  # box without a toolkit: use the prebuilt library shipped with the snapshot
+        raise RuntimeError("nvcc not found and no prebuilt %s" % LIB)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
+    if verbose:
+        print(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,287 @@
+// C ABI (include/ipp_b200.h): argument validation, launch planning, scratch ownership.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ipp_launch.h"
+
+struct ipp_handle {
+  ipp_config cfg;
+  ipp::LaunchPlan plan;
+  int device;
+  double* partials;     // [n_envs, n_chunks, 2]
+  int32_t* gt_params;   // [n_envs, 4]
+  uint8_t* comm;        // [n_envs, n_agents] when the caller does not ask for comm_out
+  // facade scratch (grown on demand)
+  void* fbuf;
+  size_t fbuf_bytes;
+  int64_t scratch_bytes;
+  char err[256];
+};
+
+namespace {
+
+int fail_cuda(ipp_handle* h, cudaError_t e, const char* where) {
+  if (h != nullptr) snprintf(h->err, sizeof(h->err), "%s: %s", where, cudaGetErrorString(e));
+  return IPP_ERR_CUDA;
+}
+
+#define IPP_CUDA(h, call)                                 \
+  do {                                                    \
+    cudaError_t e_ = (call);                              \
+    if (e_ != cudaSuccess) return fail_cuda(h, e_, #call); \
+  } while (0)
+
+int validate(const ipp_config* c) {
+  if (c == nullptr) return IPP_ERR_INVALID_ARG;
+  if (c->gx <= 0 || c->gy <= 0 || c->n_envs <= 0) return IPP_ERR_INVALID_ARG;
+  if ((int64_t)c->gx * c->gy > (1 << 28)) return IPP_ERR_UNSUPPORTED;
+  if (c->map_stride < c->gx * c->gy || (c->map_stride & 3) != 0) return IPP_ERR_INVALID_ARG;
+  if (c->n_agents < 1 || c->n_agents > IPP_MAX_AGENTS) return IPP_ERR_UNSUPPORTED;
+  if (c->n_alt < 1 || c->n_alt > IPP_MAX_ALT) return IPP_ERR_UNSUPPORTED;
+  if (c->px < 1 || c->px > IPP_MAX_LATTICE || c->py < 1 || c->py > IPP_MAX_LATTICE) return IPP_ERR_UNSUPPORTED;
+  if (c->spacing <= 0 || c->min_altitude % c->spacing != 0) return IPP_ERR_INVALID_ARG;
+  if (!(c->prior > 0.0f && c->prior < 1.0f)) return IPP_ERR_INVALID_ARG;
+  if (!(c->o_min > 0.0f) || !(c->o_max > c->o_min) || !(c->p_max > c->p_min)) return IPP_ERR_INVALID_ARG;
+  for (int i = 0; i < c->n_alt; ++i)
+    if (c->radius_x[i] < 0 || c->radius_y[i] < 0 || !(c->k_hi[i] > 0.0f) || !(c->k_lo[i] > 0.0f))
+      return IPP_ERR_INVALID_ARG;
+  for (int i = 0; i < c->px; ++i)
+    if (c->cell_x[i] < 0) return IPP_ERR_INVALID_ARG;
+  for (int i = 0; i < c->py; ++i)
+    if (c->cell_y[i] < 0) return IPP_ERR_INVALID_ARG;
+  return IPP_OK;
+}
+
+int check_state(const ipp_state* st) {
+  if (st == nullptr || st->local_maps == nullptr || st->global_map == nullptr || st->ground_truth == nullptr ||
+      st->episodes == nullptr)
+    return IPP_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(st->local_maps) & 15) || (reinterpret_cast<uintptr_t>(st->global_map) & 15) ||
+      (reinterpret_cast<uintptr_t>(st->ground_truth) & 3))
+    return IPP_ERR_INVALID_ARG;
+  return IPP_OK;
+}
+
+int ensure_fbuf(ipp_handle* h, size_t bytes) {
+  if (h->fbuf_bytes >= bytes) return IPP_OK;
+  if (h->fbuf != nullptr) cudaFree(h->fbuf);
+  h->fbuf = nullptr;
+  h->fbuf_bytes = 0;
+  IPP_CUDA(h, cudaMalloc(&h->fbuf, bytes));
+  h->fbuf_bytes = bytes;
+  return IPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ipp_status_string(int status) {
+  switch (status) {
+    case IPP_OK: return "ok";
+    case IPP_ERR_INVALID_ARG: return "invalid argument";
+    case IPP_ERR_UNSUPPORTED: return "unsupported configuration";
+    case IPP_ERR_CUDA: return "CUDA error (see ipp_last_error)";
+    case IPP_ERR_NO_DEVICE: return "no CUDA device";
+    case IPP_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+  }
+}
+
+const char* ipp_last_error(const ipp_handle* h) { return h != nullptr ? h->err : ""; }
+
+int ipp_version(void) { return 100; }
+
+int ipp_create(const ipp_config* cfg, ipp_handle** out) {
+  if (out == nullptr) return IPP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc != IPP_OK) return rc;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return IPP_ERR_NO_DEVICE;
+  ipp_handle* h = new (std::nothrow) ipp_handle;
+  if (h == nullptr) return IPP_ERR_ALLOC;
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  if (cudaGetDevice(&h->device) != cudaSuccess) {
+    delete h;
+    return IPP_ERR_NO_DEVICE;
+  }
+  const int32_t n_quads = h->cfg.map_stride >> 2;
+  h->plan.quads_per_chunk = 1024;
+  h->plan.n_chunks = (n_quads + h->plan.quads_per_chunk - 1) / h->plan.quads_per_chunk;
+  const size_t pb = sizeof(double) * 2 * (size_t)cfg->n_envs * h->plan.n_chunks;
+  const size_t gb = sizeof(int32_t) * 4 * (size_t)cfg->n_envs;
+  const size_t cb = (size_t)cfg->n_envs * cfg->n_agents;
+  if (cudaMalloc(&h->partials, pb) != cudaSuccess || cudaMalloc(&h->gt_params, gb) != cudaSuccess ||
+      cudaMalloc(&h->comm, cb) != cudaSuccess) {
+    ipp_destroy(h);
+    return IPP_ERR_ALLOC;
+  }
+  h->scratch_bytes = (int64_t)(pb + gb + cb);
+  *out = h;
+  return IPP_OK;
+}
+
+int ipp_destroy(ipp_handle* h) {
+  if (h == nullptr) return IPP_OK;
+  if (h->partials) cudaFree(h->partials);
+  if (h->gt_params) cudaFree(h->gt_params);
+  if (h->comm) cudaFree(h->comm);
+  if (h->fbuf) cudaFree(h->fbuf);
+  delete h;
+  return IPP_OK;
+}
+
+int64_t ipp_scratch_bytes(const ipp_handle* h) { return h != nullptr ? h->scratch_bytes + (int64_t)h->fbuf_bytes : 0; }
+
+int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream) {
+  if (h == nullptr || pos_out == nullptr) return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  IPP_CUDA(h, ipp::launch_reset(h->cfg, *st, h->plan, pos_out, h->gt_params, (cudaStream_t)stream));
+  return IPP_OK;
+}
+
+int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+  if (h == nullptr || io == nullptr || io->pos_in == nullptr || io->pos_out == nullptr || io->pos_in == io->pos_out)
+    return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
+  ipp_step_io io2 = *io;
+  if (io2.comm_out == nullptr) io2.comm_out = h->comm;
+  cudaStream_t s = (cudaStream_t)stream;
+  IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 1, s));
+  IPP_CUDA(h, ipp::launch_step_dense(h->cfg, *st, h->plan, io2.pos_in, io2.pos_out, io2.comm_out, t, io2.reward_rel,
+                                     io2.reward_abs, h->partials, true, s));
+  return IPP_OK;
+}
+
+int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+  if (h == nullptr || io == nullptr || io->pos_in == nullptr) return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
+  ipp_step_io io2 = *io;
+  if (io2.comm_out == nullptr) io2.comm_out = h->comm;
+  cudaStream_t s = (cudaStream_t)stream;
+  IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 0, s));
+  IPP_CUDA(h, ipp::launch_step_dense(h->cfg, *st, h->plan, io2.pos_in, io2.pos_in, io2.comm_out, t, io2.reward_rel,
+                                     io2.reward_abs, h->partials, false, s));
+  return IPP_OK;
+}
+
+int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+  if (h == nullptr || io == nullptr || io->pos_in == nullptr || io->pos_out == nullptr || io->pos_in == io->pos_out)
+    return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, *io, t, 0, 1, s));
+  IPP_CUDA(h, ipp::launch_own_update(h->cfg, *st, io->pos_out, t, s));
+  return IPP_OK;
+}
+
+int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, int32_t* clipped) {
+  if (h == nullptr || position == nullptr || raw == nullptr || clipped == nullptr) return IPP_ERR_INVALID_ARG;
+  const ipp_config& c = h->cfg;
+  if (position[0] < 0 || position[1] < 0 || position[0] % c.spacing || position[1] % c.spacing ||
+      position[2] % c.spacing)
+    return IPP_ERR_INVALID_ARG;
+  const int ix = position[0] / c.spacing, iy = position[1] / c.spacing;
+  const int iz = position[2] / c.spacing - c.min_altitude / c.spacing;
+  if (ix >= c.px || iy >= c.py || iz < 0 || iz >= c.n_alt) return IPP_ERR_INVALID_ARG;
+  const int cx = c.cell_x[ix], cy = c.cell_y[iy], rx = c.radius_x[iz], ry = c.radius_y[iz];
+  raw[0] = cy - ry;  // yu
+  raw[1] = cy + ry;  // yd
+  raw[2] = cx - rx;  // xl
+  raw[3] = cx + rx;  // xr
+  auto clip = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+  clipped[0] = clip(raw[0], c.gy - 1);
+  clipped[1] = clip(raw[1], c.gy - 1);
+  clipped[2] = clip(raw[2], c.gx - 1);
+  clipped[3] = clip(raw[3], c.gx - 1);
+  return IPP_OK;
+}
+
+int ipp_update_cells(ipp_handle* h, float* x_host, const float* y_host, int32_t y_is_scalar, int64_t n,
+                     float* out_host) {
+  if (h == nullptr || x_host == nullptr || y_host == nullptr || out_host == nullptr || n < 0)
+    return IPP_ERR_INVALID_ARG;
+  if (n == 0) return IPP_OK;
+  const size_t nb = sizeof(float) * (size_t)n;
+  int rc = ensure_fbuf(h, 3 * nb);
+  if (rc != IPP_OK) return rc;
+  float* dx = static_cast<float*>(h->fbuf);
+  float* dy = dx + n;
+  float* dout = dy + n;
+  IPP_CUDA(h, cudaMemcpy(dx, x_host, nb, cudaMemcpyHostToDevice));
+  if (!y_is_scalar) IPP_CUDA(h, cudaMemcpy(dy, y_host, nb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, ipp::launch_update_cells(h->cfg, dx, dy, y_is_scalar, y_is_scalar ? y_host[0] : 0.0f, n, dout, 0));
+  IPP_CUDA(h, cudaMemcpy(x_host, dx, nb, cudaMemcpyDeviceToHost));
+  IPP_CUDA(h, cudaMemcpy(out_host, dout, nb, cudaMemcpyDeviceToHost));
+  return IPP_OK;
+}
+
+int ipp_shannon_entropy(ipp_handle* h, float* p_host, int64_t n, float* out_host) {
+  if (h == nullptr || p_host == nullptr || out_host == nullptr || n < 0) return IPP_ERR_INVALID_ARG;
+  if (n == 0) return IPP_OK;
+  const size_t nb = sizeof(float) * (size_t)n;
+  int rc = ensure_fbuf(h, 2 * nb);
+  if (rc != IPP_OK) return rc;
+  float* dp = static_cast<float*>(h->fbuf);
+  float* dout = dp + n;
+  IPP_CUDA(h, cudaMemcpy(dp, p_host, nb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, ipp::launch_entropy(h->cfg, dp, n, dout, 0));
+  IPP_CUDA(h, cudaMemcpy(p_host, dp, nb, cudaMemcpyDeviceToHost));
+  IPP_CUDA(h, cudaMemcpy(out_host, dout, nb, cudaMemcpyDeviceToHost));
+  return IPP_OK;
+}
+
+int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host, int32_t n_others, int64_t cells,
+                 float* out_host) {
+  if (h == nullptr || own_host == nullptr || out_host == nullptr || cells < 0 || n_others < 0 ||
+      (n_others > 0 && others_host == nullptr))
+    return IPP_ERR_INVALID_ARG;
+  if (cells == 0) return IPP_OK;
+  const size_t nb = sizeof(float) * (size_t)cells;
+  int rc = ensure_fbuf(h, 3 * nb);
+  if (rc != IPP_OK) return rc;
+  float* cur = static_cast<float*>(h->fbuf);
+  float* dy = cur + cells;
+  float* nxt = dy + cells;
+  IPP_CUDA(h, cudaMemcpy(cur, own_host, nb, cudaMemcpyHostToDevice));
+  for (int32_t k = 0; k < n_others; ++k) {
+    IPP_CUDA(h, cudaMemcpy(dy, others_host + (size_t)k * cells, nb, cudaMemcpyHostToDevice));
+    IPP_CUDA(h, ipp::launch_update_cells(h->cfg, cur, dy, 0, 0.0f, cells, nxt, 0));
+    float* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  IPP_CUDA(h, cudaMemcpy(out_host, cur, nb, cudaMemcpyDeviceToHost));
+  return IPP_OK;
+}
+
+int ipp_utility_reward(ipp_handle* h, const float* last_host, const float* next_host, int64_t cells,
+                       double* out2_host) {
+  if (h == nullptr || last_host == nullptr || next_host == nullptr || out2_host == nullptr || cells <= 0)
+    return IPP_ERR_INVALID_ARG;
+  const size_t nb = sizeof(float) * (size_t)cells;
+  const size_t rb = sizeof(double) * (2 + 2 * 296);
+  const size_t nb_al = (2 * nb + 15) & ~(size_t)15;
+  int rc = ensure_fbuf(h, nb_al + rb);
+  if (rc != IPP_OK) return rc;
+  float* dl = static_cast<float*>(h->fbuf);
+  float* dn = dl + cells;
+  double* dres = reinterpret_cast<double*>(static_cast<char*>(h->fbuf) + nb_al);
+  IPP_CUDA(h, cudaMemcpy(dl, last_host, nb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, cudaMemcpy(dn, next_host, nb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, ipp::launch_utility_reward(h->cfg, dl, dn, cells, dres, 0));
+  IPP_CUDA(h, cudaMemcpy(out2_host, dres, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  return IPP_OK;
+}
+
+}  // extern "C"

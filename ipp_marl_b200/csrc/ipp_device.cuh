@@ -1,0 +1,109 @@
+// Device-side building blocks shared by all kernels: counter-based hash, footprint geometry,
+// odds-space Bayes update.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ipp_b200.h"
+
+namespace ipp {
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based hash (specification: oracle/noise.py).  Replaces the reference's global-RNG draws
+// (mapping/simulations.py:56-58, actor/network.py:94, agent/communication_log.py:46).
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t { PURPOSE_NOISE = 0, PURPOSE_ACTION = 1, PURPOSE_COMM = 2 };
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x21F0AAADu;
+  x ^= x >> 15;
+  x *= 0x735A2D97u;
+  x ^= x >> 15;
+  return x;
+}
+
+__host__ __device__ __forceinline__ uint32_t stream_key(uint32_t seed, uint32_t episode, uint32_t agent,
+                                                        uint32_t index, uint32_t purpose) {
+  uint32_t k = mix32(seed + 0x9E3779B9u);
+  k = mix32(k ^ episode);
+  k = mix32(k + ((purpose << 24) | (agent << 16) | index));
+  return k;
+}
+
+__host__ __device__ __forceinline__ uint32_t cell_hash(uint32_t key, uint32_t cell) {
+  return mix32(key ^ (cell * 0x9E3779B1u));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Footprint of a measurement (sensors/cameras.py:46-79 through the host tables).
+// ------------------------------------------------------------------------------------------------
+struct Meas {
+  int32_t xl, xr, yu, yd;  // clipped, half-open like the reference's slices (mappings.py:46-49)
+  uint32_t key;            // noise stream of this measurement
+  uint32_t thresh;         // flip threshold of its altitude
+  float k_hi, k_lo;        // odds multipliers
+};
+
+__device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return min(max(v, lo), hi); }
+
+__device__ __forceinline__ Meas make_meas(const ipp_config& c, const int32_t* pos, uint32_t episode, uint32_t agent,
+                                          uint32_t index) {
+  Meas m;
+  const int32_t ix = pos[0] / c.spacing, iy = pos[1] / c.spacing;
+  const int32_t iz = pos[2] / c.spacing - c.min_altitude / c.spacing;
+  const int32_t cx = c.cell_x[ix], cy = c.cell_y[iy];
+  const int32_t rx = c.radius_x[iz], ry = c.radius_y[iz];
+  m.xl = clampi(cx - rx, 0, c.gx - 1);
+  m.xr = clampi(cx + rx, 0, c.gx - 1);
+  m.yu = clampi(cy - ry, 0, c.gy - 1);
+  m.yd = clampi(cy + ry, 0, c.gy - 1);
+  m.key = stream_key(c.seed, episode, agent, index, PURPOSE_NOISE);
+  m.thresh = c.flip_thresh[iz];
+  m.k_hi = c.k_hi[iz];
+  m.k_lo = c.k_lo[iz];
+  return m;
+}
+
+__device__ __forceinline__ bool in_rect(const Meas& m, int32_t x, int32_t y) {
+  return (uint32_t)(x - m.xl) < (uint32_t)(m.xr - m.xl) && (uint32_t)(y - m.yu) < (uint32_t)(m.yd - m.yu);
+}
+
+// Odds multiplier of this measurement at a cell inside its rect:
+// mapping/simulations.py:42-65 (value = accuracy if the cell is seen as 1 else 1-accuracy).
+__device__ __forceinline__ float meas_k(const Meas& m, uint32_t cell, uint32_t gt) {
+  const bool wrong = cell_hash(m.key, cell) < m.thresh;
+  const bool seen_one = (gt != 0u) != wrong;
+  return seen_one ? m.k_hi : m.k_lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bayes update in odds space (specification: oracle/kernel_model.py::_apply).
+// Only IEEE float32 +,-,*,/,min,max: the belief path is bit-reproducible on the CPU.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clamp_p(const ipp_config& c, float p) { return fminf(fmaxf(p, c.p_min), c.p_max); }
+
+__device__ __forceinline__ float to_odds(float pc) { return __fdiv_rn(pc, __fsub_rn(1.0f, pc)); }
+
+__device__ __forceinline__ float odds_pass(float o, float k, float o_min, float o_max) {
+  return __fmul_rn(fminf(fmaxf(o, o_min), o_max), k);
+}
+
+__device__ __forceinline__ float from_odds(float o) {
+  const float d = __fadd_rn(1.0f, o);
+  return (o < 1.0f) ? __fdiv_rn(o, d) : __fsub_rn(1.0f, __fdiv_rn(1.0f, d));
+}
+
+// Weighted entropy terms of the reward (utils/state.py:53-76,118-121; utils/reward.py:68-82).
+__device__ __forceinline__ float shannon(const ipp_config& c, float p) {
+  const float pc = clamp_p(c, p);
+  const float q = 1.0f - pc;
+  return -pc * log2f(pc) - q * log2f(q);
+}
+
+__device__ __forceinline__ float weight_of(float p_next) {
+  const double d = (double)p_next;
+  return d > 0.501 ? 1.0f : (d < 0.499 ? 0.0f : 0.5f);
+}
+
+}  // namespace ipp

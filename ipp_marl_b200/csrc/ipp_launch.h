@@ -1,0 +1,34 @@
+// Host-visible launch plan + launcher prototypes (kernels live in ipp_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ipp_b200.h"
+
+namespace ipp {
+
+constexpr int STEP_THREADS = 256;
+
+struct LaunchPlan {
+  int32_t n_chunks;         // chunks per env map (1 => per-env reward finishes inside the block)
+  int32_t quads_per_chunk;  // float4 groups of cells per chunk
+};
+
+cudaError_t launch_move(const ipp_config& cfg, const uint32_t* episodes, const ipp_step_io& io, int32_t t, int do_comm,
+                        int do_move, cudaStream_t s);
+cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, const int32_t* pos_in,
+                              const int32_t* pos_out, const uint8_t* comm, int32_t t, float* reward_rel,
+                              float* reward_abs, double* partials, bool do_own, cudaStream_t s);
+cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const int32_t* pos_out, int32_t t,
+                              cudaStream_t s);
+cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, int32_t* pos_out,
+                         int32_t* gt_params, cudaStream_t s);
+
+// single-map helpers used by the facade entry points (device pointers)
+cudaError_t launch_update_cells(const ipp_config& cfg, float* x, const float* y, int y_is_scalar, float y_scalar,
+                                int64_t n, float* out, cudaStream_t s);
+cudaError_t launch_entropy(const ipp_config& cfg, float* p, int64_t n, float* out, cudaStream_t s);
+cudaError_t launch_utility_reward(const ipp_config& cfg, const float* last, const float* next, int64_t n,
+                                  double* out2, cudaStream_t s);
+
+}  // namespace ipp

@@ -1,0 +1,167 @@
+"""BatchedIPPEnv — B independent multi-UAV IPP environments stepped by the CUDA kernels.
+
+Host-side mirror of the reference's per-episode objects for a whole batch:
+``Mapping`` + ``Simulation`` (mapping/mappings.py:19-30), the ``Agent`` list
+(missions/episode_generator.py:90-102) and the per-timestep sequence of
+``COMAWrapper.build_observations`` / ``.steps`` (coma_wrapper.py:37-183), with the state kept
+resident in HBM between steps.  PyTorch is only the allocator / stream provider here; every
+computation goes through the C ABI (include/ipp_b200.h).  There is no CPU path: constructing
+the env without a CUDA device or without the compiled library raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+from .geometry import HostTables, make_config
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class BatchedIPPEnv:
+    def __init__(self, params, n_envs, device=None, env_id_base=0):
+        if not torch.cuda.is_available():
+            raise N.IppError("BatchedIPPEnv needs a CUDA device (no CPU fallback exists)")
+        self.lib = N.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.tables = HostTables(params)
+        self.B = int(n_envs)
+        self.A = self.tables.n_agents
+        self.T = self.tables.budget + 1
+        self.env_id_base = int(env_id_base)
+        t = self.tables
+        self.cfg = make_config(t, self.B)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib, None, self.lib.ipp_create(C.byref(self.cfg), C.byref(self._h)), "ipp_create")
+        S = t.map_stride
+        dev = self.device
+        self._local = torch.empty((self.B, self.A, S), dtype=torch.float32, device=dev)
+        self._glob = torch.empty((self.B, S), dtype=torch.float32, device=dev)
+        self._gt = torch.empty((self.B, S), dtype=torch.uint8, device=dev)
+        self.episodes = torch.zeros((self.B,), dtype=torch.int32, device=dev)  # bit pattern = uint32
+        self.positions = torch.zeros((self.T + 1, self.B, self.A, 3), dtype=torch.int32, device=dev)
+        self.actions = torch.zeros((self.B, self.A), dtype=torch.int32, device=dev)
+        self.masks = torch.zeros((self.B, self.A), dtype=torch.uint8, device=dev)
+        self.comm = torch.zeros((self.B, self.A), dtype=torch.uint8, device=dev)
+        self.reward_rel = torch.zeros((self.B,), dtype=torch.float32, device=dev)
+        self.reward_abs = torch.zeros((self.B,), dtype=torch.float32, device=dev)
+        self.stuck = torch.zeros((self.B,), dtype=torch.uint8, device=dev)
+        self._state = N.IppState(_ptr(self._local), _ptr(self._glob), _ptr(self._gt), _ptr(self.episodes))
+        self.t = 0
+        self._observed = False
+
+    # ---- views in the reference's array convention: [.., gx, gy], first axis = world x ----------
+    def _view(self, flat):
+        t = self.tables
+        return flat[..., : t.n_cells].unflatten(-1, (t.gx, t.gy))
+
+    @property
+    def local_maps(self):
+        return self._view(self._local)
+
+    @property
+    def global_map(self):
+        return self._view(self._glob)
+
+    @property
+    def ground_truth(self):
+        return self._view(self._gt)
+
+    @property
+    def pos(self):
+        return self.positions[self.t]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if self._h:
+            self.lib.ipp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- episode reset ------------------------------------------------------------------------
+    def reset(self, episodes=None):
+        """Start episode ``episodes[b]`` in env b (default: global env index + 1)."""
+        if episodes is None:
+            ep = torch.arange(self.B, dtype=torch.int64) + (self.env_id_base + 1)
+        else:
+            ep = torch.as_tensor(episodes, dtype=torch.int64).reshape(self.B)
+        ep32 = torch.where(ep >= 2**31, ep - 2**32, ep).to(torch.int32)
+        self.episodes.copy_(ep32, non_blocking=True)
+        self.t = 0
+        self._observed = False
+        rc = self.lib.ipp_reset(self._h, C.byref(self._state), _ptr(self.positions[0]), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_reset")
+
+    def _io(self, actions, probs, greedy):
+        io = N.IppStepIO()
+        io.pos_in = _ptr(self.positions[self.t])
+        io.pos_out = _ptr(self.positions[self.t + 1])
+        io.actions_in = _ptr(actions)
+        io.probs_in = _ptr(probs)
+        io.greedy = 1 if greedy else 0
+        io.actions_out = _ptr(self.actions)
+        io.mask_out = _ptr(self.masks)
+        io.comm_out = _ptr(self.comm)
+        io.reward_rel = _ptr(self.reward_rel)
+        io.reward_abs = _ptr(self.reward_abs)
+        io.stuck_out = _ptr(self.stuck)
+        return io
+
+    def _prep(self, actions, probs):
+        if actions is not None:
+            actions = torch.as_tensor(actions, device=self.device).to(torch.int32).reshape(self.B, self.A).contiguous()
+        if probs is not None:
+            probs = torch.as_tensor(probs, device=self.device).to(torch.float32).reshape(self.B, self.A, 6).contiguous()
+        return actions, probs
+
+    # ---- one fused timestep -------------------------------------------------------------------
+    def step(self, actions=None, probs=None, greedy=False):
+        """Whole timestep in one pass over the maps.  Returns (reward_rel, reward_abs, done)."""
+        if self.t >= self.T:
+            raise N.IppError("episode finished: call reset()")
+        actions, probs = self._prep(actions, probs)
+        io = self._io(actions, probs, greedy)
+        rc = self.lib.ipp_step(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_step")
+        done = self.t == self.tables.budget  # coma_wrapper.py:163-164
+        self.t += 1
+        return self.reward_rel, self.reward_abs, done
+
+    # ---- the same timestep split around a policy network --------------------------------------
+    def observe(self):
+        """Fuse local + global maps and compute the reward (everything before the actor forward)."""
+        if self.t >= self.T:
+            raise N.IppError("episode finished: call reset()")
+        io = self._io(None, None, False)
+        rc = self.lib.ipp_observe(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_observe")
+        self._observed = True
+        return self.reward_rel, self.reward_abs
+
+    def act(self, actions=None, probs=None, greedy=False):
+        """Masks, action choice, moves and the measurement at the new positions."""
+        if not self._observed:
+            raise N.IppError("act() must follow observe() in the same timestep")
+        actions, probs = self._prep(actions, probs)
+        io = self._io(actions, probs, greedy)
+        rc = self.lib.ipp_act(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_act")
+        self._observed = False
+        done = self.t == self.tables.budget
+        self.t += 1
+        return self.actions, done
+
+    # ---- sizes for the roofline (SURVEY.md section 8d contract figure) --------------------------
+    def algorithmic_bytes_per_env_step(self):
+        t = self.tables
+        return t.n_cells * (2 * 4 * (self.A + 1) + 1)

@@ -1,0 +1,149 @@
+"""Host-side tables for the kernels, evaluated with the reference's own float64 expressions.
+
+The footprint radii and ``floor(position / res)`` sit on floating-point knife edges
+(``res = 0.9999999999999998`` for the synthetic 50x50 grid; ``170.99999999999997 -> 170`` for
+the default camera at 15 m), so they are never recomputed on the device:
+this module evaluates exactly what the reference evaluates and ships integers.
+
+Reference: mapping/grid_maps.py:16-66, sensors/cameras.py:31-79, agent/state_space.py:10-21,
+sensors/models/sensor_models.py:13-22, mapping/mappings.py:109-124,
+agent/communication_log.py:39-58 (paths relative to marl_framework/).
+"""
+import math
+
+import numpy as np
+
+from . import _native as N
+
+NOISE_BY_ALTITUDE = {5: 0.01, 10: 0.265, 15: 0.375}  # sensors/models/sensor_models.py:13-22
+
+
+class HostTables:
+    def __init__(self, params):
+        env = params["environment"]
+        sen = params["sensor"]
+        con = params["experiment"]["constraints"]
+        self.params = params
+        self.seed = int(env["seed"])
+        self.x_dim_m = int(env["x_dim"])
+        self.y_dim_m = int(env["y_dim"])
+        self.spacing = int(con["spacing"])
+        self.min_altitude = int(con["min_altitude"])
+        self.max_altitude = int(con["max_altitude"])
+        self.budget = int(con["budget"])
+        self.n_actions = int(con["num_actions"])
+        if self.n_actions != 6:
+            raise ValueError("only the 6-action space (params.yaml default) is implemented on the GPU path")
+        self.n_agents = int(params["experiment"]["missions"]["n_agents"])
+        self.prior = float(params["mapping"]["prior"])
+        self.comm_range = float(params["experiment"]["uav"]["communication_range"])
+        self.failure_rate = float(params["experiment"]["uav"]["failure_rate"])
+        ax = sen["field_of_view"]["angle_x"]
+        ay = sen["field_of_view"]["angle_y"]
+        # grid_maps.py:52-66
+        self.res_x = (2 * self.min_altitude * math.tan(math.radians(ax) * 0.5)) / sen["pixel"]["number_x"]
+        self.res_y = (2 * self.min_altitude * math.tan(math.radians(ay) * 0.5)) / sen["pixel"]["number_y"]
+        # grid_maps.py:29-32,46-49
+        self.gx = int(self.x_dim_m / self.res_x)
+        self.gy = int(self.y_dim_m / self.res_y)
+        # state_space.py:16-18
+        self.px = self.x_dim_m // self.spacing + 1
+        self.py = self.y_dim_m // self.spacing + 1
+        self.n_alt = (self.max_altitude - self.min_altitude) // self.spacing + 1
+        self.altitudes = [self.min_altitude + i * self.spacing for i in range(self.n_alt)]
+        if self.n_alt > N.MAX_ALT or max(self.px, self.py) > N.MAX_LATTICE or self.n_agents > N.MAX_AGENTS:
+            raise ValueError("configuration exceeds the compiled table sizes")
+        if self.min_altitude % self.spacing != 0:
+            raise ValueError("min_altitude must be a multiple of spacing")
+
+        # cameras.py:62-67: radius per altitude
+        self.radius_x = np.zeros(self.n_alt, np.int32)
+        self.radius_y = np.zeros(self.n_alt, np.int32)
+        for i, z in enumerate(self.altitudes):
+            x_range_m = 2 * z * np.tan(0.5 * np.radians(ax))
+            y_range_m = 2 * z * np.tan(0.5 * np.radians(ay))
+            cells = np.array([np.floor(x_range_m / self.res_x), np.floor(y_range_m / self.res_y)])
+            r = np.floor(0.5 * cells)
+            self.radius_x[i] = int(r[0])
+            self.radius_y[i] = int(r[1])
+        # cameras.py:66: floor(position[:2] / res_x) — the x resolution for both axes
+        self.cell_x = np.array(
+            [int(np.floor(np.array([i * self.spacing]) / self.res_x)[0]) for i in range(self.px)], np.int32)
+        self.cell_y = np.array(
+            [int(np.floor(np.array([i * self.spacing]) / self.res_x)[0]) for i in range(self.py)], np.int32)
+
+        # mappings.py:112-117: l_y in float32 (measurement is float32), l_p float64; k = exp(l_y - l_p)
+        l_p = np.log(self.prior / (1 - self.prior))
+        self.k_hi = np.zeros(self.n_alt, np.float32)
+        self.k_lo = np.zeros(self.n_alt, np.float32)
+        self.flip_thresh = np.zeros(self.n_alt, np.uint32)
+        self.noise = np.zeros(self.n_alt, np.float64)
+        for i, z in enumerate(self.altitudes):
+            noise = NOISE_BY_ALTITUDE.get(int(z), 0)
+            acc = 1 - noise
+            y_hi = np.float32(np.round(acc, 3))        # simulations.py:47-50
+            y_lo = np.float32(np.round(1 - acc, 3))
+            with np.errstate(divide="ignore"):
+                l_hi = np.log(y_hi / (1 - y_hi))
+                l_lo = np.log(y_lo / (1 - y_lo))
+            self.k_hi[i] = np.float32(np.exp(np.float64(l_hi) - l_p))
+            self.k_lo[i] = np.float32(np.exp(np.float64(l_lo) - l_p))
+            self.flip_thresh[i] = np.uint32(int(np.floor(float(noise) * 4294967296.0)))
+            self.noise[i] = noise
+        half = np.float32(0.5)
+        self.k_out = np.float32(np.exp(np.float64(np.log(half / (1 - half))) - l_p))
+        self.p_min = np.float32(0.0001)   # mappings.py:110-111 evaluated in float32 on the first pass
+        self.p_max = np.float32(0.9999)
+        one = np.float32(1)
+        self.o_min = min(np.float32(0.0001 / 0.9999), self.p_min / (one - self.p_min))
+        self.o_max = max(np.float32(0.9999 / 0.0001), self.p_max / (one - self.p_max))
+
+        # communication_log.py:49-53: 0.001 <= ||dp|| <= range  <=>  0 < d2 <= comm_d2_max (d2 integer m^2)
+        r = self.comm_range
+        d2 = int(np.floor(r * r)) + 2
+        while d2 > 0 and not (np.sqrt(np.float64(d2)) <= r):
+            d2 -= 1
+        self.comm_d2_max = d2 if r >= 0 else -1
+        # r >= failure_rate with r = n / 2^24  <=>  n >= fail_thresh24
+        fr = self.failure_rate
+        n = int(np.ceil(fr * 16777216.0))
+        while n > 0 and (n - 1) / 16777216.0 >= fr:
+            n -= 1
+        while n / 16777216.0 < fr:
+            n += 1
+        self.fail_thresh24 = n
+
+    @property
+    def n_cells(self):
+        return self.gx * self.gy
+
+    @property
+    def map_stride(self):
+        return (self.n_cells + 3) // 4 * 4
+
+
+def make_config(tables, n_envs):
+    """Fill the C struct ipp_config (include/ipp_b200.h) from the host tables."""
+    t = tables
+    c = N.IppConfig()
+    c.gx, c.gy, c.map_stride = t.gx, t.gy, t.map_stride
+    c.px, c.py, c.n_alt = t.px, t.py, t.n_alt
+    c.n_agents, c.n_envs, c.spacing = t.n_agents, int(n_envs), t.spacing
+    c.min_altitude, c.max_altitude = t.min_altitude, t.max_altitude
+    c.x_dim_m, c.y_dim_m, c.budget = t.x_dim_m, t.y_dim_m, t.budget
+    c.seed = t.seed & 0xFFFFFFFF
+    c.comm_d2_max = min(int(t.comm_d2_max), 2**31 - 1)
+    c.fail_thresh24 = int(t.fail_thresh24)
+    c.prior, c.k_out = float(t.prior), float(t.k_out)
+    c.p_min, c.p_max, c.o_min, c.o_max = float(t.p_min), float(t.p_max), float(t.o_min), float(t.o_max)
+    for i in range(t.n_alt):
+        c.radius_x[i] = int(t.radius_x[i])
+        c.radius_y[i] = int(t.radius_y[i])
+        c.k_hi[i] = float(t.k_hi[i])
+        c.k_lo[i] = float(t.k_lo[i])
+        c.flip_thresh[i] = int(t.flip_thresh[i])
+    for i in range(t.px):
+        c.cell_x[i] = int(t.cell_x[i])
+    for i in range(t.py):
+        c.cell_y[i] = int(t.cell_y[i])
+    return c

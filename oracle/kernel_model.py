@@ -295,3 +295,27 @@ class KernelModelEnv:
         self.pos = new_pos
         self.t += 1
         return dict(comm=comm, mask=masks, action=acts, reward_rel=rel, reward_abs=ab)
+
+    # ---- the same timestep split around a policy network (ipp_observe / ipp_act) ----------------
+    def observe(self):
+        """Fuse + reward only; the fused local maps are rounded to float32 here (state in HBM)."""
+        A = self.A
+        comm = self.comm()
+        prev = [self._k_of(self.pos[:, j], j, self.t) for j in range(A)]
+        last = self.glob
+        self.glob = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
+        rel, ab = self._reward(last, self.glob)
+        for i in range(A):
+            passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
+            self.local[:, i] = self._apply(self.local[:, i], passes)
+        return dict(comm=comm, reward_rel=rel, reward_abs=ab)
+
+    def act(self, actions=None):
+        A = self.A
+        new_pos, masks, acts = self._choose_and_move(actions)
+        for i in range(A):
+            inr, k = self._k_of(new_pos[:, i], i, self.t + 1)
+            self.local[:, i] = self._apply(self.local[:, i], [(inr, k, False)])
+        self.pos = new_pos
+        self.t += 1
+        return dict(mask=masks, action=acts)

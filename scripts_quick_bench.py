@@ -1,0 +1,25 @@
+"""Quick kernel timing (development aid; bench.py is the contract benchmark)."""
+import json, sys, time
+import torch
+sys.path.insert(0, "/root/repo")
+from ipp_marl_b200 import BatchedIPPEnv
+params = json.load(open("/root/repo/tests/golden/kats.json"))["synthetic50"]["params"]
+for (B, A) in [(1024, 2), (8192, 2), (8192, 4), (65536, 4)]:
+    params["experiment"]["missions"]["n_agents"] = A
+    env = BatchedIPPEnv(params, B, device="cuda:0")
+    env.reset()
+    for _ in range(15): env.step()
+    torch.cuda.synchronize()
+    n_ep = 10
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for ep in range(n_ep):
+        env.reset()
+        for _ in range(15): env.step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps = n_ep * 15
+    sps = B * steps / (ms * 1e-3)
+    byt = env.algorithmic_bytes_per_env_step()
+    print(f"B={B} A={A}: {ms/steps*1e3:.1f} us/step  {sps:.3e} env-steps/s  {sps*byt/1e9:.0f} GB/s algorithmic")
+    del env

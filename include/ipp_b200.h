@@ -15,7 +15,7 @@
  *   belief maps   float32 [..., map_stride], cell (x, y) at x * gy + y  — first array axis is
  *                 world x exactly as in the reference (mapping/mappings.py:46-61); map_stride >=
  *                 gx*gy is a multiple of 4 cells so every map starts 16-byte aligned.
- *   ground truth  uint8   [n_envs, map_stride]   (mapping/ground_truths.py:42-56 half-plane field)
+ *   ground truth  uint8   [n_envs, gt_stride]    (mapping/ground_truths.py:42-56 half-plane field)
  *   positions     int32   [n_envs, n_agents, 3]  metres (x, y, z), as agent/agent.py keeps them
  *   episodes      uint32  [n_envs]               episode number of each env (seeds + random streams)
  */
@@ -49,7 +49,9 @@ typedef enum ipp_status {
  */
 typedef struct ipp_config {
   int32_t gx, gy;          /* belief cells per side: mapping/grid_maps.py:16-50                    */
-  int32_t map_stride;      /* cells between consecutive maps, multiple of 4, >= gx*gy             */
+  int32_t map_stride;      /* cells between consecutive float32 maps, multiple of 4, >= gx*gy     */
+  int32_t gt_stride;       /* bytes between consecutive ground-truth maps, multiple of 16, >=      */
+                           /* map_stride (16-byte rows so that TMA bulk copies can stage them)     */
   int32_t px, py, n_alt;   /* agent lattice: agent/state_space.py:16-18                            */
   int32_t n_agents;        /* 1..IPP_MAX_AGENTS                                                    */
   int32_t n_envs;          /* envs owned by this handle (this GPU's shard)                         */
@@ -74,7 +76,7 @@ typedef struct ipp_config {
 typedef struct ipp_state {
   float* local_maps;   /* [n_envs, n_agents, map_stride]  Agent.local_map                          */
   float* global_map;   /* [n_envs, map_stride]            accumulated_map_knowledge                */
-  uint8_t* ground_truth; /* [n_envs, map_stride]          Mapping.simulated_map                    */
+  uint8_t* ground_truth; /* [n_envs, gt_stride]           Mapping.simulated_map                    */
   uint32_t* episodes;  /* [n_envs]                                                                  */
 } ipp_state;
 
@@ -91,7 +93,8 @@ typedef struct ipp_step_io {
   uint8_t* comm_out;        /* [n_envs, n_agents] bit j = agent i received agent j's message       */
   float* reward_rel;        /* [n_envs] 22*rel-0.5 : utils/reward.py:39-41                         */
   float* reward_abs;        /* [n_envs] 10*abs-0.17: utils/reward.py:38                            */
-  uint8_t* stuck_out;       /* [n_envs] 1 if some agent had an all-zero mask (stayed in place)     */
+  uint8_t* stuck_out;       /* [n_envs] bit0: some agent had an all-zero mask and stayed in place;  */
+                            /*          bit1: an injected action would have left the lattice (-> stay) */
 } ipp_step_io;
 
 typedef struct ipp_handle ipp_handle;
@@ -104,6 +107,15 @@ int ipp_version(void);
 /* Validate the config, pick launch geometry, allocate the (small) per-handle scratch. */
 int ipp_create(const ipp_config* cfg, ipp_handle** out);
 int ipp_destroy(ipp_handle* h);
+/* Which implementation of the map kernel ipp_step / ipp_observe launch.  Default: the TMA-staged
+ * persistent kernel when the (G, A) shape fits its shared-memory ring, else the direct-load kernel;
+ * the environment variable IPP_STEP_VARIANT=direct|tma overrides the default at ipp_create.
+ * Both produce bit-identical belief maps. */
+#define IPP_VARIANT_DIRECT 0
+#define IPP_VARIANT_TMA 1
+int ipp_set_step_variant(ipp_handle* h, int32_t variant);
+int ipp_get_step_variant(const ipp_handle* h);
+
 /* Bytes of device scratch held by the handle (reward partials, reset parameters). */
 int64_t ipp_scratch_bytes(const ipp_handle* h);
 
@@ -126,6 +138,14 @@ int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream
  * (mapping/mappings.py:32-78).  t is the timestep index (0..budget).
  */
 int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
+
+/* ipp_step with its two launches selectable (profiling aid: lets bench.py bracket the map kernel
+ * alone with CUDA events).  phases = IPP_PHASE_MOVE | IPP_PHASE_MAPS is exactly ipp_step; the MAPS
+ * phase needs comm_out / pos_out of a preceding MOVE phase of the same timestep. */
+#define IPP_PHASE_MOVE 1
+#define IPP_PHASE_MAPS 2
+int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, int32_t phases,
+                    void* stream);
 
 /* The same timestep split around the policy network: ipp_observe = everything before the actor
  * forward (fuse local + global + reward; io->pos_in only), ipp_act = masks, action choice, move

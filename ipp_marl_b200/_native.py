@@ -12,7 +12,7 @@ N_ACTIONS = 6
 
 class IppConfig(C.Structure):
     _fields_ = [
-        ("gx", C.c_int32), ("gy", C.c_int32), ("map_stride", C.c_int32),
+        ("gx", C.c_int32), ("gy", C.c_int32), ("map_stride", C.c_int32), ("gt_stride", C.c_int32),
         ("px", C.c_int32), ("py", C.c_int32), ("n_alt", C.c_int32),
         ("n_agents", C.c_int32), ("n_envs", C.c_int32), ("spacing", C.c_int32),
         ("min_altitude", C.c_int32), ("max_altitude", C.c_int32),
@@ -45,7 +45,8 @@ class IppStepIO(C.Structure):
 
 EXPORTS = [
     "ipp_status_string", "ipp_last_error", "ipp_version", "ipp_create", "ipp_destroy", "ipp_scratch_bytes",
-    "ipp_reset", "ipp_step", "ipp_observe", "ipp_act", "ipp_project_fov", "ipp_update_cells",
+    "ipp_set_step_variant", "ipp_get_step_variant",
+    "ipp_reset", "ipp_step", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_project_fov", "ipp_update_cells",
     "ipp_shannon_entropy", "ipp_fuse_map", "ipp_utility_reward",
 ]
 
@@ -79,9 +80,12 @@ def load():
     lib.ipp_destroy.argtypes = [vp]
     lib.ipp_scratch_bytes.restype = i64
     lib.ipp_scratch_bytes.argtypes = [vp]
+    lib.ipp_set_step_variant.argtypes = [vp, i32]
+    lib.ipp_get_step_variant.argtypes = [vp]
     lib.ipp_reset.argtypes = [vp, C.POINTER(IppState), vp, vp]
     for name in ("ipp_step", "ipp_observe", "ipp_act"):
         getattr(lib, name).argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp]
+    lib.ipp_step_phases.argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), i32, vp]
     lib.ipp_project_fov.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.ipp_update_cells.argtypes = [vp, vp, vp, i32, i64, vp]
     lib.ipp_shannon_entropy.argtypes = [vp, vp, i64, vp]

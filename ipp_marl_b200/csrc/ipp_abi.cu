@@ -1,5 +1,6 @@
 // C ABI (include/ipp_b200.h): argument validation, launch planning, scratch ownership.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -7,7 +8,10 @@
 
 struct ipp_handle {
   ipp_config cfg;
-  ipp::LaunchPlan plan;
+  ipp::LaunchPlan plan;   // direct-load variant (also used by reset)
+  ipp::TmaPlan tma;       // TMA-staged variant
+  int variant;            // IPP_VARIANT_DIRECT / IPP_VARIANT_TMA
+  int n_sm;
   int device;
   double* partials;     // [n_envs, n_chunks, 2]
   int32_t* gt_params;   // [n_envs, 4]
@@ -32,11 +36,27 @@ int fail_cuda(ipp_handle* h, cudaError_t e, const char* where) {
     if (e_ != cudaSuccess) return fail_cuda(h, e_, #call); \
   } while (0)
 
+cudaError_t launch_maps(ipp_handle* h, const ipp_state* st, const ipp_step_io& io, int32_t t, bool do_own,
+                        cudaStream_t s) {
+  const int32_t* pos_out = do_own ? io.pos_out : io.pos_in;
+  if (h->variant == IPP_VARIANT_TMA) {
+    cudaError_t e = ipp::launch_step_tma(h->cfg, *st, h->tma, h->n_sm, io.pos_in, pos_out, io.comm_out, t,
+                                         io.reward_rel, io.reward_abs, h->partials, do_own, s);
+    if (e != cudaSuccess) return e;
+    if (h->tma.n_chunks > 1)
+      e = ipp::launch_reward_finalize(h->cfg, h->partials, h->tma.n_chunks, io.reward_rel, io.reward_abs, s);
+    return e;
+  }
+  return ipp::launch_step_dense(h->cfg, *st, h->plan, io.pos_in, pos_out, io.comm_out, t, io.reward_rel,
+                                io.reward_abs, h->partials, do_own, s);
+}
+
 int validate(const ipp_config* c) {
   if (c == nullptr) return IPP_ERR_INVALID_ARG;
   if (c->gx <= 0 || c->gy <= 0 || c->n_envs <= 0) return IPP_ERR_INVALID_ARG;
   if ((int64_t)c->gx * c->gy > (1 << 28)) return IPP_ERR_UNSUPPORTED;
   if (c->map_stride < c->gx * c->gy || (c->map_stride & 3) != 0) return IPP_ERR_INVALID_ARG;
+  if (c->gt_stride < c->map_stride || (c->gt_stride & 15) != 0) return IPP_ERR_INVALID_ARG;
   if (c->n_agents < 1 || c->n_agents > IPP_MAX_AGENTS) return IPP_ERR_UNSUPPORTED;
   if (c->n_alt < 1 || c->n_alt > IPP_MAX_ALT) return IPP_ERR_UNSUPPORTED;
   if (c->px < 1 || c->px > IPP_MAX_LATTICE || c->py < 1 || c->py > IPP_MAX_LATTICE) return IPP_ERR_UNSUPPORTED;
@@ -58,7 +78,7 @@ int check_state(const ipp_state* st) {
       st->episodes == nullptr)
     return IPP_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(st->local_maps) & 15) || (reinterpret_cast<uintptr_t>(st->global_map) & 15) ||
-      (reinterpret_cast<uintptr_t>(st->ground_truth) & 3))
+      (reinterpret_cast<uintptr_t>(st->ground_truth) & 15))
     return IPP_ERR_INVALID_ARG;
   return IPP_OK;
 }
@@ -111,7 +131,17 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
   const int32_t n_quads = h->cfg.map_stride >> 2;
   h->plan.quads_per_chunk = 1024;
   h->plan.n_chunks = (n_quads + h->plan.quads_per_chunk - 1) / h->plan.quads_per_chunk;
-  const size_t pb = sizeof(double) * 2 * (size_t)cfg->n_envs * h->plan.n_chunks;
+  int smem_optin = 0;
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
+  h->tma = ipp::plan_tma(h->cfg, smem_optin);
+  h->variant = h->tma.ok ? IPP_VARIANT_TMA : IPP_VARIANT_DIRECT;
+  if (const char* v = getenv("IPP_STEP_VARIANT")) {
+    if (strcmp(v, "direct") == 0) h->variant = IPP_VARIANT_DIRECT;
+    if (strcmp(v, "tma") == 0 && h->tma.ok) h->variant = IPP_VARIANT_TMA;
+  }
+  const int32_t max_chunks = h->tma.ok && h->tma.n_chunks > h->plan.n_chunks ? h->tma.n_chunks : h->plan.n_chunks;
+  const size_t pb = sizeof(double) * 2 * (size_t)cfg->n_envs * max_chunks;
   const size_t gb = sizeof(int32_t) * 4 * (size_t)cfg->n_envs;
   const size_t cb = (size_t)cfg->n_envs * cfg->n_agents;
   if (cudaMalloc(&h->partials, pb) != cudaSuccess || cudaMalloc(&h->gt_params, gb) != cudaSuccess ||
@@ -134,6 +164,22 @@ int ipp_destroy(ipp_handle* h) {
   return IPP_OK;
 }
 
+int ipp_set_step_variant(ipp_handle* h, int32_t variant) {
+  if (h == nullptr) return IPP_ERR_INVALID_ARG;
+  if (variant == IPP_VARIANT_DIRECT) {
+    h->variant = variant;
+    return IPP_OK;
+  }
+  if (variant == IPP_VARIANT_TMA) {
+    if (!h->tma.ok) return IPP_ERR_UNSUPPORTED;
+    h->variant = variant;
+    return IPP_OK;
+  }
+  return IPP_ERR_INVALID_ARG;
+}
+
+int ipp_get_step_variant(const ipp_handle* h) { return h != nullptr ? h->variant : IPP_ERR_INVALID_ARG; }
+
 int64_t ipp_scratch_bytes(const ipp_handle* h) { return h != nullptr ? h->scratch_bytes + (int64_t)h->fbuf_bytes : 0; }
 
 int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream) {
@@ -144,7 +190,8 @@ int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream
   return IPP_OK;
 }
 
-int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, int32_t phases,
+                    void* stream) {
   if (h == nullptr || io == nullptr || io->pos_in == nullptr || io->pos_out == nullptr || io->pos_in == io->pos_out)
     return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
@@ -153,10 +200,13 @@ int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* i
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 1, s));
-  IPP_CUDA(h, ipp::launch_step_dense(h->cfg, *st, h->plan, io2.pos_in, io2.pos_out, io2.comm_out, t, io2.reward_rel,
-                                     io2.reward_abs, h->partials, true, s));
+  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 1, s));
+  if (phases & IPP_PHASE_MAPS) IPP_CUDA(h, launch_maps(h, st, io2, t, true, s));
   return IPP_OK;
+}
+
+int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+  return ipp_step_phases(h, st, t, io, IPP_PHASE_MOVE | IPP_PHASE_MAPS, stream);
 }
 
 int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
@@ -168,8 +218,7 @@ int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
   IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 0, s));
-  IPP_CUDA(h, ipp::launch_step_dense(h->cfg, *st, h->plan, io2.pos_in, io2.pos_in, io2.comm_out, t, io2.reward_rel,
-                                     io2.reward_abs, h->partials, false, s));
+  IPP_CUDA(h, launch_maps(h, st, io2, t, false, s));
   return IPP_OK;
 }
 

@@ -50,8 +50,9 @@ __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { r
 __device__ __forceinline__ Meas make_meas(const ipp_config& c, const int32_t* pos, uint32_t episode, uint32_t agent,
                                           uint32_t index) {
   Meas m;
-  const int32_t ix = pos[0] / c.spacing, iy = pos[1] / c.spacing;
-  const int32_t iz = pos[2] / c.spacing - c.min_altitude / c.spacing;
+  // clamped so that a corrupt position can never index outside the tables
+  const int32_t ix = clampi(pos[0] / c.spacing, 0, c.px - 1), iy = clampi(pos[1] / c.spacing, 0, c.py - 1);
+  const int32_t iz = clampi(pos[2] / c.spacing - c.min_altitude / c.spacing, 0, c.n_alt - 1);
   const int32_t cx = c.cell_x[ix], cy = c.cell_y[iy];
   const int32_t rx = c.radius_x[iz], ry = c.radius_y[iz];
   m.xl = clampi(cx - rx, 0, c.gx - 1);

@@ -7,7 +7,7 @@
 //   reset_prep / reset_fill   episode reset (MT19937-compatible start positions + ground truth)
 //
 // Arithmetic specification: oracle/kernel_model.py (bit-exact for belief maps).
-#include "ipp_device.cuh"
+#include "ipp_cell.cuh"
 #include "ipp_launch.h"
 
 namespace ipp {
@@ -84,7 +84,14 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ ipp_c
     const int32_t cnt = __popc(m);
     int32_t act = -1;
     if (io.actions_in != nullptr) {
+      // injected action (the reference's policy never emits a masked one): an action that would
+      // leave the lattice is turned into "stay" and flagged, so positions always index the tables
       act = io.actions_in[(int64_t)b * A + a];
+      if (act < -1 || act >= IPP_N_ACTIONS) act = -1;
+      if (act >= 0 && !((bounds_mask(cfg, pos[a]) >> act) & 1u)) {
+        act = -1;
+        stuck |= 2u;
+      }
     } else if (cnt > 0) {
       const uint32_t key = stream_key(cfg.seed, ep, a, (uint32_t)t, PURPOSE_ACTION);
       const float u = (float)(cell_hash(key, 0u) >> 8) * (1.0f / 16777216.0f);
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ ipp_c
         act = kth_set_bit(m, min((int32_t)(u * (float)cnt), cnt - 1));
       }
     }
-    if (cnt == 0) stuck = 1;  // the reference raises here; we stay in place and flag
+    if (cnt == 0) stuck |= 1u;  // the reference raises here; we stay in place and flag
     int32_t off[3] = {0, 0, 0};
     if (act == 0) off[2] = cfg.spacing;
     if (act == 1) off[0] = -cfg.spacing;
@@ -137,43 +144,28 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ ipp_c
 }
 
 // =================================================================================================
-// dense per-cell pass: mapping/mappings.py:80-124 (fuse local/global), :32-78 (own update),
-// utils/reward.py:68-82 + utils/state.py:53-76,118-121 (reward sums)
+// dense per-cell pass, direct-load variant (per-quad arithmetic: ipp_cell.cuh)
+// one block per (env, chunk); each thread owns quads tid, tid+256, ... of the chunk in all A+1 maps
 // =================================================================================================
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, off);
-  return v;
-}
-
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(STEP_THREADS)
     step_dense_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const int32_t* __restrict__ pos_in,
                       const int32_t* __restrict__ pos_out, const uint8_t* __restrict__ comm, const int32_t t,
                       float* __restrict__ reward_rel, float* __restrict__ reward_abs, double* __restrict__ partials,
                       const int32_t n_chunks, const int32_t quads_per_chunk) {
-  const int32_t b = blockIdx.y;
-  const int32_t chunk = blockIdx.x;
+  const int32_t b = blockIdx.x / n_chunks;
+  const int32_t chunk = blockIdx.x - b * n_chunks;
   const int32_t tid = threadIdx.x;
-  __shared__ Meas s_prev[A];
-  __shared__ Meas s_new[A];
-  __shared__ uint32_t s_comm[A];
+  __shared__ EnvMeta<A> s_meta;
   __shared__ double s_red[2][STEP_THREADS / 32];
 
-  const uint32_t ep = st.episodes[b];
-  if (tid < A) {
-    s_prev[tid] = make_meas(cfg, pos_in + ((int64_t)b * A + tid) * 3, ep, tid, (uint32_t)t);
-    if (DO_OWN) s_new[tid] = make_meas(cfg, pos_out + ((int64_t)b * A + tid) * 3, ep, tid, (uint32_t)t + 1u);
-    s_comm[tid] = (uint32_t)comm[(int64_t)b * A + tid] & ~(1u << tid);  // own measurement already used
-  }
+  load_env_meta<A>(cfg, &s_meta, tid, b, st.episodes[b], pos_in, pos_out, comm, t, DO_OWN);
   __syncthreads();
 
   const int32_t n_cells = cfg.gx * cfg.gy;
   const int32_t n_quads = (n_cells + 3) >> 2;
   const int64_t stride = cfg.map_stride;
-  const bool kout_one = (cfg.k_out == 1.0f);
-  const float o_min = cfg.o_min, o_max = cfg.o_max, k_out = cfg.k_out;
-  const uint8_t* gt_b = st.ground_truth + (int64_t)b * stride;
+  const uint8_t* gt_b = st.ground_truth + (int64_t)b * cfg.gt_stride;
   float* glob_b = st.global_map + (int64_t)b * stride;
   float* loc_b = st.local_maps + (int64_t)b * A * stride;
 
@@ -181,96 +173,20 @@ __global__ void __launch_bounds__(STEP_THREADS)
   const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
   for (int32_t q = chunk * quads_per_chunk + tid; q < q_end; q += STEP_THREADS) {
     const int32_t c0 = q << 2;
-    int32_t xs[4], ys[4];
+    QuadCtx<A> qc;
+    make_quad_ctx<A>(cfg, s_meta, c0, *reinterpret_cast<const uint32_t*>(gt_b + c0), n_cells, qc);
     {
-      int32_t x = c0 / cfg.gy, y = c0 - x * cfg.gy;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        xs[c] = x;
-        ys[c] = y;
-        if (++y == cfg.gy) { y = 0; ++x; }
-      }
-    }
-    const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt_b + c0);
-    // multipliers of the A communicated (previous) measurements at these 4 cells
-    float kprev[A][4];
-    uint32_t in_prev = 0;  // bit (j*4+c): cell c inside rect of agent j's communicated measurement
-#pragma unroll
-    for (int j = 0; j < A; ++j) {
-      const Meas m = s_prev[j];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float k = k_out;
-        if (c0 + c < n_cells && in_rect(m, xs[c], ys[c])) {
-          k = meas_k(m, (uint32_t)(c0 + c), (g4 >> (8 * c)) & 0xFFu);
-          in_prev |= 1u << (j * 4 + c);
-        }
-        kprev[j][c] = k;
-      }
-    }
-
-    // ---- global map: fuse every agent's communicated measurement, accumulate the reward sums ----
-    {
-      float4 p4 = *reinterpret_cast<const float4*>(glob_b + c0);
+      const float4 p4 = *reinterpret_cast<const float4*>(glob_b + c0);
       float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c0 + c >= n_cells) continue;
-        const float p = pv[c];
-        const float pc = clamp_p(cfg, p);
-        const bool touched = ((in_prev >> c) & 0x11111111u) != 0u || !kout_one;
-        float pn = pc;
-        if (touched) {
-          float o = to_odds(pc);
-#pragma unroll
-          for (int j = 0; j < A; ++j) o = odds_pass(o, kprev[j][c], o_min, o_max);
-          pn = from_odds(o);
-        }
-        const float hl = shannon(cfg, p);
-        const float hn = touched ? shannon(cfg, pn) : hl;
-        const float w = weight_of(pn);
-        s1 += (double)(w * (hl - hn));
-        s2 += (double)(w * hl);
-        pv[c] = pn;
-      }
+      update_global_quad<A>(cfg, qc, pv, s1, s2);
       *reinterpret_cast<float4*>(glob_b + c0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
     }
-
-    // ---- local maps: fuse the received peers' measurements, then the own new measurement ----
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       float* lp = loc_b + (int64_t)i * stride + c0;
-      float4 p4 = *reinterpret_cast<const float4*>(lp);
+      const float4 p4 = *reinterpret_cast<const float4*>(lp);
       float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-      const uint32_t en = s_comm[i];
-      const bool any_fuse = en != 0u;
-      uint32_t en4 = 0;  // enabled-peer bits replicated over the 4 cells
-#pragma unroll
-      for (int j = 0; j < A; ++j)
-        if ((en >> j) & 1u) en4 |= 0xFu << (j * 4);
-      Meas mn;
-      if (DO_OWN) mn = s_new[i];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c0 + c >= n_cells) continue;
-        const float p = pv[c];
-        bool own_in = false;
-        if (DO_OWN) own_in = in_rect(mn, xs[c], ys[c]);
-        const bool touched = (((in_prev & en4) >> c) & 0x11111111u) != 0u || (any_fuse && !kout_one) || own_in;
-        const bool clamped = any_fuse || own_in;
-        const float pc = clamp_p(cfg, p);
-        float out = clamped ? pc : p;
-        if (touched) {
-          float o = to_odds(pc);
-#pragma unroll
-          for (int j = 0; j < A; ++j)
-            if ((en >> j) & 1u) o = odds_pass(o, kprev[j][c], o_min, o_max);
-          if (DO_OWN && own_in)
-            o = odds_pass(o, meas_k(mn, (uint32_t)(c0 + c), (g4 >> (8 * c)) & 0xFFu), o_min, o_max);
-          out = from_odds(o);
-        }
-        pv[c] = out;
-      }
+      update_local_quad<A, DO_OWN>(cfg, s_meta, qc, i, pv);
       *reinterpret_cast<float4*>(lp) = make_float4(pv[0], pv[1], pv[2], pv[3]);
     }
   }
@@ -291,8 +207,7 @@ __global__ void __launch_bounds__(STEP_THREADS)
       t2 += s_red[1][w];
     }
     if (n_chunks == 1) {
-      if (reward_rel != nullptr) reward_rel[b] = (float)(22.0 * (t1 / t2) - 0.5);
-      if (reward_abs != nullptr) reward_abs[b] = (float)(10.0 * (t1 / (double)n_cells) - 0.17);
+      write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
     } else {
       partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
       partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
@@ -331,7 +246,7 @@ __global__ void __launch_bounds__(256) own_update_kernel(const __grid_constant__
   if (w <= 0 || h <= 0) return;
   const int64_t stride = cfg.map_stride;
   float* lp = st.local_maps + ((int64_t)b * A + a) * stride;
-  const uint8_t* gt = st.ground_truth + (int64_t)b * stride;
+  const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
   for (int32_t idx = threadIdx.x; idx < w * h; idx += blockDim.x) {
     const int32_t x = m.xl + idx / w, y = m.yu + idx % w;
     const int32_t cell = x * cfg.gy + y;
@@ -436,8 +351,8 @@ __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__
 template <int A>
 __global__ void __launch_bounds__(STEP_THREADS)
     reset_fill_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const int32_t* __restrict__ pos,
-                      const int32_t* __restrict__ gt_params, const int32_t quads_per_chunk) {
-  const int32_t b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+                      const int32_t* __restrict__ gt_params, const int32_t n_chunks, const int32_t quads_per_chunk) {
+  const int32_t b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks, tid = threadIdx.x;
   __shared__ Meas s_m[A];
   const uint32_t ep = st.episodes[b];
   if (tid < A) s_m[tid] = make_meas(cfg, pos + ((int64_t)b * A + tid) * 3, ep, tid, 0u);
@@ -465,7 +380,7 @@ __global__ void __launch_bounds__(STEP_THREADS)
         if (++y == cfg.gy) { y = 0; ++x; }
       }
     }
-    *reinterpret_cast<uint32_t*>(st.ground_truth + (int64_t)b * stride + c0) = g4;
+    *reinterpret_cast<uint32_t*>(st.ground_truth + (int64_t)b * cfg.gt_stride + c0) = g4;
     *reinterpret_cast<float4*>(st.global_map + (int64_t)b * stride + c0) = make_float4(prior, prior, prior, prior);
 #pragma unroll
     for (int i = 0; i < A; ++i) {
@@ -511,7 +426,7 @@ cudaError_t launch_move(const ipp_config& cfg, const uint32_t* episodes, const i
 cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, const int32_t* pos_in,
                               const int32_t* pos_out, const uint8_t* comm, int32_t t, float* reward_rel,
                               float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
-  const dim3 grid(plan.n_chunks, cfg.n_envs);
+  const dim3 grid((unsigned)plan.n_chunks * (unsigned)cfg.n_envs);
   if (do_own) {
     IPP_DISPATCH_A(cfg.n_agents, (step_dense_kernel<kA, true><<<grid, STEP_THREADS, 0, s>>>(
                                      cfg, st, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials, plan.n_chunks,
@@ -523,13 +438,16 @@ cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const 
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (plan.n_chunks > 1) {
-    const int threads = 128;
-    reward_finalize_kernel<<<(cfg.n_envs + threads - 1) / threads, threads, 0, s>>>(
-        partials, cfg.n_envs, plan.n_chunks, cfg.gx * cfg.gy, reward_rel, reward_abs);
-    e = cudaGetLastError();
-  }
+  if (plan.n_chunks > 1) e = launch_reward_finalize(cfg, partials, plan.n_chunks, reward_rel, reward_abs, s);
   return e;
+}
+
+cudaError_t launch_reward_finalize(const ipp_config& cfg, const double* partials, int32_t n_chunks, float* reward_rel,
+                                   float* reward_abs, cudaStream_t s) {
+  const int threads = 128;
+  reward_finalize_kernel<<<(cfg.n_envs + threads - 1) / threads, threads, 0, s>>>(
+      partials, cfg.n_envs, n_chunks, cfg.gx * cfg.gy, reward_rel, reward_abs);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const int32_t* pos_out, int32_t t,
@@ -545,9 +463,9 @@ cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const Launc
   reset_prep_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(cfg, st.episodes, pos_out, gt_params);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const dim3 grid(plan.n_chunks, cfg.n_envs);
-  IPP_DISPATCH_A(cfg.n_agents, (reset_fill_kernel<kA><<<grid, STEP_THREADS, 0, s>>>(cfg, st, pos_out, gt_params,
-                                                                                   plan.quads_per_chunk)));
+  const dim3 grid((unsigned)plan.n_chunks * (unsigned)cfg.n_envs);
+  IPP_DISPATCH_A(cfg.n_agents, (reset_fill_kernel<kA><<<grid, STEP_THREADS, 0, s>>>(
+                                   cfg, st, pos_out, gt_params, plan.n_chunks, plan.quads_per_chunk)));
   return cudaGetLastError();
 }
 

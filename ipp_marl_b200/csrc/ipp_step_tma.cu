@@ -1,0 +1,289 @@
+// TMA-staged, warp-specialised, persistent variant of the dense step kernel (sm_100a).
+//
+// One CTA per SM walks the (env, chunk) work items with a 4-stage shared-memory ring:
+//   producer warp : per item, derives the env's footprints / noise keys (EnvMeta) and issues
+//                   cp.async.bulk (TMA 1-D bulk copies, SASS UBLKCP) of the env's global map, its A local
+//                   maps and its ground-truth bytes into the stage; completion is signalled on an
+//                   mbarrier (expect_tx / complete_tx).
+//   20 consumer warps : update the maps in place in shared memory (ipp_cell.cuh), reduce the two
+//                   reward sums (warp shuffles + one named barrier), then one thread writes the stage
+//                   back with cp.async.bulk shared->global and releases the stage once the bulk
+//                   engine has finished reading it.
+// HBM traffic is exactly one read + one write of every belief map and one read of the ground truth;
+// all global addressing is done by the TMA unit, so the SM issue slots go to the map arithmetic.
+#include "ipp_cell.cuh"
+#include "ipp_launch.h"
+
+namespace ipp {
+
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+}  // namespace ptx
+
+template <int A>
+struct StageMeta {
+  EnvMeta<A> env;
+  int32_t b, chunk, nq, pad;
+};
+
+template <int A, bool DO_OWN>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+    step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const int32_t* __restrict__ pos_in,
+                    const int32_t* __restrict__ pos_out, const uint8_t* __restrict__ comm, const int32_t t,
+                    float* __restrict__ reward_rel, float* __restrict__ reward_abs, double* __restrict__ partials,
+                    const int32_t n_chunks, const int32_t qpc, const int32_t n_items, const int32_t stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NW = TMA_CONSUMERS / 32;
+  unsigned char* stages = smem;
+  StageMeta<A>* meta = reinterpret_cast<StageMeta<A>*>(smem + (size_t)TMA_STAGES * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + TMA_STAGES);  // full[STAGES], empty[STAGES]
+  double* red = reinterpret_cast<double*>(bars + 2 * TMA_STAGES);   // [2 parities][2 sums][NW]
+
+  const int32_t tid = threadIdx.x;
+  const int32_t n_cells = cfg.gx * cfg.gy;
+  const int32_t n_quads = (n_cells + 3) >> 2;
+  const int64_t stride = cfg.map_stride;
+
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars[s]), 1);               // full: producer's arrive.expect_tx
+      ptx::mbar_init(ptx::smem_u32(&bars[TMA_STAGES + s]), 1);  // empty: consumer thread 0
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (tid >= TMA_CONSUMERS) {
+    // ------------------------------------------------------------------ producer warp
+    const int lane = tid - TMA_CONSUMERS;
+    int32_t k = 0;
+    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const int s = k % TMA_STAGES;
+      const uint32_t ph = (uint32_t)(k / TMA_STAGES) & 1u;
+      ptx::mbar_wait(ptx::smem_u32(&bars[TMA_STAGES + s]), ph ^ 1u);
+      const int32_t b = item / n_chunks;
+      const int32_t chunk = item - b * n_chunks;
+      const int32_t nq = min(qpc, n_quads - chunk * qpc);
+      load_env_meta<A>(cfg, &meta[s].env, lane, b, st.episodes[b], pos_in, pos_out, comm, t, DO_OWN);
+      if (lane == 0) {
+        meta[s].b = b;
+        meta[s].chunk = chunk;
+        meta[s].nq = nq;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t full = ptx::smem_u32(&bars[s]);
+        const uint32_t map_bytes = (uint32_t)nq * 16u;
+        const uint32_t gt_bytes = ((uint32_t)nq * 4u + 15u) & ~15u;
+        ptx::mbar_arrive_expect_tx(full, map_bytes * (A + 1) + gt_bytes);
+        const uint32_t dst = ptx::smem_u32(stages + (size_t)s * stage_bytes);
+        const int64_t cell0 = (int64_t)chunk * qpc * 4;
+        ptx::bulk_load(dst, st.global_map + (int64_t)b * stride + cell0, map_bytes, full);
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+          ptx::bulk_load(dst + (uint32_t)(1 + i) * (uint32_t)qpc * 16u,
+                         st.local_maps + ((int64_t)b * A + i) * stride + cell0, map_bytes, full);
+        ptx::bulk_load(dst + (uint32_t)(A + 1) * (uint32_t)qpc * 16u,
+                       st.ground_truth + (int64_t)b * cfg.gt_stride + cell0, gt_bytes, full);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  int32_t k = 0;
+  for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+    const int s = k % TMA_STAGES;
+    const uint32_t ph = (uint32_t)(k / TMA_STAGES) & 1u;
+    ptx::mbar_wait(ptx::smem_u32(&bars[s]), ph);
+    const StageMeta<A>& sm = meta[s];
+    const int32_t b = sm.b, chunk = sm.chunk, nq = sm.nq;
+    unsigned char* base = stages + (size_t)s * stage_bytes;
+    float4* maps = reinterpret_cast<float4*>(base);
+    const uint32_t* gtw = reinterpret_cast<const uint32_t*>(base + (size_t)(A + 1) * qpc * 16);
+
+    double s1 = 0.0, s2 = 0.0;
+    for (int32_t ql = tid; ql < nq; ql += TMA_CONSUMERS) {
+      const int32_t c0 = (chunk * qpc + ql) << 2;
+      QuadCtx<A> qc;
+      make_quad_ctx<A>(cfg, sm.env, c0, gtw[ql], n_cells, qc);
+      {
+        const float4 p4 = maps[ql];
+        float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+        update_global_quad<A>(cfg, qc, pv, s1, s2);
+        maps[ql] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        float4* mp = maps + (size_t)(1 + i) * qpc + ql;
+        const float4 p4 = *mp;
+        float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+        update_local_quad<A, DO_OWN>(cfg, sm.env, qc, i, pv);
+        *mp = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    double* r = red + (size_t)(k & 1) * 2 * NW;
+    if ((tid & 31) == 0) {
+      r[tid >> 5] = s1;
+      r[NW + (tid >> 5)] = s2;
+    }
+    ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
+    ptx::named_bar_sync(1, TMA_CONSUMERS);
+    if (tid == 0) {
+      double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        t1 += r[w];
+        t2 += r[NW + w];
+      }
+      if (n_chunks == 1) {
+        write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
+      } else {
+        partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
+        partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
+      }
+      const uint32_t src = ptx::smem_u32(base);
+      const uint32_t map_bytes = (uint32_t)nq * 16u;
+      const int64_t cell0 = (int64_t)chunk * qpc * 4;
+      ptx::bulk_store(st.global_map + (int64_t)b * stride + cell0, src, map_bytes);
+#pragma unroll
+      for (int i = 0; i < A; ++i)
+        ptx::bulk_store(st.local_maps + ((int64_t)b * A + i) * stride + cell0,
+                        src + (uint32_t)(1 + i) * (uint32_t)qpc * 16u, map_bytes);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<1>();  // the previous item's stores have finished reading their stage
+      if (k > 0) ptx::mbar_arrive(ptx::smem_u32(&bars[TMA_STAGES + (k - 1) % TMA_STAGES]));
+    }
+  }
+  if (tid == 0) {
+    ptx::bulk_wait_read<0>();
+    if (k > 0) ptx::mbar_arrive(ptx::smem_u32(&bars[TMA_STAGES + (k - 1) % TMA_STAGES]));
+    ptx::bulk_wait<0>();  // all writes to global memory complete before the CTA retires
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+static size_t tma_smem_bytes(int A, int stage_bytes) {
+  size_t meta = 0;
+  switch (A) {
+    case 1: meta = sizeof(StageMeta<1>); break;
+    case 2: meta = sizeof(StageMeta<2>); break;
+    case 3: meta = sizeof(StageMeta<3>); break;
+    case 4: meta = sizeof(StageMeta<4>); break;
+    case 5: meta = sizeof(StageMeta<5>); break;
+    case 6: meta = sizeof(StageMeta<6>); break;
+    case 7: meta = sizeof(StageMeta<7>); break;
+    default: meta = sizeof(StageMeta<8>); break;
+  }
+  return (size_t)TMA_STAGES * stage_bytes + TMA_STAGES * meta + 2 * TMA_STAGES * sizeof(uint64_t) +
+         2 * 2 * (TMA_CONSUMERS / 32) * sizeof(double) + 64;
+}
+
+TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
+  TmaPlan p;
+  const int A = cfg.n_agents;
+  const int n_quads = (cfg.gx * cfg.gy + 3) >> 2;
+  const int per_quad = 16 * (A + 1) + 4;
+  const int budget = (max_smem_optin - 4096) / TMA_STAGES;  // bytes per stage
+  int qpc = (budget / per_quad) & ~3;
+  if (qpc > n_quads) qpc = (n_quads + 3) & ~3;
+  p.quads_per_chunk = qpc;
+  p.n_chunks = (n_quads + qpc - 1) / qpc;
+  p.stage_bytes = ((qpc * per_quad) + 127) & ~127;
+  p.smem_bytes = (int)tma_smem_bytes(A, p.stage_bytes);
+  p.ok = qpc >= 4 && p.smem_bytes <= max_smem_optin;
+  return p;
+}
+
+template <int A, bool DO_OWN>
+static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, const TmaPlan& plan, int n_sm,
+                                const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
+                                float* reward_rel, float* reward_abs, double* partials, cudaStream_t s) {
+  auto kern = step_tma_kernel<A, DO_OWN>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_items = cfg.n_envs * plan.n_chunks;
+  const int grid = n_items < n_sm ? n_items : n_sm;
+  kern<<<grid, TMA_THREADS, plan.smem_bytes, s>>>(cfg, st, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
+                                                   plan.n_chunks, plan.quads_per_chunk, n_items, plan.stage_bytes);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_step_tma(const ipp_config& cfg, const ipp_state& st, const TmaPlan& plan, int n_sm,
+                            const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
+                            float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
+#define IPP_TMA_CASE(A_)                                                                                          \
+  case A_:                                                                                                        \
+    return do_own ? launch_tma_t<A_, true>(cfg, st, plan, n_sm, pos_in, pos_out, comm, t, reward_rel, reward_abs, \
+                                           partials, s)                                                           \
+                  : launch_tma_t<A_, false>(cfg, st, plan, n_sm, pos_in, pos_out, comm, t, reward_rel,            \
+                                            reward_abs, partials, s);
+  switch (cfg.n_agents) {
+    IPP_TMA_CASE(1)
+    IPP_TMA_CASE(2)
+    IPP_TMA_CASE(3)
+    IPP_TMA_CASE(4)
+    IPP_TMA_CASE(5)
+    IPP_TMA_CASE(6)
+    IPP_TMA_CASE(7)
+    IPP_TMA_CASE(8)
+    default: return cudaErrorInvalidValue;
+  }
+#undef IPP_TMA_CASE
+}
+
+}  // namespace ipp

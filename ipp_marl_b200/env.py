@@ -40,7 +40,7 @@ class BatchedIPPEnv:
         dev = self.device
         self._local = torch.empty((self.B, self.A, S), dtype=torch.float32, device=dev)
         self._glob = torch.empty((self.B, S), dtype=torch.float32, device=dev)
-        self._gt = torch.empty((self.B, S), dtype=torch.uint8, device=dev)
+        self._gt = torch.zeros((self.B, t.gt_stride), dtype=torch.uint8, device=dev)
         self.episodes = torch.zeros((self.B,), dtype=torch.int32, device=dev)  # bit pattern = uint32
         self.positions = torch.zeros((self.T + 1, self.B, self.A, 3), dtype=torch.int32, device=dev)
         self.actions = torch.zeros((self.B, self.A), dtype=torch.int32, device=dev)
@@ -76,6 +76,18 @@ class BatchedIPPEnv:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    VARIANTS = {"direct": 0, "tma": 1}
+
+    def set_step_variant(self, name):
+        """Pick the map-kernel implementation ("direct" | "tma"); both give identical results."""
+        rc = self.lib.ipp_set_step_variant(self._h, self.VARIANTS[name])
+        N.check(self.lib, self._h, rc, "ipp_set_step_variant(%s)" % name)
+
+    @property
+    def step_variant(self):
+        v = self.lib.ipp_get_step_variant(self._h)
+        return {0: "direct", 1: "tma"}[v]
 
     def close(self):
         if self._h:
@@ -125,14 +137,24 @@ class BatchedIPPEnv:
         return actions, probs
 
     # ---- one fused timestep -------------------------------------------------------------------
-    def step(self, actions=None, probs=None, greedy=False):
-        """Whole timestep in one pass over the maps.  Returns (reward_rel, reward_abs, done)."""
+    def step(self, actions=None, probs=None, greedy=False, _phase_hook=None):
+        """Whole timestep in one pass over the maps.  Returns (reward_rel, reward_abs, done).
+
+        ``_phase_hook(phase)`` (bench.py only) is called between the two launches of the step so
+        that the map kernel can be bracketed with CUDA events."""
         if self.t >= self.T:
             raise N.IppError("episode finished: call reset()")
         actions, probs = self._prep(actions, probs)
         io = self._io(actions, probs, greedy)
-        rc = self.lib.ipp_step(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
-        N.check(self.lib, self._h, rc, "ipp_step")
+        if _phase_hook is None:
+            rc = self.lib.ipp_step(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
+            N.check(self.lib, self._h, rc, "ipp_step")
+        else:
+            for phase in (1, 2):
+                _phase_hook(phase, True)
+                rc = self.lib.ipp_step_phases(self._h, C.byref(self._state), self.t, C.byref(io), phase, self._stream())
+                N.check(self.lib, self._h, rc, "ipp_step_phases")
+                _phase_hook(phase, False)
         done = self.t == self.tables.budget  # coma_wrapper.py:163-164
         self.t += 1
         return self.reward_rel, self.reward_abs, done

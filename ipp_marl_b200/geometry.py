@@ -121,12 +121,16 @@ class HostTables:
     def map_stride(self):
         return (self.n_cells + 3) // 4 * 4
 
+    @property
+    def gt_stride(self):
+        return (self.n_cells + 15) // 16 * 16
+
 
 def make_config(tables, n_envs):
     """Fill the C struct ipp_config (include/ipp_b200.h) from the host tables."""
     t = tables
     c = N.IppConfig()
-    c.gx, c.gy, c.map_stride = t.gx, t.gy, t.map_stride
+    c.gx, c.gy, c.map_stride, c.gt_stride = t.gx, t.gy, t.map_stride, t.gt_stride
     c.px, c.py, c.n_alt = t.px, t.py, t.n_alt
     c.n_agents, c.n_envs, c.spacing = t.n_agents, int(n_envs), t.spacing
     c.min_altitude, c.max_altitude = t.min_altitude, t.max_altitude

@@ -242,7 +242,18 @@ class KernelModelEnv:
                 pick = (m & (order == kth[:, None])).argmax(1)
                 act = np.where(cnt > 0, pick, -1)
             else:
-                act = np.asarray(actions)[:, a].astype(np.int64)
+                act = np.asarray(actions)[:, a].astype(np.int64).copy()
+                act[(act < -1) | (act >= 6)] = -1
+                # an injected action that would leave the lattice becomes "stay" (kernel rule)
+                bounds = np.ones((B, 6), dtype=bool)
+                bounds[:, 0] &= p[:, 2] != geo.max_altitude
+                bounds[:, 5] &= p[:, 2] != geo.min_altitude
+                bounds[:, 2] &= p[:, 1] != 0
+                bounds[:, 3] &= p[:, 1] != geo.y_dim_m
+                bounds[:, 1] &= p[:, 0] != 0
+                bounds[:, 4] &= p[:, 0] != geo.x_dim_m
+                bad = (act >= 0) & ~np.take_along_axis(bounds, np.maximum(act, 0)[:, None], 1)[:, 0]
+                act[bad] = -1
             self.flag_stuck |= cnt == 0
             off = np.zeros((B, 3), dtype=np.int64)
             off[act == 0, 2] = sp

@@ -4,9 +4,13 @@ import torch
 sys.path.insert(0, "/root/repo")
 from ipp_marl_b200 import BatchedIPPEnv
 params = json.load(open("/root/repo/tests/golden/kats.json"))["synthetic50"]["params"]
-for (B, A) in [(1024, 2), (8192, 2), (8192, 4), (65536, 4)]:
+import itertools
+only = sys.argv[1:]
+for (B, A), variant in itertools.product([(1024, 2), (8192, 2), (8192, 4), (65536, 4)], ["direct", "tma"]):
+    if only and variant not in only: continue
     params["experiment"]["missions"]["n_agents"] = A
     env = BatchedIPPEnv(params, B, device="cuda:0")
+    env.set_step_variant(variant)
     env.reset()
     for _ in range(15): env.step()
     torch.cuda.synchronize()
@@ -21,5 +25,5 @@ for (B, A) in [(1024, 2), (8192, 2), (8192, 4), (65536, 4)]:
     steps = n_ep * 15
     sps = B * steps / (ms * 1e-3)
     byt = env.algorithmic_bytes_per_env_step()
-    print(f"B={B} A={A}: {ms/steps*1e3:.1f} us/step  {sps:.3e} env-steps/s  {sps*byt/1e9:.0f} GB/s algorithmic")
+    print(f"{variant:6s} B={B} A={A}: {ms/steps*1e3:.1f} us/step  {sps:.3e} env-steps/s  {sps*byt/1e9:.0f} GB/s algorithmic")
     del env

@@ -17,11 +17,13 @@ RTOL = 1e-5
 ATOL = 1e-5
 
 
-def _env(params, episodes):
+def _env(params, episodes, variant=None):
     import torch
     from ipp_marl_b200 import BatchedIPPEnv
 
     env = BatchedIPPEnv(params, len(episodes), device="cuda:0")
+    if variant is not None:
+        env.set_step_variant(variant)
     env.reset(episodes)
     torch.cuda.synchronize()
     return env
@@ -67,10 +69,11 @@ def test_fused_step_vs_reference_golden(path):
     print("worst", worst)
 
 
-def test_default_g493_vs_reference_golden():
+@pytest.mark.parametrize("variant", ["direct", "tma"])
+def test_default_g493_vs_reference_golden(variant):
     """Reference default config (493x493 belief cells): rewards, moves and the final global map."""
     g = load_episode([p for p in golden_episodes() if "g493" in p][0])
-    env = _env(g["params"], [g["episode"]])
+    env = _env(g["params"], [g["episode"]], variant)
     assert np.array_equal(env.ground_truth[0].cpu().numpy(), g["gt"])
     for t in range(len(g["reward_rel"])):
         rel, ab, _ = env.step()
@@ -83,14 +86,17 @@ def test_default_g493_vs_reference_golden():
     assert s["fail_gate"] == 0, s
 
 
-@pytest.mark.parametrize("tag,n_agents,B", [("synthetic50", 4, 64), ("synthetic50", 2, 64), ("synthetic100", 8, 8)])
-def test_fused_step_bit_exact_vs_kernel_model(tag, n_agents, B):
+@pytest.mark.parametrize("variant", ["direct", "tma"])
+@pytest.mark.parametrize("tag,n_agents,B", [("synthetic50", 4, 64), ("synthetic50", 2, 64), ("synthetic50", 1, 16),
+                                            ("synthetic50", 3, 700), ("synthetic100", 8, 8)])
+def test_fused_step_bit_exact_vs_kernel_model(tag, n_agents, B, variant):
     from oracle import kernel_model as km
 
     params = load_kats()[tag]["params"]
     params["experiment"]["missions"]["n_agents"] = n_agents
     episodes = np.arange(1, B + 1)
-    env = _env(params, episodes)
+    env = _env(params, episodes, variant)
+    assert env.step_variant == variant
     model = km.KernelModelEnv(params, episodes)
     assert np.array_equal(env.ground_truth.cpu().numpy(), model.gt)
     assert np.array_equal(env.positions[0].cpu().numpy(), model.pos)
@@ -109,14 +115,15 @@ def test_fused_step_bit_exact_vs_kernel_model(tag, n_agents, B):
         assert np.array_equal(env.stuck.cpu().numpy().astype(bool), model.flag_stuck) or t < env.T
 
 
-def test_split_observe_act_bit_exact_vs_kernel_model():
+@pytest.mark.parametrize("variant", ["direct", "tma"])
+def test_split_observe_act_bit_exact_vs_kernel_model(variant):
     from oracle import kernel_model as km
 
     params = load_kats()["synthetic50"]["params"]
     params["experiment"]["uav"]["communication_range"] = 15
     params["experiment"]["uav"]["failure_rate"] = 0.25
     episodes = np.arange(3, 35)
-    env = _env(params, episodes)
+    env = _env(params, episodes, variant)
     model = km.KernelModelEnv(params, episodes)
     rng = np.random.RandomState(0)
     for t in range(env.T):
@@ -189,10 +196,10 @@ def test_partition_invariance_and_determinism():
 
     params = load_kats()["synthetic50"]["params"]
     eps = np.arange(1, 257)
-    full = _env(params, eps)
-    lo = _env(params, eps[:100])
-    hi = _env(params, eps[100:])
-    again = _env(params, eps)
+    full = _env(params, eps, "tma")
+    lo = _env(params, eps[:100], "tma")
+    hi = _env(params, eps[100:], "direct")
+    again = _env(params, eps, "direct")
     for t in range(full.T):
         for e in (full, lo, hi, again):
             e.step()

@@ -1,9 +1,9 @@
 """Quick kernel timing (development aid; bench.py is the contract benchmark)."""
 import json, sys, time
 import torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from ipp_marl_b200 import BatchedIPPEnv
-params = json.load(open("/root/repo/tests/golden/kats.json"))["synthetic50"]["params"]
+params = json.load(open(__import__("os").path.join(sys.path[0], "tests/golden/kats.json")))["synthetic50"]["params"]
 import itertools
 only = sys.argv[1:]
 for (B, A), variant in itertools.product([(1024, 2), (8192, 2), (8192, 4), (65536, 4)], ["direct", "tma"]):

@@ -53,7 +53,7 @@ cudaError_t launch_maps(ipp_handle* h, const ipp_state* st, const ipp_step_io& i
 
 int validate(const ipp_config* c) {
   if (c == nullptr) return IPP_ERR_INVALID_ARG;
-  if (c->gx <= 0 || c->gy <= 0 || c->n_envs <= 0) return IPP_ERR_INVALID_ARG;
+  if (c->gx <= 0 || c->gy < 4 || c->n_envs <= 0) return IPP_ERR_INVALID_ARG;  // a quad spans <= 2 rows
   if ((int64_t)c->gx * c->gy > (1 << 28)) return IPP_ERR_UNSUPPORTED;
   if (c->map_stride < c->gx * c->gy || (c->map_stride & 3) != 0) return IPP_ERR_INVALID_ARG;
   if (c->gt_stride < c->map_stride || (c->gt_stride & 15) != 0) return IPP_ERR_INVALID_ARG;

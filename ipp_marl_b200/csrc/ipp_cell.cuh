@@ -1,7 +1,15 @@
 // Per-quad (4 consecutive cells) map arithmetic shared by the direct-load and the TMA-staged step
 // kernels.  Reference: mapping/mappings.py:80-124 (fuse), :32-78 (own update),
 // utils/reward.py:68-82 + utils/state.py:53-76,118-121 (reward terms).
-// Specification: oracle/kernel_model.py::_apply / _reward.
+// Specification: oracle/kernel_model.py::_apply / _reward  (belief maps bit-exact).
+//
+// The kernel is issue-bound, not HBM-bound, unless this code is lean (profiles/): so
+//   * the 4 cells of a quad are processed branch-free, two cells per instruction with the sm_100
+//     packed-float32 FFMA2 / FMUL2 forms (IEEE per lane => still bit-exact);
+//   * divisions use the fast path of div.rn.f32 (MUFU.RCP + 5 FMAs) without its range check —
+//     every operand here is a normal number in [1e-4, 1.1e4] (clamped probabilities / odds);
+//   * a fuse pass whose footprint touches no cell of the whole warp degenerates to a clamp, clamps
+//     are idempotent, so such passes are skipped warp-uniformly and one clamp is applied instead.
 #pragma once
 #include "ipp_device.cuh"
 
@@ -10,9 +18,9 @@ namespace ipp {
 // Everything about one env that the per-cell code needs; lives in shared memory.
 template <int A>
 struct EnvMeta {
-  Meas prev[A];       // communicated measurements (taken at pos_in, index t)
-  Meas next[A];       // measurements after the move (taken at pos_out, index t+1)
-  uint32_t comm[A];   // bit j: agent i fuses agent j's measurement (own bit cleared)
+  Meas prev[A];      // communicated measurements (taken at pos_in, index t)
+  Meas next[A];      // measurements after the move (taken at pos_out, index t+1)
+  uint32_t comm[A];  // bit j: agent i fuses agent j's measurement (own bit cleared)
 };
 
 template <int A>
@@ -29,112 +37,251 @@ __device__ __forceinline__ void load_env_meta(const ipp_config& cfg, EnvMeta<A>*
   }
 }
 
-// Coordinates + multipliers of the communicated measurements at the 4 cells of one quad.
-template <int A>
-struct QuadCtx {
-  float kprev[A][4];
-  uint32_t in_prev;  // bit (j*4+c): cell c lies inside agent j's communicated footprint
-  uint32_t valid;    // bit c: cell c0+c < n_cells
-  int32_t xs[4], ys[4];
-  uint32_t g4;       // 4 ground-truth bytes
-  int32_t c0;
+// ------------------------------------------------------------------------------------------------
+// packed float32 helpers (cells (0,1) in .lo, (2,3) in .hi)
+// ------------------------------------------------------------------------------------------------
+struct F4 {
+  float2 lo, hi;
 };
 
+__device__ __forceinline__ F4 f4_from(const float4 v) { return F4{make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+__device__ __forceinline__ float4 f4_to(const F4 v) { return make_float4(v.lo.x, v.lo.y, v.hi.x, v.hi.y); }
+__device__ __forceinline__ float f4_get(const F4& v, int c) {
+  return c == 0 ? v.lo.x : (c == 1 ? v.lo.y : (c == 2 ? v.hi.x : v.hi.y));
+}
+__device__ __forceinline__ F4 f4_splat(float s) { return F4{make_float2(s, s), make_float2(s, s)}; }
+__device__ __forceinline__ F4 f4_fma(const F4 a, const F4 b, const F4 c) {
+  return F4{__ffma2_rn(a.lo, b.lo, c.lo), __ffma2_rn(a.hi, b.hi, c.hi)};
+}
+__device__ __forceinline__ F4 f4_mul(const F4 a, const F4 b) {
+  return F4{__fmul2_rn(a.lo, b.lo), __fmul2_rn(a.hi, b.hi)};
+}
+__device__ __forceinline__ F4 f4_clamp(const F4 v, float lo, float hi) {
+  return F4{make_float2(fminf(fmaxf(v.lo.x, lo), hi), fminf(fmaxf(v.lo.y, lo), hi)),
+            make_float2(fminf(fmaxf(v.hi.x, lo), hi), fminf(fmaxf(v.hi.y, lo), hi))};
+}
+__device__ __forceinline__ F4 f4_select(uint32_t mask4, const F4 a, const F4 b) {  // bit c set -> a else b
+  return F4{make_float2((mask4 & 1u) ? a.lo.x : b.lo.x, (mask4 & 2u) ? a.lo.y : b.lo.y),
+            make_float2((mask4 & 4u) ? a.hi.x : b.hi.x, (mask4 & 8u) ? a.hi.y : b.hi.y)};
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// a / b, given b and nb = -b: instruction-for-instruction the fast path nvcc emits for div.rn.f32
+// (MUFU.RCP, two Newton steps on the reciprocal/quotient, one remainder correction), i.e. the
+// correctly rounded quotient for normal operands with a normal quotient.
+__device__ __forceinline__ F4 f4_div(const F4 a, const F4 b, const F4 nb) {
+  const F4 one = f4_splat(1.0f);
+  const F4 r0 = F4{make_float2(rcp_approx(b.lo.x), rcp_approx(b.lo.y)),
+                   make_float2(rcp_approx(b.hi.x), rcp_approx(b.hi.y))};
+  const F4 e = f4_fma(nb, r0, one);
+  const F4 r = f4_fma(r0, e, r0);
+  const F4 q = f4_mul(a, r);
+  const F4 rem = f4_fma(nb, q, a);
+  return f4_fma(r, rem, q);
+}
+
+// o = pc / (1 - pc)
+__device__ __forceinline__ F4 f4_to_odds(const F4 pc) {
+  const F4 one = f4_splat(1.0f), mone = f4_splat(-1.0f);
+  const F4 b = f4_fma(pc, mone, one);   // 1 - pc   (single rounding, == __fsub_rn(1, pc))
+  const F4 nb = f4_fma(pc, one, mone);  // pc - 1 == -(1 - pc) exactly
+  return f4_div(pc, b, nb);
+}
+
+// p = o/(1+o) for o < 1, 1 - 1/(1+o) otherwise (symmetric form: keeps the accuracy of 1-p near p = 1)
+__device__ __forceinline__ F4 f4_from_odds(const F4 o) {
+  const F4 one = f4_splat(1.0f), mone = f4_splat(-1.0f);
+  const F4 d = f4_fma(o, one, one);     // 1 + o
+  const F4 nd = f4_fma(o, mone, mone);  // -(1 + o)
+  const F4 num = F4{make_float2(fminf(o.lo.x, 1.0f), fminf(o.lo.y, 1.0f)),
+                    make_float2(fminf(o.hi.x, 1.0f), fminf(o.hi.y, 1.0f))};
+  const F4 q = f4_div(num, d, nd);
+  const F4 alt = f4_fma(q, mone, one);  // 1 - q
+  return F4{make_float2(o.lo.x < 1.0f ? q.lo.x : alt.lo.x, o.lo.y < 1.0f ? q.lo.y : alt.lo.y),
+            make_float2(o.hi.x < 1.0f ? q.hi.x : alt.hi.x, o.hi.y < 1.0f ? q.hi.y : alt.hi.y)};
+}
+
+// ------------------------------------------------------------------------------------------------
+// footprint masks of a quad
+// ------------------------------------------------------------------------------------------------
+// Cells c0..c0+3 lie in row x0 from column y0 (n0 = cells before the row wraps, 1..4) and, when
+// n0 < 4, continue in row x0+1 from column 0 (requires gy >= 4).
+__device__ __forceinline__ uint32_t rect_mask4(const Meas& m, int32_t x0, int32_t y0, int32_t n0) {
+  uint32_t mask = 0;
+  {
+    const int32_t lo = max(m.yu - y0, 0), hi = min(m.yd - y0, n0);
+    if ((uint32_t)(x0 - m.xl) < (uint32_t)(m.xr - m.xl) && hi > lo) mask = (1u << hi) - (1u << lo);
+  }
+  if (n0 < 4) {
+    const int32_t lo = m.yu, hi = min(m.yd, 4 - n0);
+    if ((uint32_t)(x0 + 1 - m.xl) < (uint32_t)(m.xr - m.xl) && hi > lo) mask |= ((1u << hi) - (1u << lo)) << n0;
+  }
+  return mask;
+}
+
+// odds multipliers of measurement m at the 4 cells (k_out where the cell is outside its footprint)
+__device__ __forceinline__ F4 meas_k4(const Meas& m, uint32_t mask4, int32_t c0, uint32_t g4, float k_out) {
+  float k[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const bool wrong = cell_hash(m.key, (uint32_t)(c0 + c)) < m.thresh;
+    const bool seen_one = (((g4 >> (8 * c)) & 0xFFu) != 0u) != wrong;
+    const float kin = seen_one ? m.k_hi : m.k_lo;
+    k[c] = ((mask4 >> c) & 1u) ? kin : k_out;
+  }
+  return F4{make_float2(k[0], k[1]), make_float2(k[2], k[3])};
+}
+
+template <int A>
+struct QuadCtx {
+  F4 kprev[A];       // multipliers of the communicated measurements
+  uint32_t in_prev;  // bit (j*4+c): cell c lies inside agent j's communicated footprint
+  uint32_t wcov;     // bit j: some active lane of this warp has a cell inside footprint j
+  uint32_t valid;    // bit c: cell c0+c < n_cells
+  uint32_t g4;       // 4 ground-truth bytes
+  int32_t c0, x0, y0, n0;
+};
+
+// Must be called with the warp's loop-active lanes converged (it votes over __activemask()).
 template <int A>
 __device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMeta<A>& meta, int32_t c0, uint32_t g4,
                                               int32_t n_cells, QuadCtx<A>& q) {
   q.c0 = c0;
   q.g4 = g4;
-  q.valid = 0;
-  {
-    int32_t x = c0 / cfg.gy, y = c0 - x * cfg.gy;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      q.xs[c] = x;
-      q.ys[c] = y;
-      if (c0 + c < n_cells) q.valid |= 1u << c;
-      if (++y == cfg.gy) { y = 0; ++x; }
-    }
-  }
+  q.x0 = c0 / cfg.gy;
+  q.y0 = c0 - q.x0 * cfg.gy;
+  q.n0 = min(4, cfg.gy - q.y0);
+  const int32_t left = n_cells - c0;
+  q.valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
   q.in_prev = 0;
+  q.wcov = 0;
+  const uint32_t active = __activemask();
+  const bool kout_one = (cfg.k_out == 1.0f);
 #pragma unroll
   for (int j = 0; j < A; ++j) {
     const Meas m = meta.prev[j];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float k = cfg.k_out;
-      if (((q.valid >> c) & 1u) && in_rect(m, q.xs[c], q.ys[c])) {
-        k = meas_k(m, (uint32_t)(c0 + c), (g4 >> (8 * c)) & 0xFFu);
-        q.in_prev |= 1u << (j * 4 + c);
-      }
-      q.kprev[j][c] = k;
-    }
+    const uint32_t mask = rect_mask4(m, q.x0, q.y0, q.n0) & q.valid;
+    q.in_prev |= mask << (j * 4);
+    if (__any_sync(active, mask != 0u) || !kout_one) q.wcov |= 1u << j;
+    q.kprev[j] = f4_splat(cfg.k_out);
+    if (mask != 0u) q.kprev[j] = meas_k4(m, mask, c0, g4, cfg.k_out);
   }
 }
 
-// Global map: fuse every agent's communicated measurement (coma_wrapper.py:93-95) and accumulate
-// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last).
+// ------------------------------------------------------------------------------------------------
+// One belief map of the quad through its chain of passes.
+//   en      : bit j = fuse pass j enabled for this map (warp-uniform)
+//   own     : 4-bit mask of cells inside the own new footprint, k_own their multipliers
+// Semantics per cell (oracle/kernel_model.py::_apply): every enabled fuse pass clamps the odds and
+// multiplies by k_j (k_out outside footprint j); then, inside the own footprint only, clamp and
+// multiply by k_own.  Untouched cells keep p (or clamp(p) if some fuse pass ran) bit for bit.
+// Returns the new probabilities; `touched` receives the 4-bit mask of recomputed cells.
+// ------------------------------------------------------------------------------------------------
 template <int A>
-__device__ __forceinline__ void update_global_quad(const ipp_config& cfg, const QuadCtx<A>& q, float (&pv)[4],
-                                                   double& s1, double& s2) {
+__device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadCtx<A>& q, const F4 p,
+                                              const uint32_t en, const uint32_t own, const F4 k_own, F4& pc_out,
+                                              uint32_t& touched) {
   const bool kout_one = (cfg.k_out == 1.0f);
+  const bool any_fuse = en != 0u;
+  uint32_t t = own;
+#pragma unroll
+  for (int j = 0; j < A; ++j)
+    if ((en >> j) & 1u) t |= (q.in_prev >> (j * 4)) & 0xFu;
+  if (any_fuse && !kout_one) t = 0xFu;
+  t &= q.valid;
+  touched = t;
+  const F4 pc = f4_clamp(p, cfg.p_min, cfg.p_max);
+  pc_out = pc;
+  const F4 fallback = any_fuse ? pc : p;
+  if (t == 0u) return f4_select(q.valid, fallback, p);
+
+  F4 o = f4_to_odds(pc);
+  bool clean = true;  // o is known to lie inside [o_min, o_max] (fresh from pc, or just clamped)
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    if (!((en >> j) & 1u)) continue;  // warp-uniform
+    if ((q.wcov >> j) & 1u) {         // warp-uniform: somebody's cell is inside footprint j
+      if (!clean) o = f4_clamp(o, cfg.o_min, cfg.o_max);
+      o = f4_mul(o, q.kprev[j]);
+      clean = false;
+    }
+    // else: the pass is a pure clamp for the whole warp; clamps are idempotent, so it is absorbed by
+    // the clamp of the next executed pass or by the one below
+  }
+  // A fuse pass skipped AFTER the last executed one still owes its clamp to every cell (warp-uniform).
+  {
+    const uint32_t exec = en & q.wcov;
+    const bool pending = exec != 0u && (en >> (32 - __clz(exec))) != 0u;  // enabled pass above the last executed
+    if (pending) {
+      o = f4_clamp(o, cfg.o_min, cfg.o_max);
+      clean = true;
+    }
+  }
+  if (own != 0u) {  // own update: only the cells inside the own footprint are clamped and multiplied
+    const F4 oc = clean ? o : f4_clamp(o, cfg.o_min, cfg.o_max);
+    o = f4_select(own, f4_mul(oc, k_own), o);
+  }
+  const F4 pn = f4_from_odds(o);
+  return f4_select(t, pn, f4_select(q.valid, fallback, p));
+}
+
+// float32 reward terms of one cell pair set; H in bits (utils/state.py:118-121)
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float entropy_bits(float pc) {  // pc already clamped to [p_min, p_max]
+  const float qc = 1.0f - pc;
+  return -(pc * lg2_approx(pc) + qc * lg2_approx(qc));
+}
+
+// Global map: fuse every agent's communicated measurement (coma_wrapper.py:93-95) and accumulate
+// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last)  (utils/reward.py:68-82).
+template <int A>
+__device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, const QuadCtx<A>& q, const float4 p4,
+                                                     double& s1, double& s2) {
+  F4 pc;
+  uint32_t touched;
+  const F4 pn = update_map_quad<A>(cfg, q, f4_from(p4), (1u << A) - 1u, 0u, f4_splat(1.0f), pc, touched);
+  float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     if (!((q.valid >> c) & 1u)) continue;
-    const float p = pv[c];
-    const float pc = clamp_p(cfg, p);
-    const bool touched = ((q.in_prev >> c) & 0x11111111u) != 0u || !kout_one;
-    float pn = pc;
-    if (touched) {
-      float o = to_odds(pc);
-#pragma unroll
-      for (int j = 0; j < A; ++j) o = odds_pass(o, q.kprev[j][c], cfg.o_min, cfg.o_max);
-      pn = from_odds(o);
-    }
-    const float hl = shannon(cfg, p);
-    const float hn = touched ? shannon(cfg, pn) : hl;
-    const float w = weight_of(pn);
-    s1 += (double)(w * (hl - hn));
-    s2 += (double)(w * hl);
-    pv[c] = pn;
+    const float next = f4_get(pn, c);
+    const float hl = entropy_bits(f4_get(pc, c));
+    float hn = hl;
+    if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl below
+      hn = ((touched >> c) & 1u) ? entropy_bits(fminf(fmaxf(next, cfg.p_min), cfg.p_max)) : hl;
+    const float w = next > 0.501f ? 1.0f : (next < 0.499f ? 0.0f : 0.5f);  // == the float64 compares
+    a1 += w * (hl - hn);
+    a2 += w * hl;
   }
+  s1 += (double)a1;
+  s2 += (double)a2;
+  return f4_to(pn);
 }
 
 // Local map of agent i: fuse the received peers' measurements (agent/agent.py:62-71), then the own
 // measurement at the new position (agent/agent.py:91-94) when DO_OWN.
 template <int A, bool DO_OWN>
-__device__ __forceinline__ void update_local_quad(const ipp_config& cfg, const EnvMeta<A>& meta,
-                                                  const QuadCtx<A>& q, int i, float (&pv)[4]) {
-  const bool kout_one = (cfg.k_out == 1.0f);
-  const uint32_t en = meta.comm[i];
-  const bool any_fuse = en != 0u;
-  uint32_t en4 = 0;  // enabled-peer bits replicated over the 4 cells
-#pragma unroll
-  for (int j = 0; j < A; ++j)
-    if ((en >> j) & 1u) en4 |= 0xFu << (j * 4);
-  Meas mn;
-  if (DO_OWN) mn = meta.next[i];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (!((q.valid >> c) & 1u)) continue;
-    const float p = pv[c];
-    bool own_in = false;
-    if (DO_OWN) own_in = in_rect(mn, q.xs[c], q.ys[c]);
-    const bool touched = (((q.in_prev & en4) >> c) & 0x11111111u) != 0u || (any_fuse && !kout_one) || own_in;
-    const bool clamped = any_fuse || own_in;
-    const float pc = clamp_p(cfg, p);
-    float out = clamped ? pc : p;
-    if (touched) {
-      float o = to_odds(pc);
-#pragma unroll
-      for (int j = 0; j < A; ++j)
-        if ((en >> j) & 1u) o = odds_pass(o, q.kprev[j][c], cfg.o_min, cfg.o_max);
-      if (DO_OWN && own_in)
-        o = odds_pass(o, meas_k(mn, (uint32_t)(q.c0 + c), (q.g4 >> (8 * c)) & 0xFFu), cfg.o_min, cfg.o_max);
-      out = from_odds(o);
-    }
-    pv[c] = out;
+__device__ __forceinline__ float4 update_local_quad(const ipp_config& cfg, const EnvMeta<A>& meta,
+                                                    const QuadCtx<A>& q, int i, const float4 p4) {
+  uint32_t own = 0;
+  F4 k_own = f4_splat(1.0f);
+  if (DO_OWN) {
+    const Meas mn = meta.next[i];
+    own = rect_mask4(mn, q.x0, q.y0, q.n0) & q.valid;
+    if (own != 0u) k_own = meas_k4(mn, own, q.c0, q.g4, 1.0f);
   }
+  F4 pc;
+  uint32_t touched;
+  return f4_to(update_map_quad<A>(cfg, q, f4_from(p4), meta.comm[i], own, k_own, pc, touched));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -175,19 +175,13 @@ __global__ void __launch_bounds__(STEP_THREADS)
     const int32_t c0 = q << 2;
     QuadCtx<A> qc;
     make_quad_ctx<A>(cfg, s_meta, c0, *reinterpret_cast<const uint32_t*>(gt_b + c0), n_cells, qc);
-    {
-      const float4 p4 = *reinterpret_cast<const float4*>(glob_b + c0);
-      float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-      update_global_quad<A>(cfg, qc, pv, s1, s2);
-      *reinterpret_cast<float4*>(glob_b + c0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-    }
+    *reinterpret_cast<float4*>(glob_b + c0) =
+        update_global_quad<A>(cfg, qc, *reinterpret_cast<const float4*>(glob_b + c0), s1, s2);
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       float* lp = loc_b + (int64_t)i * stride + c0;
-      const float4 p4 = *reinterpret_cast<const float4*>(lp);
-      float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-      update_local_quad<A, DO_OWN>(cfg, s_meta, qc, i, pv);
-      *reinterpret_cast<float4*>(lp) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      *reinterpret_cast<float4*>(lp) =
+          update_local_quad<A, DO_OWN>(cfg, s_meta, qc, i, *reinterpret_cast<const float4*>(lp));
     }
   }
 

@@ -155,19 +155,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       const int32_t c0 = (chunk * qpc + ql) << 2;
       QuadCtx<A> qc;
       make_quad_ctx<A>(cfg, sm.env, c0, gtw[ql], n_cells, qc);
-      {
-        const float4 p4 = maps[ql];
-        float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-        update_global_quad<A>(cfg, qc, pv, s1, s2);
-        maps[ql] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-      }
+      maps[ql] = update_global_quad<A>(cfg, qc, maps[ql], s1, s2);
 #pragma unroll
       for (int i = 0; i < A; ++i) {
         float4* mp = maps + (size_t)(1 + i) * qpc + ql;
-        const float4 p4 = *mp;
-        float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-        update_local_quad<A, DO_OWN>(cfg, sm.env, qc, i, pv);
-        *mp = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        *mp = update_local_quad<A, DO_OWN>(cfg, sm.env, qc, i, *mp);
       }
     }
     s1 = warp_sum(s1);

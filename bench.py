@@ -101,7 +101,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -262,7 +262,7 @@ def run_gpu(args):
             ev.record()
             evs.append(ev)
 
-    for i in range(args.steps):
+    for i in range(min(args.steps, 300)):
         if i % EP_LEN == 0:
             env.reset()
         env.step(_phase_hook=hook)
@@ -314,7 +314,8 @@ def run_gpu(args):
             "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "step_dense_kernel<%d,true>" % A, "kernel_ms": kern_ms,
+                         "kernel": "%s<%d,true>" % ("step_tma_kernel" if env.step_variant == "tma" else
+                                                    "step_dense_kernel", A), "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg,
                          "note": "dense contract bytes G^2*(8(A+1)+1) per env-step (SURVEY.md 8d)"},
         }
@@ -328,7 +329,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=150)
+    ap.add_argument("--steps", type=int, default=1500)
     ap.add_argument("--warmup", type=int, default=15)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=8192, help="envs per GPU")

@@ -159,6 +159,12 @@ int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io
  * raw[4], clipped[4] = [yu, yd, xl, xr].  Pure host arithmetic on the config tables. */
 int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, int32_t* clipped);
 
+/* Simulation.get_measurement (mapping/simulations.py:42-65): gt_host [gx*gy] uint8, rect = clipped
+ * footprint [yu, yd, xl, xr], noise stream (episode, agent, index); writes the [xr-xl, yd-yu] block of
+ * measurement values (y_hi where the cell is seen as 1, y_lo otherwise) to out_host. */
+int ipp_measure(ipp_handle* h, const uint8_t* gt_host, const int32_t* rect, int32_t altitude_m, uint32_t episode,
+                uint32_t agent, uint32_t index, float y_hi, float y_lo, float* out_host);
+
 /* Mapping.update_cells / apply_update (mapping/mappings.py:106-124) on n cells:
  * x is clamped IN PLACE like the reference; y is per cell (y_is_scalar == 0) or one value
  * (IG_baseline.py:240-245 passes a Python float); out = updated probabilities. */

@@ -46,7 +46,7 @@ class IppStepIO(C.Structure):
 EXPORTS = [
     "ipp_status_string", "ipp_last_error", "ipp_version", "ipp_create", "ipp_destroy", "ipp_scratch_bytes",
     "ipp_set_step_variant", "ipp_get_step_variant",
-    "ipp_reset", "ipp_step", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_project_fov", "ipp_update_cells",
+    "ipp_reset", "ipp_step", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_project_fov", "ipp_measure", "ipp_update_cells",
     "ipp_shannon_entropy", "ipp_fuse_map", "ipp_utility_reward",
 ]
 
@@ -87,6 +87,8 @@ def load():
         getattr(lib, name).argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp]
     lib.ipp_step_phases.argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), i32, vp]
     lib.ipp_project_fov.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.ipp_measure.argtypes = [vp, vp, C.POINTER(i32), i32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
+                                C.c_float, vp]
     lib.ipp_update_cells.argtypes = [vp, vp, vp, i32, i64, vp]
     lib.ipp_shannon_entropy.argtypes = [vp, vp, i64, vp]
     lib.ipp_fuse_map.argtypes = [vp, vp, vp, i32, i64, vp]

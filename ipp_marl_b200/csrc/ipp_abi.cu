@@ -4,6 +4,7 @@
 #include <cstring>
 #include <new>
 
+#include "ipp_device.cuh"
 #include "ipp_launch.h"
 
 struct ipp_handle {
@@ -253,6 +254,29 @@ int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, 
   clipped[1] = clip(raw[1], c.gy - 1);
   clipped[2] = clip(raw[2], c.gx - 1);
   clipped[3] = clip(raw[3], c.gx - 1);
+  return IPP_OK;
+}
+
+int ipp_measure(ipp_handle* h, const uint8_t* gt_host, const int32_t* rect, int32_t altitude_m, uint32_t episode,
+                uint32_t agent, uint32_t index, float y_hi, float y_lo, float* out_host) {
+  if (h == nullptr || gt_host == nullptr || rect == nullptr || out_host == nullptr) return IPP_ERR_INVALID_ARG;
+  const ipp_config& c = h->cfg;
+  if (rect[0] < 0 || rect[1] > c.gy || rect[2] < 0 || rect[3] > c.gx) return IPP_ERR_INVALID_ARG;
+  const int64_t n = (int64_t)(rect[3] - rect[2]) * (rect[1] - rect[0]);
+  if (rect[3] <= rect[2] || rect[1] <= rect[0]) return IPP_OK;  // empty footprint: nothing to write
+  const int iz = altitude_m / c.spacing - c.min_altitude / c.spacing;
+  // sensors/models/sensor_models.py:13-22 returns noise 0 for an unknown altitude: never measured wrongly
+  const uint32_t thresh = (altitude_m % c.spacing == 0 && iz >= 0 && iz < c.n_alt) ? c.flip_thresh[iz] : 0u;
+  const size_t cells = (size_t)c.gx * c.gy;
+  const size_t gt_al = (cells + 15) & ~(size_t)15;
+  int rc = ensure_fbuf(h, gt_al + sizeof(float) * (size_t)n);
+  if (rc != IPP_OK) return rc;
+  uint8_t* dgt = static_cast<uint8_t*>(h->fbuf);
+  float* dout = reinterpret_cast<float*>(dgt + gt_al);
+  IPP_CUDA(h, cudaMemcpy(dgt, gt_host, cells, cudaMemcpyHostToDevice));
+  const uint32_t key = ipp::stream_key(c.seed, episode, agent, index, ipp::PURPOSE_NOISE);
+  IPP_CUDA(h, ipp::launch_measure(c, dgt, rect, key, thresh, y_hi, y_lo, dout, 0));
+  IPP_CUDA(h, cudaMemcpy(out_host, dout, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
   return IPP_OK;
 }
 

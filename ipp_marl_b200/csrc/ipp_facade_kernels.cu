@@ -76,6 +76,31 @@ __global__ void utility_final_kernel(const double* __restrict__ partial, const i
   out2[1] = absolute / (t2 / (double)n);  // utils/reward.py:82
 }
 
+// Simulation.get_measurement (mapping/simulations.py:42-65): noisy view of the ground truth inside a
+// clipped footprint [yu, yd, xl, xr]; out is the [xr-xl, yd-yu] float32 block the reference returns.
+__global__ void measure_kernel(const __grid_constant__ ipp_config cfg, const uint8_t* __restrict__ gt,
+                               const int32_t yu, const int32_t yd, const int32_t xl, const int32_t xr,
+                               const uint32_t key, const uint32_t thresh, const float y_hi, const float y_lo,
+                               float* __restrict__ out) {
+  const int32_t w = yd - yu, n = (xr - xl) * w;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t x = xl + i / w, y = yu + i % w;
+    const uint32_t cell = (uint32_t)(x * cfg.gy + y);
+    const bool wrong = cell_hash(key, cell) < thresh;
+    const bool seen_one = (gt[cell] != 0) != wrong;
+    out[i] = seen_one ? y_hi : y_lo;
+  }
+}
+
+cudaError_t launch_measure(const ipp_config& cfg, const uint8_t* gt, const int32_t* rect, uint32_t key,
+                           uint32_t thresh, float y_hi, float y_lo, float* out, cudaStream_t s) {
+  const int64_t n = (int64_t)(rect[3] - rect[2]) * (rect[1] - rect[0]);
+  if (n <= 0) return cudaSuccess;
+  measure_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(cfg, gt, rect[0], rect[1], rect[2], rect[3], key, thresh, y_hi,
+                                                        y_lo, out);
+  return cudaGetLastError();
+}
+
 static int grid_for(int64_t n, int threads, int cap) {
   int64_t b = (n + threads - 1) / threads;
   if (b < 1) b = 1;

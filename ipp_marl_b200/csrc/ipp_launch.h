@@ -42,6 +42,8 @@ cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const Launc
 // single-map helpers used by the facade entry points (device pointers)
 cudaError_t launch_update_cells(const ipp_config& cfg, float* x, const float* y, int y_is_scalar, float y_scalar,
                                 int64_t n, float* out, cudaStream_t s);
+cudaError_t launch_measure(const ipp_config& cfg, const uint8_t* gt, const int32_t* rect, uint32_t key,
+                           uint32_t thresh, float y_hi, float y_lo, float* out, cudaStream_t s);
 cudaError_t launch_entropy(const ipp_config& cfg, float* p, int64_t n, float* out, cudaStream_t s);
 cudaError_t launch_utility_reward(const ipp_config& cfg, const float* last, const float* next, int64_t n,
                                   double* out2, cudaStream_t s);

@@ -242,11 +242,11 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
                                 const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
                                 float* reward_rel, float* reward_abs, double* partials, cudaStream_t s) {
   auto kern = step_tma_kernel<A, DO_OWN>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
+  static int configured_bytes = 0;  // per template instantiation; grows to the largest plan seen
+  if (plan.smem_bytes > configured_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured_bytes = plan.smem_bytes;
   }
   const int n_items = cfg.n_envs * plan.n_chunks;
   const int grid = n_items < n_sm ? n_items : n_sm;

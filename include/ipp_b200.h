@@ -18,6 +18,7 @@
  *   ground truth  uint8   [n_envs, gt_stride]    (mapping/ground_truths.py:42-56 half-plane field)
  *   positions     int32   [n_envs, n_agents, 3]  metres (x, y, z), as agent/agent.py keeps them
  *   episodes      uint32  [n_envs]               episode number of each env (seeds + random streams)
+ *   meas codes    uint8   [2, n_envs, code_stride]  latest measurement of every agent, 1 byte per (quad, agent)
  */
 #ifndef IPP_B200_H
 #define IPP_B200_H
@@ -52,6 +53,7 @@ typedef struct ipp_config {
   int32_t map_stride;      /* cells between consecutive float32 maps, multiple of 4, >= gx*gy     */
   int32_t gt_stride;       /* bytes between consecutive ground-truth maps, multiple of 16, >=      */
                            /* map_stride (16-byte rows so that TMA bulk copies can stage them)     */
+  int32_t code_stride;     /* bytes of measurement codes per env: roundup16(ceil(gx*gy/4) * (A<=4 ? 4 : 8)) */
   int32_t px, py, n_alt;   /* agent lattice: agent/state_space.py:16-18                            */
   int32_t n_agents;        /* 1..IPP_MAX_AGENTS                                                    */
   int32_t n_envs;          /* envs owned by this handle (this GPU's shard)                         */
@@ -78,6 +80,10 @@ typedef struct ipp_state {
   float* global_map;   /* [n_envs, map_stride]            accumulated_map_knowledge                */
   uint8_t* ground_truth; /* [n_envs, gt_stride]           Mapping.simulated_map                    */
   uint32_t* episodes;  /* [n_envs]                                                                  */
+  uint8_t* meas_codes; /* [2, n_envs, code_stride] compact form of Agent.map2communicate: one byte per   */
+                       /* (4-cell quad, agent): low nibble = cell inside the agent's latest footprint,   */
+                       /* high nibble = cell measured as occupied.  Half (t & 1) holds the measurements  */
+                       /* communicated at step t, the other half receives those taken after the moves.   */
 } ipp_state;
 
 /* Per-step inputs / outputs (device pointers; any output may be NULL). */

@@ -17,6 +17,7 @@ struct ipp_handle {
   double* partials;     // [n_envs, n_chunks, 2]
   int32_t* gt_params;   // [n_envs, 4]
   uint8_t* comm;        // [n_envs, n_agents] when the caller does not ask for comm_out
+  float4* lut;          // [n_alt, 256] odds multipliers of a quad for every measurement code byte
   // facade scratch (grown on demand)
   void* fbuf;
   size_t fbuf_bytes;
@@ -41,14 +42,14 @@ cudaError_t launch_maps(ipp_handle* h, const ipp_state* st, const ipp_step_io& i
                         cudaStream_t s) {
   const int32_t* pos_out = do_own ? io.pos_out : io.pos_in;
   if (h->variant == IPP_VARIANT_TMA) {
-    cudaError_t e = ipp::launch_step_tma(h->cfg, *st, h->tma, h->n_sm, io.pos_in, pos_out, io.comm_out, t,
+    cudaError_t e = ipp::launch_step_tma(h->cfg, *st, h->lut, h->tma, h->n_sm, io.pos_in, pos_out, io.comm_out, t,
                                          io.reward_rel, io.reward_abs, h->partials, do_own, s);
     if (e != cudaSuccess) return e;
     if (h->tma.n_chunks > 1)
       e = ipp::launch_reward_finalize(h->cfg, h->partials, h->tma.n_chunks, io.reward_rel, io.reward_abs, s);
     return e;
   }
-  return ipp::launch_step_dense(h->cfg, *st, h->plan, io.pos_in, pos_out, io.comm_out, t, io.reward_rel,
+  return ipp::launch_step_dense(h->cfg, *st, h->lut, h->plan, io.pos_in, pos_out, io.comm_out, t, io.reward_rel,
                                 io.reward_abs, h->partials, do_own, s);
 }
 
@@ -58,6 +59,10 @@ int validate(const ipp_config* c) {
   if ((int64_t)c->gx * c->gy > (1 << 28)) return IPP_ERR_UNSUPPORTED;
   if (c->map_stride < c->gx * c->gy || (c->map_stride & 3) != 0) return IPP_ERR_INVALID_ARG;
   if (c->gt_stride < c->map_stride || (c->gt_stride & 15) != 0) return IPP_ERR_INVALID_ARG;
+  {
+    const int64_t need = (((int64_t)c->gx * c->gy + 3) / 4) * (c->n_agents <= 4 ? 4 : 8);
+    if (c->code_stride < need || (c->code_stride & 15) != 0) return IPP_ERR_INVALID_ARG;
+  }
   if (c->n_agents < 1 || c->n_agents > IPP_MAX_AGENTS) return IPP_ERR_UNSUPPORTED;
   if (c->n_alt < 1 || c->n_alt > IPP_MAX_ALT) return IPP_ERR_UNSUPPORTED;
   if (c->px < 1 || c->px > IPP_MAX_LATTICE || c->py < 1 || c->py > IPP_MAX_LATTICE) return IPP_ERR_UNSUPPORTED;
@@ -76,10 +81,10 @@ int validate(const ipp_config* c) {
 
 int check_state(const ipp_state* st) {
   if (st == nullptr || st->local_maps == nullptr || st->global_map == nullptr || st->ground_truth == nullptr ||
-      st->episodes == nullptr)
+      st->episodes == nullptr || st->meas_codes == nullptr)
     return IPP_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(st->local_maps) & 15) || (reinterpret_cast<uintptr_t>(st->global_map) & 15) ||
-      (reinterpret_cast<uintptr_t>(st->ground_truth) & 15))
+      (reinterpret_cast<uintptr_t>(st->ground_truth) & 15) || (reinterpret_cast<uintptr_t>(st->meas_codes) & 15))
     return IPP_ERR_INVALID_ARG;
   return IPP_OK;
 }
@@ -150,7 +155,30 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
     ipp_destroy(h);
     return IPP_ERR_ALLOC;
   }
-  h->scratch_bytes = (int64_t)(pb + gb + cb);
+  // lut[alt][byte][c]: cell c of a quad with code `byte` (low nibble: inside the footprint, high nibble:
+  // seen as 1) is multiplied by k_hi / k_lo of the altitude, cells outside the footprint by k_out
+  const size_t lb = sizeof(float) * 4 * 256 * (size_t)cfg->n_alt;
+  {
+    float* host = new (std::nothrow) float[4 * 256 * (size_t)cfg->n_alt];
+    if (host == nullptr || cudaMalloc(&h->lut, lb) != cudaSuccess) {
+      delete[] host;
+      ipp_destroy(h);
+      return IPP_ERR_ALLOC;
+    }
+    for (int a = 0; a < cfg->n_alt; ++a)
+      for (int byte = 0; byte < 256; ++byte)
+        for (int c = 0; c < 4; ++c) {
+          const bool in = (byte >> c) & 1, one = (byte >> (4 + c)) & 1;
+          host[((size_t)a * 256 + byte) * 4 + c] = in ? (one ? cfg->k_hi[a] : cfg->k_lo[a]) : cfg->k_out;
+        }
+    const cudaError_t e = cudaMemcpy(h->lut, host, lb, cudaMemcpyHostToDevice);
+    delete[] host;
+    if (e != cudaSuccess) {
+      ipp_destroy(h);
+      return IPP_ERR_CUDA;
+    }
+  }
+  h->scratch_bytes = (int64_t)(pb + gb + cb + lb);
   *out = h;
   return IPP_OK;
 }
@@ -160,6 +188,7 @@ int ipp_destroy(ipp_handle* h) {
   if (h->partials) cudaFree(h->partials);
   if (h->gt_params) cudaFree(h->gt_params);
   if (h->comm) cudaFree(h->comm);
+  if (h->lut) cudaFree(h->lut);
   if (h->fbuf) cudaFree(h->fbuf);
   delete h;
   return IPP_OK;
@@ -187,7 +216,7 @@ int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream
   if (h == nullptr || pos_out == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
-  IPP_CUDA(h, ipp::launch_reset(h->cfg, *st, h->plan, pos_out, h->gt_params, (cudaStream_t)stream));
+  IPP_CUDA(h, ipp::launch_reset(h->cfg, *st, h->lut, h->plan, pos_out, h->gt_params, (cudaStream_t)stream));
   return IPP_OK;
 }
 
@@ -201,7 +230,7 @@ int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_ste
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 1, s));
+  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 1, s));
   if (phases & IPP_PHASE_MAPS) IPP_CUDA(h, launch_maps(h, st, io2, t, true, s));
   return IPP_OK;
 }
@@ -218,7 +247,7 @@ int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, io2, t, 1, 0, s));
+  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 0, s));
   IPP_CUDA(h, launch_maps(h, st, io2, t, false, s));
   return IPP_OK;
 }
@@ -230,8 +259,8 @@ int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io
   if (rc != IPP_OK) return rc;
   if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_move(h->cfg, st->episodes, *io, t, 0, 1, s));
-  IPP_CUDA(h, ipp::launch_own_update(h->cfg, *st, io->pos_out, t, s));
+  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, *io, t, 0, 1, s));
+  IPP_CUDA(h, ipp::launch_own_update(h->cfg, *st, h->lut, io->pos_out, t, s));
   return IPP_OK;
 }
 

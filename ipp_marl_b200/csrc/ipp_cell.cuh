@@ -1,9 +1,13 @@
-// Per-quad (4 consecutive cells) map arithmetic shared by the direct-load and the TMA-staged step
+// Per-quad (4 consecutive cells) belief arithmetic shared by the direct-load and the TMA-staged map
 // kernels.  Reference: mapping/mappings.py:80-124 (fuse), :32-78 (own update),
 // utils/reward.py:68-82 + utils/state.py:53-76,118-121 (reward terms).
 // Specification: oracle/kernel_model.py::_apply / _reward  (belief maps bit-exact).
 //
-// The kernel is issue-bound, not HBM-bound, unless this code is lean (profiles/): so
+// The map kernels are issue-bound (ALU pipe), not HBM-bound, unless this code is lean (profiles/):
+//   * everything geometric / random about a measurement (footprint test, noise hash, ground truth) is
+//     done once per step by plan_kernel, rect-sparse, and handed over as one CODE BYTE per (quad, agent):
+//     low nibble = cell inside the footprint, high nibble = cell seen as 1.  The map kernels turn a
+//     code byte into the 4 odds multipliers with ONE 16-byte table load (lut[altitude][byte]);
 //   * the 4 cells of a quad are processed branch-free, two cells per instruction with the sm_100
 //     packed-float32 FFMA2 / FMUL2 forms (IEEE per lane => still bit-exact);
 //   * divisions use the fast path of div.rn.f32 (MUFU.RCP + 5 FMAs) without its range check —
@@ -15,25 +19,30 @@
 
 namespace ipp {
 
-// Everything about one env that the per-cell code needs; lives in shared memory.
+// Per-env facts the per-quad code needs (shared memory).
 template <int A>
 struct EnvMeta {
-  Meas prev[A];      // communicated measurements (taken at pos_in, index t)
-  Meas next[A];      // measurements after the move (taken at pos_out, index t+1)
-  uint32_t comm[A];  // bit j: agent i fuses agent j's measurement (own bit cleared)
+  uint32_t comm[A];      // bit j: agent i fuses agent j's measurement (own bit cleared)
+  uint32_t lut_prev[A];  // float4 index of the LUT row (altitude) of agent j's communicated measurement
+  uint32_t lut_next[A];  // same for the measurement after the move
 };
+
+__device__ __forceinline__ uint32_t lut_row(const ipp_config& c, const int32_t* pos) {
+  const int32_t iz = clampi(pos[2] / c.spacing - c.min_altitude / c.spacing, 0, c.n_alt - 1);
+  return (uint32_t)iz * 256u;
+}
 
 template <int A>
 __device__ __forceinline__ void load_env_meta(const ipp_config& cfg, EnvMeta<A>* m, int lane_or_tid, int32_t b,
-                                              uint32_t ep, const int32_t* pos_in, const int32_t* pos_out,
-                                              const uint8_t* comm, int32_t t, bool do_own) {
+                                              const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm,
+                                              bool do_own) {
   if (lane_or_tid < A) {
     const int a = lane_or_tid;
-    m->prev[a] = make_meas(cfg, pos_in + ((int64_t)b * A + a) * 3, ep, a, (uint32_t)t);
+    m->lut_prev[a] = lut_row(cfg, pos_in + ((int64_t)b * A + a) * 3);
     m->comm[a] = (uint32_t)comm[(int64_t)b * A + a] & ~(1u << a);  // own measurement already used
-  } else if (lane_or_tid < 2 * A && do_own) {
+  } else if (lane_or_tid < 2 * A) {
     const int a = lane_or_tid - A;
-    m->next[a] = make_meas(cfg, pos_out + ((int64_t)b * A + a) * 3, ep, a, (uint32_t)t + 1u);
+    m->lut_next[a] = do_own ? lut_row(cfg, pos_out + ((int64_t)b * A + a) * 3) : 0u;
   }
 }
 
@@ -72,7 +81,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 // a / b, given b and nb = -b: instruction-for-instruction the fast path nvcc emits for div.rn.f32
-// (MUFU.RCP, two Newton steps on the reciprocal/quotient, one remainder correction), i.e. the
+// (MUFU.RCP, one Newton step on the reciprocal, quotient, one remainder correction), i.e. the
 // correctly rounded quotient for normal operands with a normal quotient.
 __device__ __forceinline__ F4 f4_div(const F4 a, const F4 b, const F4 nb) {
   const F4 one = f4_splat(1.0f);
@@ -107,69 +116,54 @@ __device__ __forceinline__ F4 f4_from_odds(const F4 o) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// footprint masks of a quad
+// measurement codes: one byte per (quad, agent), AP = 4 (A <= 4) or 8 bytes per quad
 // ------------------------------------------------------------------------------------------------
-// Cells c0..c0+3 lie in row x0 from column y0 (n0 = cells before the row wraps, 1..4) and, when
-// n0 < 4, continue in row x0+1 from column 0 (requires gy >= 4).
-__device__ __forceinline__ uint32_t rect_mask4(const Meas& m, int32_t x0, int32_t y0, int32_t n0) {
-  uint32_t mask = 0;
-  {
-    const int32_t lo = max(m.yu - y0, 0), hi = min(m.yd - y0, n0);
-    if ((uint32_t)(x0 - m.xl) < (uint32_t)(m.xr - m.xl) && hi > lo) mask = (1u << hi) - (1u << lo);
-  }
-  if (n0 < 4) {
-    const int32_t lo = m.yu, hi = min(m.yd, 4 - n0);
-    if ((uint32_t)(x0 + 1 - m.xl) < (uint32_t)(m.xr - m.xl) && hi > lo) mask |= ((1u << hi) - (1u << lo)) << n0;
-  }
-  return mask;
-}
+template <int A>
+struct CodeWord {
+  static constexpr int WORDS = (A + 3) / 4;
+  uint32_t w[WORDS];
+  __device__ __forceinline__ uint32_t byte(int j) const { return (w[j >> 2] >> (8 * (j & 3))) & 0xFFu; }
+};
 
-// odds multipliers of measurement m at the 4 cells (k_out where the cell is outside its footprint)
-__device__ __forceinline__ F4 meas_k4(const Meas& m, uint32_t mask4, int32_t c0, uint32_t g4, float k_out) {
-  float k[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const bool wrong = cell_hash(m.key, (uint32_t)(c0 + c)) < m.thresh;
-    const bool seen_one = (((g4 >> (8 * c)) & 0xFFu) != 0u) != wrong;
-    const float kin = seen_one ? m.k_hi : m.k_lo;
-    k[c] = ((mask4 >> c) & 1u) ? kin : k_out;
+template <int A>
+__device__ __forceinline__ CodeWord<A> load_code(const void* base, int32_t quad) {
+  CodeWord<A> c;
+  if (CodeWord<A>::WORDS == 1) {
+    c.w[0] = reinterpret_cast<const uint32_t*>(base)[quad];
+  } else {
+    const uint2 v = reinterpret_cast<const uint2*>(base)[quad];
+    c.w[0] = v.x;
+    c.w[CodeWord<A>::WORDS - 1] = v.y;
   }
-  return F4{make_float2(k[0], k[1]), make_float2(k[2], k[3])};
+  return c;
 }
 
 template <int A>
 struct QuadCtx {
-  F4 kprev[A];       // multipliers of the communicated measurements
-  uint32_t in_prev;  // bit (j*4+c): cell c lies inside agent j's communicated footprint
+  F4 kprev[A];       // multipliers of the communicated measurements (k_out outside a footprint)
+  uint32_t in_prev;  // bits 4j..4j+3: cells inside agent j's communicated footprint
   uint32_t wcov;     // bit j: some active lane of this warp has a cell inside footprint j
-  uint32_t valid;    // bit c: cell c0+c < n_cells
-  uint32_t g4;       // 4 ground-truth bytes
-  int32_t c0, x0, y0, n0;
 };
 
 // Must be called with the warp's loop-active lanes converged (it votes over __activemask()).
+// `lut` is the [n_alt][256] float4 table (shared or global memory).
 template <int A>
-__device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMeta<A>& meta, int32_t c0, uint32_t g4,
-                                              int32_t n_cells, QuadCtx<A>& q) {
-  q.c0 = c0;
-  q.g4 = g4;
-  q.x0 = c0 / cfg.gy;
-  q.y0 = c0 - q.x0 * cfg.gy;
-  q.n0 = min(4, cfg.gy - q.y0);
-  const int32_t left = n_cells - c0;
-  q.valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
+__device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& prev,
+                                              const float4* lut, QuadCtx<A>& q) {
   q.in_prev = 0;
   q.wcov = 0;
   const uint32_t active = __activemask();
   const bool kout_one = (cfg.k_out == 1.0f);
 #pragma unroll
   for (int j = 0; j < A; ++j) {
-    const Meas m = meta.prev[j];
-    const uint32_t mask = rect_mask4(m, q.x0, q.y0, q.n0) & q.valid;
-    q.in_prev |= mask << (j * 4);
-    if (__any_sync(active, mask != 0u) || !kout_one) q.wcov |= 1u << j;
+    const uint32_t byte = prev.byte(j);
+    const uint32_t in = byte & 0xFu;
+    q.in_prev |= in << (4 * j);
     q.kprev[j] = f4_splat(cfg.k_out);
-    if (mask != 0u) q.kprev[j] = meas_k4(m, mask, c0, g4, cfg.k_out);
+    if (__any_sync(active, in != 0u) || !kout_one) {  // warp-uniform
+      q.wcov |= 1u << j;
+      q.kprev[j] = f4_from(lut[meta.lut_prev[j] + byte]);
+    }
   }
 }
 
@@ -180,7 +174,7 @@ __device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMe
 // Semantics per cell (oracle/kernel_model.py::_apply): every enabled fuse pass clamps the odds and
 // multiplies by k_j (k_out outside footprint j); then, inside the own footprint only, clamp and
 // multiply by k_own.  Untouched cells keep p (or clamp(p) if some fuse pass ran) bit for bit.
-// Returns the new probabilities; `touched` receives the 4-bit mask of recomputed cells.
+// Padding cells beyond gx*gy are never inside a footprint, hold the prior and stay unchanged.
 // ------------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadCtx<A>& q, const F4 p,
@@ -191,14 +185,17 @@ __device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadC
   uint32_t t = own;
 #pragma unroll
   for (int j = 0; j < A; ++j)
-    if ((en >> j) & 1u) t |= (q.in_prev >> (j * 4)) & 0xFu;
+    if ((en >> j) & 1u) t |= (q.in_prev >> (4 * j)) & 0xFu;
   if (any_fuse && !kout_one) t = 0xFu;
-  t &= q.valid;
   touched = t;
+  if (t == 0u && !any_fuse) {  // nothing happens to this quad of this map
+    pc_out = p;
+    return p;
+  }
   const F4 pc = f4_clamp(p, cfg.p_min, cfg.p_max);
   pc_out = pc;
   const F4 fallback = any_fuse ? pc : p;
-  if (t == 0u) return f4_select(q.valid, fallback, p);
+  if (t == 0u) return fallback;
 
   F4 o = f4_to_odds(pc);
   bool clean = true;  // o is known to lie inside [o_min, o_max] (fresh from pc, or just clamped)
@@ -226,11 +223,10 @@ __device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadC
     const F4 oc = clean ? o : f4_clamp(o, cfg.o_min, cfg.o_max);
     o = f4_select(own, f4_mul(oc, k_own), o);
   }
-  const F4 pn = f4_from_odds(o);
-  return f4_select(t, pn, f4_select(q.valid, fallback, p));
+  return f4_select(t, f4_from_odds(o), fallback);
 }
 
-// float32 reward terms of one cell pair set; H in bits (utils/state.py:118-121)
+// float32 reward terms; H in bits (utils/state.py:118-121)
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -242,21 +238,22 @@ __device__ __forceinline__ float entropy_bits(float pc) {  // pc already clamped
 }
 
 // Global map: fuse every agent's communicated measurement (coma_wrapper.py:93-95) and accumulate
-// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last)  (utils/reward.py:68-82).
+// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last)  (utils/reward.py:68-82).  `valid`: bit c = cell exists.
 template <int A>
 __device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, const QuadCtx<A>& q, const float4 p4,
-                                                     double& s1, double& s2) {
+                                                     const uint32_t valid, double& s1, double& s2) {
   F4 pc;
   uint32_t touched;
-  const F4 pn = update_map_quad<A>(cfg, q, f4_from(p4), (1u << A) - 1u, 0u, f4_splat(1.0f), pc, touched);
+  const F4 p = f4_from(p4);
+  const F4 pn = update_map_quad<A>(cfg, q, p, (1u << A) - 1u, 0u, f4_splat(1.0f), pc, touched);
   float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (!((q.valid >> c) & 1u)) continue;
+    if (!((valid >> c) & 1u)) continue;
     const float next = f4_get(pn, c);
     const float hl = entropy_bits(f4_get(pc, c));
     float hn = hl;
-    if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl below
+    if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl
       hn = ((touched >> c) & 1u) ? entropy_bits(fminf(fmaxf(next, cfg.p_min), cfg.p_max)) : hl;
     const float w = next > 0.501f ? 1.0f : (next < 0.499f ? 0.0f : 0.5f);  // == the float64 compares
     a1 += w * (hl - hn);
@@ -268,20 +265,25 @@ __device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, cons
 }
 
 // Local map of agent i: fuse the received peers' measurements (agent/agent.py:62-71), then the own
-// measurement at the new position (agent/agent.py:91-94) when DO_OWN.
+// measurement at the new position (agent/agent.py:91-94) when DO_OWN (code byte `own_byte`).
 template <int A, bool DO_OWN>
 __device__ __forceinline__ float4 update_local_quad(const ipp_config& cfg, const EnvMeta<A>& meta,
-                                                    const QuadCtx<A>& q, int i, const float4 p4) {
+                                                    const QuadCtx<A>& q, int i, const uint32_t own_byte,
+                                                    const float4* lut, const float4 p4) {
   uint32_t own = 0;
   F4 k_own = f4_splat(1.0f);
   if (DO_OWN) {
-    const Meas mn = meta.next[i];
-    own = rect_mask4(mn, q.x0, q.y0, q.n0) & q.valid;
-    if (own != 0u) k_own = meas_k4(mn, own, q.c0, q.g4, 1.0f);
+    own = own_byte & 0xFu;
+    k_own = f4_from(lut[meta.lut_next[i] + own_byte]);
   }
   F4 pc;
   uint32_t touched;
   return f4_to(update_map_quad<A>(cfg, q, f4_from(p4), meta.comm[i], own, k_own, pc, touched));
+}
+
+__device__ __forceinline__ uint32_t valid_mask4(int32_t c0, int32_t n_cells) {
+  const int32_t left = n_cells - c0;
+  return left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

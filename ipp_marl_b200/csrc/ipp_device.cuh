@@ -70,6 +70,39 @@ __device__ __forceinline__ bool in_rect(const Meas& m, int32_t x, int32_t y) {
   return (uint32_t)(x - m.xl) < (uint32_t)(m.xr - m.xl) && (uint32_t)(y - m.yu) < (uint32_t)(m.yd - m.yu);
 }
 
+// 4-bit footprint mask of a quad.  Cells c0..c0+3 lie in row x0 from column y0 (n0 = cells before
+// the row wraps, 1..4) and, when n0 < 4, continue in row x0+1 from column 0 (requires gy >= 4).
+__device__ __forceinline__ uint32_t rect_mask4(const Meas& m, int32_t x0, int32_t y0, int32_t n0) {
+  uint32_t mask = 0;
+  {
+    const int32_t lo = max(m.yu - y0, 0), hi = min(m.yd - y0, n0);
+    if ((uint32_t)(x0 - m.xl) < (uint32_t)(m.xr - m.xl) && hi > lo) mask = (1u << hi) - (1u << lo);
+  }
+  if (n0 < 4) {
+    const int32_t lo = m.yu, hi = min(m.yd, 4 - n0);
+    if ((uint32_t)(x0 + 1 - m.xl) < (uint32_t)(m.xr - m.xl) && hi > lo) mask |= ((1u << hi) - (1u << lo)) << n0;
+  }
+  return mask;
+}
+
+// Measurement code byte of quad (cells c0..c0+3) for measurement m: low nibble = cell inside the
+// footprint, high nibble = cell seen as 1 (mapping/simulations.py:42-65 with the hash noise).
+__device__ __forceinline__ uint32_t meas_code_byte(const ipp_config& c, const Meas& m, int32_t c0, uint32_t g4) {
+  const int32_t x0 = c0 / c.gy, y0 = c0 - x0 * c.gy;
+  const int32_t left = c.gx * c.gy - c0;
+  const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
+  const uint32_t in = rect_mask4(m, x0, y0, min(4, c.gy - y0)) & valid;
+  if (in == 0u) return 0u;
+  uint32_t seen = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool wrong = cell_hash(m.key, (uint32_t)(c0 + k)) < m.thresh;
+    const bool one = (((g4 >> (8 * k)) & 0xFFu) != 0u) != wrong;
+    seen |= (one ? 1u : 0u) << k;
+  }
+  return in | ((seen & in) << 4);
+}
+
 // Odds multiplier of this measurement at a cell inside its rect:
 // mapping/simulations.py:42-65 (value = accuracy if the cell is seen as 1 else 1-accuracy).
 __device__ __forceinline__ float meas_k(const Meas& m, uint32_t cell, uint32_t gt) {

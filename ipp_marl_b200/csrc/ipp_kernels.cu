@@ -1,9 +1,10 @@
 // Hot-path kernels of the batched IPP environment (sm_100a).
 //
-//   move_kernel          comm matrix + sequential masks / action choice / moves   (1 thread / env)
-//   step_dense_kernel    per-cell fuse (local + global) + own measurement update + reward sums
+//   plan_kernel          per env: comm matrix, sequential masks / action choice / moves, and the
+//                        measurement codes of the footprints at the new positions (rect-sparse)
+//   step_dense_kernel    direct-load map kernel: fuse (local + global) + own update + reward sums
 //   reward_finalize      per-env reward from per-chunk partial sums (only when an env spans >1 chunk)
-//   own_update_kernel    footprint-sparse measurement update (split observe/act mode)
+//   own_update_kernel    own measurement update of the local maps (split observe/act mode)
 //   reset_prep / reset_fill   episode reset (MT19937-compatible start positions + ground truth)
 //
 // Arithmetic specification: oracle/kernel_model.py (bit-exact for belief maps).
@@ -13,7 +14,8 @@
 namespace ipp {
 
 // =================================================================================================
-// comm matrix + moves: agent/communication_log.py:39-58, agent/action_space.py:56-70,211-223,328-344
+// plan: agent/communication_log.py:39-58, agent/action_space.py:56-70,211-223,328-344,
+//       sensors/cameras.py:46-79 + mapping/simulations.py:42-65 (measurement at the new position)
 // =================================================================================================
 __device__ __forceinline__ uint32_t bounds_mask(const ipp_config& c, const int32_t* p) {
   uint32_t m = 0x3Fu;
@@ -49,13 +51,10 @@ __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
   return -1;
 }
 
-__global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ ipp_config cfg,
-                                                   const uint32_t* __restrict__ episodes, const ipp_step_io io,
-                                                   const int32_t t, const int32_t do_comm, const int32_t do_move) {
-  const int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= cfg.n_envs) return;
+// comm matrix + sequential moves of one env (one thread)
+__device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_t ep, const ipp_step_io& io,
+                           const int32_t t, const bool do_comm, const bool do_move, int32_t (*npos)[3]) {
   const int32_t A = cfg.n_agents;
-  const uint32_t ep = episodes[b];
   int32_t pos[IPP_MAX_AGENTS][3];
   for (int32_t a = 0; a < A; ++a)
     for (int32_t d = 0; d < 3; ++d) pos[a][d] = io.pos_in[((int64_t)b * A + a) * 3 + d];
@@ -76,7 +75,6 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ ipp_c
   }
   if (!do_move) return;
 
-  int32_t npos[IPP_MAX_AGENTS][3];
   uint32_t stuck = 0;
   for (int32_t a = 0; a < A; ++a) {
     uint32_t m = bounds_mask(cfg, pos[a]);
@@ -143,45 +141,94 @@ __global__ void __launch_bounds__(128) move_kernel(const __grid_constant__ ipp_c
   if (io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)stuck;
 }
 
+// Write the code bytes of measurement `m` (agent a) for every quad its footprint overlaps.
+// `codes` = this env's code row (AP bytes per quad), already zeroed.
+__device__ __forceinline__ void write_meas_codes(const ipp_config& cfg, const Meas& m, const int a, const int ap,
+                                                 const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
+                                                 const int tid, const int nthreads) {
+  const int32_t h = m.xr - m.xl, w = m.yd - m.yu;
+  if (h <= 0 || w <= 0) return;
+  const int32_t per_row = (w + 3) / 4 + 1;  // upper bound of quads overlapping one footprint row
+  for (int32_t task = tid; task < h * per_row; task += nthreads) {
+    const int32_t r = task / per_row, k = task - r * per_row;
+    const int32_t row0 = (m.xl + r) * cfg.gy;
+    const int32_t q = ((row0 + m.yu) >> 2) + k;
+    if (q > ((row0 + m.yd - 1) >> 2)) continue;
+    const int32_t c0 = q << 2;
+    const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
+    // a quad straddling two rows is reached from both; both tasks compute the same full byte
+    codes[(int64_t)q * ap + a] = (uint8_t)meas_code_byte(cfg, m, c0, g4);
+  }
+}
+
+constexpr int PLAN_THREADS = 128;
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+    plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
+                const int32_t do_comm, const int32_t do_move) {
+  const int32_t b = blockIdx.x;
+  const int32_t A = cfg.n_agents;
+  __shared__ int32_t s_npos[IPP_MAX_AGENTS][3];
+  __shared__ Meas s_meas[IPP_MAX_AGENTS];
+  const uint32_t ep = st.episodes[b];
+  const int tid = threadIdx.x;
+  if (tid == 0) plan_moves(cfg, b, ep, io, t, do_comm != 0, do_move != 0, s_npos);
+  if (!do_move) return;
+  // codes of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
+  uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
+  uint4* cz = reinterpret_cast<uint4*>(codes);
+  for (int32_t i = tid; i < (cfg.code_stride >> 4); i += PLAN_THREADS) cz[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (tid < A) s_meas[tid] = make_meas(cfg, s_npos[tid], ep, (uint32_t)tid, (uint32_t)t + 1u);
+  __syncthreads();
+  const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
+  const int ap = A <= 4 ? 4 : 8;
+  for (int a = 0; a < A; ++a) write_meas_codes(cfg, s_meas[a], a, ap, gt, codes, tid, PLAN_THREADS);
+}
+
 // =================================================================================================
-// dense per-cell pass, direct-load variant (per-quad arithmetic: ipp_cell.cuh)
+// map kernel, direct-load variant (per-quad arithmetic: ipp_cell.cuh)
 // one block per (env, chunk); each thread owns quads tid, tid+256, ... of the chunk in all A+1 maps
 // =================================================================================================
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(STEP_THREADS)
-    step_dense_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const int32_t* __restrict__ pos_in,
-                      const int32_t* __restrict__ pos_out, const uint8_t* __restrict__ comm, const int32_t t,
-                      float* __restrict__ reward_rel, float* __restrict__ reward_abs, double* __restrict__ partials,
-                      const int32_t n_chunks, const int32_t quads_per_chunk) {
+    step_dense_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut,
+                      const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
+                      const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
+                      float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks,
+                      const int32_t quads_per_chunk) {
   const int32_t b = blockIdx.x / n_chunks;
   const int32_t chunk = blockIdx.x - b * n_chunks;
   const int32_t tid = threadIdx.x;
   __shared__ EnvMeta<A> s_meta;
   __shared__ double s_red[2][STEP_THREADS / 32];
 
-  load_env_meta<A>(cfg, &s_meta, tid, b, st.episodes[b], pos_in, pos_out, comm, t, DO_OWN);
+  load_env_meta<A>(cfg, &s_meta, tid, b, pos_in, pos_out, comm, DO_OWN);
   __syncthreads();
 
   const int32_t n_cells = cfg.gx * cfg.gy;
   const int32_t n_quads = (n_cells + 3) >> 2;
   const int64_t stride = cfg.map_stride;
-  const uint8_t* gt_b = st.ground_truth + (int64_t)b * cfg.gt_stride;
   float* glob_b = st.global_map + (int64_t)b * stride;
   float* loc_b = st.local_maps + (int64_t)b * A * stride;
+  const uint8_t* code_prev = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const uint8_t* code_next = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
 
   double s1 = 0.0, s2 = 0.0;
   const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
   for (int32_t q = chunk * quads_per_chunk + tid; q < q_end; q += STEP_THREADS) {
     const int32_t c0 = q << 2;
     QuadCtx<A> qc;
-    make_quad_ctx<A>(cfg, s_meta, c0, *reinterpret_cast<const uint32_t*>(gt_b + c0), n_cells, qc);
-    *reinterpret_cast<float4*>(glob_b + c0) =
-        update_global_quad<A>(cfg, qc, *reinterpret_cast<const float4*>(glob_b + c0), s1, s2);
+    make_quad_ctx<A>(cfg, s_meta, load_code<A>(code_prev, q), lut, qc);
+    CodeWord<A> next;
+    if (DO_OWN) next = load_code<A>(code_next, q);
+    *reinterpret_cast<float4*>(glob_b + c0) = update_global_quad<A>(
+        cfg, qc, *reinterpret_cast<const float4*>(glob_b + c0), valid_mask4(c0, n_cells), s1, s2);
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       float* lp = loc_b + (int64_t)i * stride + c0;
-      *reinterpret_cast<float4*>(lp) =
-          update_local_quad<A, DO_OWN>(cfg, s_meta, qc, i, *reinterpret_cast<const float4*>(lp));
+      *reinterpret_cast<float4*>(lp) = update_local_quad<A, DO_OWN>(
+          cfg, s_meta, qc, i, DO_OWN ? next.byte(i) : 0u, lut, *reinterpret_cast<const float4*>(lp));
     }
   }
 
@@ -219,35 +266,37 @@ __global__ void reward_finalize_kernel(const double* __restrict__ partials, cons
     t1 += partials[((int64_t)b * n_chunks + c) * 2 + 0];
     t2 += partials[((int64_t)b * n_chunks + c) * 2 + 1];
   }
-  if (reward_rel != nullptr) reward_rel[b] = (float)(22.0 * (t1 / t2) - 0.5);
-  if (reward_abs != nullptr) reward_abs[b] = (float)(10.0 * (t1 / (double)n_cells) - 0.17);
+  write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
 }
 
 // =================================================================================================
-// footprint-sparse own measurement update (ipp_act): mapping/mappings.py:32-61
-// one block per (env, agent); threads walk the rect row by row
+// own measurement update of the local maps (ipp_act): mapping/mappings.py:32-61, driven by the codes
+// plan_kernel just wrote; only quads inside the footprint are read and written.
 // =================================================================================================
-__global__ void __launch_bounds__(256) own_update_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st,
-                                                         const int32_t* __restrict__ pos_out, const int32_t t) {
-  const int32_t A = cfg.n_agents;
-  const int32_t b = blockIdx.x / A, a = blockIdx.x % A;
-  __shared__ Meas s_m;
-  if (threadIdx.x == 0)
-    s_m = make_meas(cfg, pos_out + ((int64_t)b * A + a) * 3, st.episodes[b], (uint32_t)a, (uint32_t)t + 1u);
-  __syncthreads();
-  const Meas m = s_m;
-  const int32_t w = m.yd - m.yu, h = m.xr - m.xl;
-  if (w <= 0 || h <= 0) return;
+template <int A>
+__global__ void __launch_bounds__(256)
+    own_update_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut,
+                      const int32_t* __restrict__ pos_out, const int32_t t, const int32_t blocks_per_env) {
+  const int32_t b = blockIdx.x / blocks_per_env;
+  const int32_t n_quads = (cfg.gx * cfg.gy + 3) >> 2;
+  const uint8_t* code_next = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
   const int64_t stride = cfg.map_stride;
-  float* lp = st.local_maps + ((int64_t)b * A + a) * stride;
-  const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
-  for (int32_t idx = threadIdx.x; idx < w * h; idx += blockDim.x) {
-    const int32_t x = m.xl + idx / w, y = m.yu + idx % w;
-    const int32_t cell = x * cfg.gy + y;
-    const float pc = clamp_p(cfg, lp[cell]);
-    float o = to_odds(pc);
-    o = odds_pass(o, meas_k(m, (uint32_t)cell, gt[cell]), cfg.o_min, cfg.o_max);
-    lp[cell] = from_odds(o);
+  __shared__ uint32_t s_row[A];
+  if (threadIdx.x < A) s_row[threadIdx.x] = lut_row(cfg, pos_out + ((int64_t)b * A + threadIdx.x) * 3);
+  __syncthreads();
+  for (int32_t q = (blockIdx.x - b * blocks_per_env) * 256 + threadIdx.x; q < n_quads; q += blocks_per_env * 256) {
+    const CodeWord<A> cw = load_code<A>(code_next, q);
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const uint32_t byte = cw.byte(i);
+      const uint32_t own = byte & 0xFu;
+      if (own == 0u) continue;
+      float* lp = st.local_maps + ((int64_t)b * A + i) * stride + ((int64_t)q << 2);
+      const F4 p = f4_from(*reinterpret_cast<const float4*>(lp));
+      const F4 pc = f4_clamp(p, cfg.p_min, cfg.p_max);
+      const F4 o = f4_mul(f4_to_odds(pc), f4_from(lut[s_row[i] + byte]));
+      *reinterpret_cast<float4*>(lp) = f4_to(f4_select(own, f4_from_odds(o), p));
+    }
   }
 }
 
@@ -342,14 +391,21 @@ __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__
   }
 }
 
+// dense write of the ground truth, the prior maps with the t = 0 measurement applied, and the codes of
+// that measurement (half 0 of the ping-pong buffer; half 1 is cleared by the first plan_kernel)
 template <int A>
 __global__ void __launch_bounds__(STEP_THREADS)
-    reset_fill_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const int32_t* __restrict__ pos,
-                      const int32_t* __restrict__ gt_params, const int32_t n_chunks, const int32_t quads_per_chunk) {
+    reset_fill_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut,
+                      const int32_t* __restrict__ pos, const int32_t* __restrict__ gt_params, const int32_t n_chunks,
+                      const int32_t quads_per_chunk) {
   const int32_t b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks, tid = threadIdx.x;
   __shared__ Meas s_m[A];
+  __shared__ uint32_t s_row[A];
   const uint32_t ep = st.episodes[b];
-  if (tid < A) s_m[tid] = make_meas(cfg, pos + ((int64_t)b * A + tid) * 3, ep, tid, 0u);
+  if (tid < A) {
+    s_m[tid] = make_meas(cfg, pos + ((int64_t)b * A + tid) * 3, ep, tid, 0u);
+    s_row[tid] = lut_row(cfg, pos + ((int64_t)b * A + tid) * 3);
+  }
   __syncthreads();
   const int32_t split = gt_params[(int64_t)b * 4 + 0], lo = gt_params[(int64_t)b * 4 + 1],
                 hi = gt_params[(int64_t)b * 4 + 2];
@@ -357,18 +413,17 @@ __global__ void __launch_bounds__(STEP_THREADS)
   const int32_t n_quads = (int32_t)(cfg.map_stride >> 2);
   const int64_t stride = cfg.map_stride;
   const float prior = cfg.prior;
-  const float o_prior = to_odds(clamp_p(cfg, prior));
+  const F4 o_prior = f4_to_odds(f4_clamp(f4_splat(prior), cfg.p_min, cfg.p_max));
+  constexpr int AP = A <= 4 ? 4 : 8;
+  uint8_t* codes = st.meas_codes + (int64_t)b * cfg.code_stride;  // half 0
   const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
   for (int32_t q = chunk * quads_per_chunk + tid; q < q_end; q += STEP_THREADS) {
     const int32_t c0 = q << 2;
-    int32_t xs[4], ys[4];
     uint32_t g4 = 0;
     {
       int32_t x = c0 / cfg.gy, y = c0 - x * cfg.gy;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        xs[c] = x;
-        ys[c] = y;
         const int32_t v = (split < 2) ? x : y;
         if (c0 + c < n_cells && v >= lo && v < hi) g4 |= 1u << (8 * c);
         if (++y == cfg.gy) { y = 0; ++x; }
@@ -376,19 +431,18 @@ __global__ void __launch_bounds__(STEP_THREADS)
     }
     *reinterpret_cast<uint32_t*>(st.ground_truth + (int64_t)b * cfg.gt_stride + c0) = g4;
     *reinterpret_cast<float4*>(st.global_map + (int64_t)b * stride + c0) = make_float4(prior, prior, prior, prior);
+    uint32_t cw[2] = {0u, 0u};
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      const Meas m = s_m[i];
-      float pv[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        pv[c] = prior;
-        if (c0 + c < n_cells && in_rect(m, xs[c], ys[c]))
-          pv[c] = from_odds(odds_pass(o_prior, meas_k(m, (uint32_t)(c0 + c), (g4 >> (8 * c)) & 0xFFu), cfg.o_min,
-                                      cfg.o_max));
-      }
-      *reinterpret_cast<float4*>(st.local_maps + ((int64_t)b * A + i) * stride + c0) =
-          make_float4(pv[0], pv[1], pv[2], pv[3]);
+      const uint32_t byte = (c0 < n_cells) ? meas_code_byte(cfg, s_m[i], c0, g4) : 0u;
+      cw[i >> 2] |= byte << (8 * (i & 3));
+      F4 pv = f4_splat(prior);
+      if (byte & 0xFu) pv = f4_select(byte & 0xFu, f4_from_odds(f4_mul(o_prior, f4_from(lut[s_row[i] + byte]))), pv);
+      *reinterpret_cast<float4*>(st.local_maps + ((int64_t)b * A + i) * stride + c0) = f4_to(pv);
+    }
+    if ((int64_t)q * AP < cfg.code_stride) {
+      if (AP == 4) reinterpret_cast<uint32_t*>(codes)[q] = cw[0];
+      else reinterpret_cast<uint2*>(codes)[q] = make_uint2(cw[0], cw[1]);
     }
   }
 }
@@ -409,26 +463,24 @@ __global__ void __launch_bounds__(STEP_THREADS)
     default: return cudaErrorInvalidValue;    \
   }
 
-cudaError_t launch_move(const ipp_config& cfg, const uint32_t* episodes, const ipp_step_io& io, int32_t t, int do_comm,
+cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, cudaStream_t s) {
-  const int threads = 128;
-  const int blocks = (cfg.n_envs + threads - 1) / threads;
-  move_kernel<<<blocks, threads, 0, s>>>(cfg, episodes, io, t, do_comm, do_move);
+  plan_kernel<<<cfg.n_envs, PLAN_THREADS, 0, s>>>(cfg, st, io, t, do_comm, do_move);
   return cudaGetLastError();
 }
 
-cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, const int32_t* pos_in,
-                              const int32_t* pos_out, const uint8_t* comm, int32_t t, float* reward_rel,
-                              float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
+cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
+                              const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
+                              float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
   const dim3 grid((unsigned)plan.n_chunks * (unsigned)cfg.n_envs);
   if (do_own) {
     IPP_DISPATCH_A(cfg.n_agents, (step_dense_kernel<kA, true><<<grid, STEP_THREADS, 0, s>>>(
-                                     cfg, st, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials, plan.n_chunks,
-                                     plan.quads_per_chunk)));
+                                     cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
+                                     plan.n_chunks, plan.quads_per_chunk)));
   } else {
     IPP_DISPATCH_A(cfg.n_agents, (step_dense_kernel<kA, false><<<grid, STEP_THREADS, 0, s>>>(
-                                     cfg, st, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials, plan.n_chunks,
-                                     plan.quads_per_chunk)));
+                                     cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
+                                     plan.n_chunks, plan.quads_per_chunk)));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -444,14 +496,18 @@ cudaError_t launch_reward_finalize(const ipp_config& cfg, const double* partials
   return cudaGetLastError();
 }
 
-cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const int32_t* pos_out, int32_t t,
-                              cudaStream_t s) {
-  own_update_kernel<<<cfg.n_envs * cfg.n_agents, 256, 0, s>>>(cfg, st, pos_out, t);
+cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const float4* lut, const int32_t* pos_out,
+                              int32_t t, cudaStream_t s) {
+  const int32_t n_quads = (cfg.gx * cfg.gy + 3) >> 2;
+  int32_t bpe = (n_quads + 1023) / 1024;
+  if (bpe < 1) bpe = 1;
+  IPP_DISPATCH_A(cfg.n_agents,
+                 (own_update_kernel<kA><<<(unsigned)cfg.n_envs * (unsigned)bpe, 256, 0, s>>>(cfg, st, lut, pos_out, t, bpe)));
   return cudaGetLastError();
 }
 
-cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, int32_t* pos_out,
-                         int32_t* gt_params, cudaStream_t s) {
+cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
+                         int32_t* pos_out, int32_t* gt_params, cudaStream_t s) {
   const int threads = 128;
   const int n = cfg.n_envs * (cfg.n_agents + 1);
   reset_prep_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(cfg, st.episodes, pos_out, gt_params);
@@ -459,7 +515,7 @@ cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const Launc
   if (e != cudaSuccess) return e;
   const dim3 grid((unsigned)plan.n_chunks * (unsigned)cfg.n_envs);
   IPP_DISPATCH_A(cfg.n_agents, (reset_fill_kernel<kA><<<grid, STEP_THREADS, 0, s>>>(
-                                   cfg, st, pos_out, gt_params, plan.n_chunks, plan.quads_per_chunk)));
+                                   cfg, st, lut, pos_out, gt_params, plan.n_chunks, plan.quads_per_chunk)));
   return cudaGetLastError();
 }
 

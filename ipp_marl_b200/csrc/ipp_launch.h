@@ -10,7 +10,7 @@ namespace ipp {
 constexpr int STEP_THREADS = 256;   // direct-load variant: threads per (env, chunk) block
 constexpr int TMA_CONSUMERS = 640;  // TMA variant: 20 consumer warps ...
 constexpr int TMA_THREADS = TMA_CONSUMERS + 32;  // ... + 1 producer warp
-constexpr int TMA_STAGES = 4;
+constexpr int TMA_MAX_STAGES = 4;
 
 struct LaunchPlan {
   int32_t n_chunks;         // chunks per env map (1 => per-env reward finishes inside the block)
@@ -18,26 +18,27 @@ struct LaunchPlan {
 };
 
 struct TmaPlan {
-  int32_t n_chunks, quads_per_chunk, stage_bytes, smem_bytes;
+  int32_t n_chunks, quads_per_chunk, stage_bytes, smem_bytes, n_stages;
   bool ok;
 };
 
 TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin);
 
-cudaError_t launch_move(const ipp_config& cfg, const uint32_t* episodes, const ipp_step_io& io, int32_t t, int do_comm,
+// lut: device table [n_alt][256] float4 = odds multipliers of the 4 cells of a quad for a code byte
+cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, cudaStream_t s);
-cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, const int32_t* pos_in,
-                              const int32_t* pos_out, const uint8_t* comm, int32_t t, float* reward_rel,
-                              float* reward_abs, double* partials, bool do_own, cudaStream_t s);
-cudaError_t launch_step_tma(const ipp_config& cfg, const ipp_state& st, const TmaPlan& plan, int n_sm,
-                            const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
+cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
+                              const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
+                              float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s);
+cudaError_t launch_step_tma(const ipp_config& cfg, const ipp_state& st, const float4* lut, const TmaPlan& plan,
+                            int n_sm, const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
                             float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s);
 cudaError_t launch_reward_finalize(const ipp_config& cfg, const double* partials, int32_t n_chunks, float* reward_rel,
                                    float* reward_abs, cudaStream_t s);
-cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const int32_t* pos_out, int32_t t,
-                              cudaStream_t s);
-cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const LaunchPlan& plan, int32_t* pos_out,
-                         int32_t* gt_params, cudaStream_t s);
+cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const float4* lut, const int32_t* pos_out,
+                              int32_t t, cudaStream_t s);
+cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
+                         int32_t* pos_out, int32_t* gt_params, cudaStream_t s);
 
 // single-map helpers used by the facade entry points (device pointers)
 cudaError_t launch_update_cells(const ipp_config& cfg, float* x, const float* y, int y_is_scalar, float y_scalar,

@@ -125,12 +125,19 @@ class HostTables:
     def gt_stride(self):
         return (self.n_cells + 15) // 16 * 16
 
+    @property
+    def code_stride(self):
+        """Bytes of measurement codes per env: one byte per (quad, agent), 4 or 8 bytes per quad."""
+        per_quad = 4 if self.n_agents <= 4 else 8
+        return ((self.n_cells + 3) // 4 * per_quad + 15) // 16 * 16
+
 
 def make_config(tables, n_envs):
     """Fill the C struct ipp_config (include/ipp_b200.h) from the host tables."""
     t = tables
     c = N.IppConfig()
     c.gx, c.gy, c.map_stride, c.gt_stride = t.gx, t.gy, t.map_stride, t.gt_stride
+    c.code_stride = t.code_stride
     c.px, c.py, c.n_alt = t.px, t.py, t.n_alt
     c.n_agents, c.n_envs, c.spacing = t.n_agents, int(n_envs), t.spacing
     c.min_altitude, c.max_altitude = t.min_altitude, t.max_altitude

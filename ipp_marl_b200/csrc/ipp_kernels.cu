@@ -141,49 +141,63 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
   if (io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)stuck;
 }
 
-// Write the code bytes of measurement `m` (agent a) for every quad its footprint overlaps.
-// `codes` = this env's code row (AP bytes per quad), already zeroed.
-__device__ __forceinline__ void write_meas_codes(const ipp_config& cfg, const Meas& m, const int a, const int ap,
-                                                 const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
-                                                 const int tid, const int nthreads) {
+// OR the code bits of measurement `m` (agent a) into this env's (zeroed) code row.  One task per
+// (footprint row, quad overlapping that row): it contributes the bits of THAT row only, so a quad
+// that straddles two grid rows simply receives two contributions.
+__device__ __forceinline__ void or_meas_codes(const ipp_config& cfg, const Meas& m, const int a, const int ap,
+                                              const uint8_t* __restrict__ gt, uint32_t* __restrict__ codes32,
+                                              const int lane) {
   const int32_t h = m.xr - m.xl, w = m.yd - m.yu;
   if (h <= 0 || w <= 0) return;
   const int32_t per_row = (w + 3) / 4 + 1;  // upper bound of quads overlapping one footprint row
-  for (int32_t task = tid; task < h * per_row; task += nthreads) {
+  const int32_t word_per_quad = ap >> 2, word_of_a = a >> 2, shift = 8 * (a & 3);
+  for (int32_t task = lane; task < h * per_row; task += 32) {
     const int32_t r = task / per_row, k = task - r * per_row;
-    const int32_t row0 = (m.xl + r) * cfg.gy;
-    const int32_t q = ((row0 + m.yu) >> 2) + k;
-    if (q > ((row0 + m.yd - 1) >> 2)) continue;
+    const int32_t first = (m.xl + r) * cfg.gy + m.yu, last = first + w - 1;
+    const int32_t q = (first >> 2) + k;
+    if (q > (last >> 2)) continue;
     const int32_t c0 = q << 2;
+    const int32_t lo = max(first - c0, 0), hi = min(last + 1 - c0, 4);
+    const uint32_t in = (1u << hi) - (1u << lo);
     const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
-    // a quad straddling two rows is reached from both; both tasks compute the same full byte
-    codes[(int64_t)q * ap + a] = (uint8_t)meas_code_byte(cfg, m, c0, g4);
+    uint32_t seen = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool wrong = cell_hash(m.key, (uint32_t)(c0 + c)) < m.thresh;
+      const bool one = (((g4 >> (8 * c)) & 0xFFu) != 0u) != wrong;
+      seen |= (one ? 1u : 0u) << c;
+    }
+    atomicOr(&codes32[(int64_t)q * word_per_quad + word_of_a], (in | ((seen & in) << 4)) << shift);
   }
 }
 
-constexpr int PLAN_THREADS = 128;
+constexpr int PLAN_WARPS = 8;  // envs per block: one warp plans one env, no block-level barrier
 
-__global__ void __launch_bounds__(PLAN_THREADS)
+__global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
                 const int32_t do_comm, const int32_t do_move) {
-  const int32_t b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t b = blockIdx.x * PLAN_WARPS + warp;
+  if (b >= cfg.n_envs) return;
   const int32_t A = cfg.n_agents;
-  __shared__ int32_t s_npos[IPP_MAX_AGENTS][3];
-  __shared__ Meas s_meas[IPP_MAX_AGENTS];
+  __shared__ int32_t s_npos[PLAN_WARPS][IPP_MAX_AGENTS][3];
   const uint32_t ep = st.episodes[b];
-  const int tid = threadIdx.x;
-  if (tid == 0) plan_moves(cfg, b, ep, io, t, do_comm != 0, do_move != 0, s_npos);
-  if (!do_move) return;
   // codes of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
   uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
-  uint4* cz = reinterpret_cast<uint4*>(codes);
-  for (int32_t i = tid; i < (cfg.code_stride >> 4); i += PLAN_THREADS) cz[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  if (tid < A) s_meas[tid] = make_meas(cfg, s_npos[tid], ep, (uint32_t)tid, (uint32_t)t + 1u);
-  __syncthreads();
+  if (do_move) {
+    uint4* cz = reinterpret_cast<uint4*>(codes);
+    for (int32_t i = lane; i < (cfg.code_stride >> 4); i += 32) cz[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (lane == 0) plan_moves(cfg, b, ep, io, t, do_comm != 0, do_move != 0, s_npos[warp]);
+  if (!do_move) return;
+  __threadfence();  // the zeroed row is visible before any lane ORs into it
+  __syncwarp();
   const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
   const int ap = A <= 4 ? 4 : 8;
-  for (int a = 0; a < A; ++a) write_meas_codes(cfg, s_meas[a], a, ap, gt, codes, tid, PLAN_THREADS);
+  for (int a = 0; a < A; ++a) {
+    const Meas m = make_meas(cfg, s_npos[warp][a], ep, (uint32_t)a, (uint32_t)t + 1u);
+    or_meas_codes(cfg, m, a, ap, gt, reinterpret_cast<uint32_t*>(codes), lane);
+  }
 }
 
 // =================================================================================================
@@ -465,7 +479,8 @@ __global__ void __launch_bounds__(STEP_THREADS)
 
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, cudaStream_t s) {
-  plan_kernel<<<cfg.n_envs, PLAN_THREADS, 0, s>>>(cfg, st, io, t, do_comm, do_move);
+  plan_kernel<<<(cfg.n_envs + PLAN_WARPS - 1) / PLAN_WARPS, PLAN_WARPS * 32, 0, s>>>(cfg, st, io, t, do_comm,
+                                                                                     do_move);
   return cudaGetLastError();
 }
 

@@ -9,8 +9,7 @@ namespace ipp {
 
 constexpr int STEP_THREADS = 256;   // direct-load variant: threads per (env, chunk) block
 constexpr int TMA_CONSUMERS = 640;  // TMA variant: 20 consumer warps ...
-constexpr int TMA_THREADS = TMA_CONSUMERS + 32;  // ... + 1 producer warp
-constexpr int TMA_MAX_STAGES = 4;
+constexpr int TMA_THREADS = TMA_CONSUMERS + 64;  // ... + 1 producer warp + 1 storer warp
 
 struct LaunchPlan {
   int32_t n_chunks;         // chunks per env map (1 => per-env reward finishes inside the block)
@@ -18,7 +17,7 @@ struct LaunchPlan {
 };
 
 struct TmaPlan {
-  int32_t n_chunks, quads_per_chunk, stage_bytes, smem_bytes, n_stages;
+  int32_t n_chunks, quads_per_chunk, slot_bytes, env_bytes, d_map, d_env, smem_bytes;
   bool ok;
 };
 

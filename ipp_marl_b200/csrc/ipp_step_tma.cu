@@ -1,13 +1,20 @@
 // TMA-staged, warp-specialised, persistent variant of the map kernel (sm_100a).
 //
-// One CTA per SM walks the (env, chunk) work items with a 3-4 stage shared-memory ring:
-//   producer warp : per item, issues cp.async.bulk (TMA 1-D bulk copies, SASS UBLKCP) of the env's global
-//                   map, its A local maps and its two measurement-code rows into the stage; completion is
-//                   signalled on an mbarrier (expect_tx / complete_tx).
-//   20 consumer warps : update the maps in place in shared memory (ipp_cell.cuh), reduce the two
-//                   reward sums (warp shuffles + one named barrier), then one thread writes the maps
-//                   back with cp.async.bulk shared->global and releases the stage once the bulk
-//                   engine has finished reading it.
+// One CTA per SM walks the (env, chunk) work items.  A chunk is 640 quads (2560 cells): one quad per
+// consumer thread, so the 50x50 grid is a single chunk.  Shared memory holds two rings:
+//   * MAP slots (10 KB each, ~16 of them): one belief map of one item per slot;
+//   * ENV slots (4): the item's two measurement-code rows + its EnvMeta + the reward partial sums.
+// Roles (no block-wide barrier anywhere after start-up; everything is mbarrier based):
+//   producer warp : per item, writes EnvMeta, bulk-loads the code rows (-> env_full) and then the
+//                   item's A+1 maps, each into the next free map slot (cp.async.bulk, SASS UBLKCP,
+//                   completion on map_full via expect_tx / complete_tx);
+//   20 consumer warps : thread q owns quad q of the item for ALL its maps: it decodes the codes once
+//                   (QuadCtx in registers), then for each map waits map_full, updates its quad in
+//                   place (ipp_cell.cuh) and the warp arrives on map_done — a warp never waits for
+//                   the other warps;
+//   storer warp   : waits map_done, writes the slot back with cp.async.bulk shared->global, frees the
+//                   slot (map_empty) once the bulk engine has read it, and finishes the per-env
+//                   reward from the warps' partial sums.
 // HBM traffic is one read + one write of every belief map plus the code rows; all global addressing
 // is done by the TMA unit, so the SM issue slots go to the map arithmetic.
 #include "ipp_cell.cuh"
@@ -62,9 +69,6 @@ __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
 }  // namespace ptx
 
 template <int A>
@@ -73,167 +77,236 @@ struct StageMeta {
   int32_t b, chunk, nq, pad;
 };
 
-// Shared-memory layout: [n_stages][stage_bytes] | lut[n_alt*256] float4 | StageMeta[MAX] | mbarriers | reduction
-// One stage: (A+1) maps of qpc float4 | qpc*AP bytes codes (communicated) | qpc*AP bytes codes (after move)
+// Ring position helper: slot index + phase parity of a monotonically increasing counter.
+struct Ring {
+  int32_t slot;
+  uint32_t phase;
+  int32_t depth;
+  __device__ __forceinline__ Ring(int32_t d) : slot(0), phase(0), depth(d) {}
+  __device__ __forceinline__ void advance() {
+    if (++slot == depth) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+constexpr int TMA_STORE_LAG = 2;  // bulk-store groups allowed in flight before a map slot is recycled
+
+// Shared-memory layout:
+//   [d_map][slot_bytes] map slots | [d_env][env_bytes] code rows | lut[n_alt*256] float4 | StageMeta[d_env] |
+//   mbarriers: map_full[d_map] map_done[d_map] map_empty[d_map] env_full[d_env] env_done[d_env] |
+//   reward partials [d_env][2][NW] double
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
                     const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
                     const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
                     float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks,
-                    const int32_t qpc, const int32_t n_items, const int32_t stage_bytes, const int32_t n_stages) {
+                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes, const int32_t d_map,
+                    const int32_t d_env) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NW = TMA_CONSUMERS / 32;
   constexpr int AP = A <= 4 ? 4 : 8;
-  unsigned char* stages = smem;
-  float4* lut = reinterpret_cast<float4*>(smem + (size_t)n_stages * stage_bytes);
+  constexpr int QPC = TMA_CONSUMERS;  // quads per chunk = one per consumer thread
+  unsigned char* map_slots = smem;
+  unsigned char* env_slots = map_slots + (size_t)d_map * slot_bytes;
+  float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)d_env * env_bytes);
   StageMeta<A>* meta = reinterpret_cast<StageMeta<A>*>(lut + cfg.n_alt * 256);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + TMA_MAX_STAGES);  // full[MAX], empty[MAX]
-  double* red = reinterpret_cast<double*>(bars + 2 * TMA_MAX_STAGES);   // [2 parities][2 sums][NW]
+  uint64_t* map_full = reinterpret_cast<uint64_t*>(meta + d_env);
+  uint64_t* map_done = map_full + d_map;
+  uint64_t* map_empty = map_done + d_map;
+  uint64_t* env_full = map_empty + d_map;
+  uint64_t* env_done = env_full + d_env;
+  double* red = reinterpret_cast<double*>(env_done + d_env);  // [d_env][2][NW]
 
   const int32_t tid = threadIdx.x;
   const int32_t n_cells = cfg.gx * cfg.gy;
   const int32_t n_quads = (n_cells + 3) >> 2;
   const int64_t stride = cfg.map_stride;
-  const uint32_t code_off = (uint32_t)(A + 1) * (uint32_t)qpc * 16u;  // offset of the code rows in a stage
-  const uint32_t code_row = (uint32_t)qpc * AP;
+  const uint32_t code_row = (uint32_t)QPC * AP;
 
   if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars[s]), 1);                   // full: producer's arrive.expect_tx
-      ptx::mbar_init(ptx::smem_u32(&bars[TMA_MAX_STAGES + s]), 1);  // empty: consumer thread 0
+    for (int s = 0; s < d_map; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&map_full[s]), 1);    // producer's arrive.expect_tx
+      ptx::mbar_init(ptx::smem_u32(&map_done[s]), NW);   // one arrival per consumer warp
+      ptx::mbar_init(ptx::smem_u32(&map_empty[s]), 1);   // storer
+    }
+    for (int s = 0; s < d_env; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&env_full[s]), 1);        // producer
+      ptx::mbar_init(ptx::smem_u32(&env_done[s]), NW + 1);   // consumer warps + storer
     }
     ptx::fence_mbar_init();
   }
   for (int32_t i = tid; i < cfg.n_alt * 256; i += TMA_THREADS) lut[i] = lut_g[i];
   __syncthreads();
 
+  if (tid >= TMA_CONSUMERS + 32) {
+    // ================================================================== storer warp (one lane)
+    if (tid != TMA_CONSUMERS + 32) return;
+    Ring er(d_env), mr(d_map), freed(d_map);
+    int32_t n_committed = 0, n_freed = 0;  // bulk-store groups committed / map slots handed back
+    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      ptx::mbar_wait(ptx::smem_u32(&env_full[er.slot]), er.phase);
+      const StageMeta<A>& sm = meta[er.slot];
+      const int32_t b = sm.b, chunk = sm.chunk;
+      const uint32_t map_bytes = (uint32_t)sm.nq * 16u;
+      const int64_t cell0 = (int64_t)chunk * QPC * 4;
+#pragma unroll 1
+      for (int m = 0; m <= A; ++m) {
+        ptx::mbar_wait(ptx::smem_u32(&map_done[mr.slot]), mr.phase);
+        float* dst;
+        if (m == 0) {
+          const double* r = red + (size_t)er.slot * 2 * NW;
+          double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            t1 += r[w];
+            t2 += r[NW + w];
+          }
+          if (n_chunks == 1) {
+            write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
+          } else {
+            partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
+            partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
+          }
+          dst = st.global_map + (int64_t)b * stride + cell0;
+        } else {
+          dst = st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
+        }
+        ptx::bulk_store(dst, ptx::smem_u32(map_slots + (size_t)mr.slot * slot_bytes), map_bytes);
+        ptx::bulk_commit();
+        ++n_committed;
+        mr.advance();
+        ptx::bulk_wait_read<TMA_STORE_LAG>();  // all but the newest LAG groups have been read out of smem
+        while (n_freed < n_committed - TMA_STORE_LAG) {
+          ptx::mbar_arrive(ptx::smem_u32(&map_empty[freed.slot]));
+          freed.advance();
+          ++n_freed;
+        }
+      }
+      ptx::mbar_arrive(ptx::smem_u32(&env_done[er.slot]));
+      er.advance();
+    }
+    ptx::bulk_wait_read<0>();
+    ptx::bulk_wait<0>();  // all writes to global memory complete before the CTA retires
+    return;
+  }
+
   if (tid >= TMA_CONSUMERS) {
-    // ------------------------------------------------------------------ producer warp
+    // ================================================================== producer warp
     const int lane = tid - TMA_CONSUMERS;
-    int32_t k = 0, s = 0;
-    uint32_t ph = 0;
-    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-      ptx::mbar_wait(ptx::smem_u32(&bars[TMA_MAX_STAGES + s]), ph ^ 1u);
+    Ring er(d_env), mr(d_map);
+    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      ptx::mbar_wait(ptx::smem_u32(&env_done[er.slot]), er.phase ^ 1u);
       const int32_t b = item / n_chunks;
       const int32_t chunk = item - b * n_chunks;
-      const int32_t nq = min(qpc, n_quads - chunk * qpc);
-      load_env_meta<A>(cfg, &meta[s].env, lane, b, pos_in, pos_out, comm, DO_OWN);
+      const int32_t nq = min(QPC, n_quads - chunk * QPC);
+      load_env_meta<A>(cfg, &meta[er.slot].env, lane, b, pos_in, pos_out, comm, DO_OWN);
       if (lane == 0) {
-        meta[s].b = b;
-        meta[s].chunk = chunk;
-        meta[s].nq = nq;
+        meta[er.slot].b = b;
+        meta[er.slot].chunk = chunk;
+        meta[er.slot].nq = nq;
       }
       __syncwarp();
       if (lane == 0) {
-        const uint32_t full = ptx::smem_u32(&bars[s]);
-        const uint32_t map_bytes = (uint32_t)nq * 16u;
+        const uint32_t efull = ptx::smem_u32(&env_full[er.slot]);
         const uint32_t code_bytes = ((uint32_t)nq * AP + 15u) & ~15u;
-        ptx::mbar_arrive_expect_tx(full, map_bytes * (A + 1) + code_bytes * (DO_OWN ? 2u : 1u));
-        const uint32_t dst = ptx::smem_u32(stages + (size_t)s * stage_bytes);
-        const int64_t cell0 = (int64_t)chunk * qpc * 4;
-        ptx::bulk_load(dst, st.global_map + (int64_t)b * stride + cell0, map_bytes, full);
-#pragma unroll
-        for (int i = 0; i < A; ++i)
-          ptx::bulk_load(dst + (uint32_t)(1 + i) * (uint32_t)qpc * 16u,
-                         st.local_maps + ((int64_t)b * A + i) * stride + cell0, map_bytes, full);
-        const int64_t code0 = (int64_t)chunk * qpc * AP;
-        ptx::bulk_load(dst + code_off,
-                       st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0, code_bytes, full);
+        const uint32_t edst = ptx::smem_u32(env_slots + (size_t)er.slot * env_bytes);
+        const int64_t code0 = (int64_t)chunk * QPC * AP;
+        ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u));
+        ptx::bulk_load(edst, st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
+                       code_bytes, efull);
         if (DO_OWN)
-          ptx::bulk_load(dst + code_off + code_row,
+          ptx::bulk_load(edst + code_row,
                          st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
-                         code_bytes, full);
+                         code_bytes, efull);
+        const uint32_t map_bytes = (uint32_t)nq * 16u;
+        const int64_t cell0 = (int64_t)chunk * QPC * 4;
+#pragma unroll 1
+        for (int m = 0; m <= A; ++m) {
+          ptx::mbar_wait(ptx::smem_u32(&map_empty[mr.slot]), mr.phase ^ 1u);
+          const uint32_t mfull = ptx::smem_u32(&map_full[mr.slot]);
+          const float* src = (m == 0) ? st.global_map + (int64_t)b * stride + cell0
+                                      : st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
+          ptx::mbar_arrive_expect_tx(mfull, map_bytes);
+          ptx::bulk_load(ptx::smem_u32(map_slots + (size_t)mr.slot * slot_bytes), src, map_bytes, mfull);
+          mr.advance();
+        }
       }
-      if (++s == n_stages) { s = 0; ph ^= 1u; }
+      er.advance();
     }
     return;
   }
 
-  // -------------------------------------------------------------------- consumer warps
-  int32_t k = 0, s = 0, s_prev = 0;
-  uint32_t ph = 0;
-  for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
-    ptx::mbar_wait(ptx::smem_u32(&bars[s]), ph);
-    const StageMeta<A>& sm = meta[s];
-    const int32_t b = sm.b, chunk = sm.chunk, nq = sm.nq;
-    unsigned char* base = stages + (size_t)s * stage_bytes;
-    float4* maps = reinterpret_cast<float4*>(base);
-    const unsigned char* code_prev = base + code_off;
-    const unsigned char* code_next = base + code_off + code_row;
-
-    double s1 = 0.0, s2 = 0.0;
-    for (int32_t ql = tid; ql < nq; ql += TMA_CONSUMERS) {
-      QuadCtx<A> qc;
-      make_quad_ctx<A>(cfg, sm.env, load_code<A>(code_prev, ql), lut, qc);
-      CodeWord<A> next;
-      if (DO_OWN) next = load_code<A>(code_next, ql);
-      maps[ql] = update_global_quad<A>(cfg, qc, maps[ql], valid_mask4((chunk * qpc + ql) << 2, n_cells), s1, s2);
+  // ==================================================================== consumer warps
+  const int lane = tid & 31, warp = tid >> 5;
+  Ring er(d_env), mr(d_map);
+  for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    ptx::mbar_wait(ptx::smem_u32(&env_full[er.slot]), er.phase);
+    const StageMeta<A>& sm = meta[er.slot];
+    const bool have = tid < sm.nq;
+    const unsigned char* code_prev = env_slots + (size_t)er.slot * env_bytes;
+    const unsigned char* code_next = code_prev + code_row;
+    QuadCtx<A> qc;
+    CodeWord<A> next;
+    uint32_t valid = 0;
+    if (have) {
+      make_quad_ctx<A>(cfg, sm.env, load_code<A>(code_prev, tid), lut, qc);
+      if (DO_OWN) next = load_code<A>(code_next, tid);
+      valid = valid_mask4((sm.chunk * QPC + tid) << 2, n_cells);
+    }
+    // ---- global map ----
+    {
+      ptx::mbar_wait(ptx::smem_u32(&map_full[mr.slot]), mr.phase);
+      double s1 = 0.0, s2 = 0.0;
+      if (have) {
+        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)mr.slot * slot_bytes) + tid;
+        *mp = update_global_quad<A>(cfg, qc, *mp, valid, s1, s2);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        double* r = red + (size_t)er.slot * 2 * NW;
+        r[warp] = s1;
+        r[NW + warp] = s2;
+      }
+      ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&map_done[mr.slot]));
+      mr.advance();
+    }
+    // ---- local maps ----
 #pragma unroll
-      for (int i = 0; i < A; ++i) {
-        float4* mp = maps + (size_t)(1 + i) * qpc + ql;
+    for (int i = 0; i < A; ++i) {
+      ptx::mbar_wait(ptx::smem_u32(&map_full[mr.slot]), mr.phase);
+      if (have) {
+        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)mr.slot * slot_bytes) + tid;
         *mp = update_local_quad<A, DO_OWN>(cfg, sm.env, qc, i, DO_OWN ? next.byte(i) : 0u, lut, *mp);
       }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&map_done[mr.slot]));
+      mr.advance();
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    double* r = red + (size_t)(k & 1) * 2 * NW;
-    if ((tid & 31) == 0) {
-      r[tid >> 5] = s1;
-      r[NW + (tid >> 5)] = s2;
-    }
-    ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
-    ptx::named_bar_sync(1, TMA_CONSUMERS);
-    if (tid == 0) {
-      double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        t1 += r[w];
-        t2 += r[NW + w];
-      }
-      if (n_chunks == 1) {
-        write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
-      } else {
-        partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
-        partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
-      }
-      const uint32_t src = ptx::smem_u32(base);
-      const uint32_t map_bytes = (uint32_t)nq * 16u;
-      const int64_t cell0 = (int64_t)chunk * qpc * 4;
-      ptx::bulk_store(st.global_map + (int64_t)b * stride + cell0, src, map_bytes);
-#pragma unroll
-      for (int i = 0; i < A; ++i)
-        ptx::bulk_store(st.local_maps + ((int64_t)b * A + i) * stride + cell0,
-                        src + (uint32_t)(1 + i) * (uint32_t)qpc * 16u, map_bytes);
-      ptx::bulk_commit();
-      ptx::bulk_wait_read<1>();  // the previous item's stores have finished reading their stage
-      if (k > 0) ptx::mbar_arrive(ptx::smem_u32(&bars[TMA_MAX_STAGES + s_prev]));
-    }
-    s_prev = s;
-    if (++s == n_stages) { s = 0; ph ^= 1u; }
-  }
-  if (tid == 0) {
-    ptx::bulk_wait_read<0>();
-    if (k > 0) ptx::mbar_arrive(ptx::smem_u32(&bars[TMA_MAX_STAGES + s_prev]));
-    ptx::bulk_wait<0>();  // all writes to global memory complete before the CTA retires
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&env_done[er.slot]));
+    er.advance();
   }
 }
 
 // --------------------------------------------------------------------------------------------------
-static size_t tma_fixed_smem(int A, int n_alt) {
-  size_t meta = 0;
+static size_t stage_meta_bytes(int A) {
   switch (A) {
-    case 1: meta = sizeof(StageMeta<1>); break;
-    case 2: meta = sizeof(StageMeta<2>); break;
-    case 3: meta = sizeof(StageMeta<3>); break;
-    case 4: meta = sizeof(StageMeta<4>); break;
-    case 5: meta = sizeof(StageMeta<5>); break;
-    case 6: meta = sizeof(StageMeta<6>); break;
-    case 7: meta = sizeof(StageMeta<7>); break;
-    default: meta = sizeof(StageMeta<8>); break;
+    case 1: return sizeof(StageMeta<1>);
+    case 2: return sizeof(StageMeta<2>);
+    case 3: return sizeof(StageMeta<3>);
+    case 4: return sizeof(StageMeta<4>);
+    case 5: return sizeof(StageMeta<5>);
+    case 6: return sizeof(StageMeta<6>);
+    case 7: return sizeof(StageMeta<7>);
+    default: return sizeof(StageMeta<8>);
   }
-  return (size_t)n_alt * 256 * sizeof(float4) + TMA_MAX_STAGES * meta + 2 * TMA_MAX_STAGES * sizeof(uint64_t) +
-         2 * 2 * (TMA_CONSUMERS / 32) * sizeof(double) + 128;
 }
 
 TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
@@ -241,26 +314,19 @@ TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
   const int A = cfg.n_agents;
   const int ap = A <= 4 ? 4 : 8;
   const int n_quads = (cfg.gx * cfg.gy + 3) >> 2;
-  const int per_quad = 16 * (A + 1) + 2 * ap;
-  const int fixed = (int)tma_fixed_smem(A, cfg.n_alt);
-  const int avail = max_smem_optin - fixed;
-  // whole env in one stage if 3 stages of it fit (per-env reward finishes in the CTA); else 4 stages of chunks
-  int stages = TMA_MAX_STAGES;
-  int qpc = ((avail / stages) / per_quad) & ~3;
-  const int whole = (n_quads + 3) & ~3;
-  if (qpc >= whole) {
-    qpc = whole;
-  } else if ((((avail / 3) / per_quad) & ~3) >= whole) {
-    stages = 3;
-    qpc = whole;
-  }
-  p.n_stages = stages;
-  p.quads_per_chunk = qpc;
-  p.ok = avail > 0 && qpc >= 4;
-  p.n_chunks = p.ok ? (n_quads + qpc - 1) / qpc : 0;
-  p.stage_bytes = ((qpc * per_quad) + 127) & ~127;
-  p.smem_bytes = stages * p.stage_bytes + fixed;
-  p.ok = p.ok && p.smem_bytes <= max_smem_optin;
+  p.quads_per_chunk = TMA_CONSUMERS;
+  p.n_chunks = (n_quads + TMA_CONSUMERS - 1) / TMA_CONSUMERS;
+  p.slot_bytes = TMA_CONSUMERS * 16;                              // 10 KB, 128-byte multiple
+  p.env_bytes = (2 * TMA_CONSUMERS * ap + 127) & ~127;
+  p.d_env = 4;
+  const int nw = TMA_CONSUMERS / 32;
+  const int fixed = cfg.n_alt * 256 * 16 + p.d_env * (p.env_bytes + (int)stage_meta_bytes(A) + 2 * nw * 8 + 16) + 256;
+  int d_map = (max_smem_optin - fixed) / (p.slot_bytes + 3 * 8);
+  if (d_map > 24) d_map = 24;
+  p.d_map = d_map;
+  p.smem_bytes = fixed + d_map * (p.slot_bytes + 3 * 8);
+  // at least one whole item + the store lag + one slot of prefetch
+  p.ok = d_map >= (A + 1) + TMA_STORE_LAG + 1 && p.smem_bytes <= max_smem_optin;
   return p;
 }
 
@@ -278,8 +344,8 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
   const int n_items = cfg.n_envs * plan.n_chunks;
   const int grid = n_items < n_sm ? n_items : n_sm;
   kern<<<grid, TMA_THREADS, plan.smem_bytes, s>>>(cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs,
-                                                   partials, plan.n_chunks, plan.quads_per_chunk, n_items,
-                                                   plan.stage_bytes, plan.n_stages);
+                                                   partials, plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes,
+                                                   plan.d_map, plan.d_env);
   return cudaGetLastError();
 }
 

@@ -188,7 +188,28 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
     uint4* cz = reinterpret_cast<uint4*>(codes);
     for (int32_t i = lane; i < (cfg.code_stride >> 4); i += 32) cz[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (lane == 0) plan_moves(cfg, b, ep, io, t, do_comm != 0, do_move != 0, s_npos[warp]);
+  if (do_comm && io.comm_out != nullptr) {
+    // comm matrix, one ordered pair (i, j) per lane: agent/communication_log.py:39-58
+    const int32_t rows_per_round = 32 / A;  // whole rows of the A x A matrix per ballot
+    for (int32_t row0 = 0; row0 < A; row0 += rows_per_round) {
+      const int32_t rows_here = min(rows_per_round, A - row0);
+      bool ok = false;
+      if (lane < rows_here * A) {
+        const int32_t i = row0 + lane / A, j = lane % A;
+        const int32_t* pi = io.pos_in + ((int64_t)b * A + i) * 3;
+        const int32_t* pj = io.pos_in + ((int64_t)b * A + j) * 3;
+        const int32_t dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+        const int32_t d2 = dx * dx + dy * dy + dz * dz;
+        const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)i, (uint32_t)t, PURPOSE_COMM);
+        const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;  // drawn for every ordered pair (:46)
+        ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
+      }
+      const uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok);
+      if (lane < rows_here)  // lane r writes row row0 + r
+        io.comm_out[(int64_t)b * A + row0 + lane] = (uint8_t)((bits >> (lane * A)) & ((1u << A) - 1u));
+    }
+  }
+  if (lane == 0) plan_moves(cfg, b, ep, io, t, false, do_move != 0, s_npos[warp]);
   if (!do_move) return;
   __threadfence();  // the zeroed row is visible before any lane ORs into it
   __syncwarp();

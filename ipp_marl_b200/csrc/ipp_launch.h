@@ -8,8 +8,9 @@
 namespace ipp {
 
 constexpr int STEP_THREADS = 256;   // direct-load variant: threads per (env, chunk) block
-constexpr int TMA_CONSUMERS = 640;  // TMA variant: 20 consumer warps ...
-constexpr int TMA_THREADS = TMA_CONSUMERS + 64;  // ... + 1 producer warp + 1 storer warp
+constexpr int TMA_QPC = 640;             // TMA variant: quads per work item (20 tiles of 32 quads, 10 KB per map)
+constexpr int TMA_CONSUMER_WARPS = 26;   // consumer warps pulling (item, tile) tasks ...
+constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 2) * 32;  // ... + 1 producer warp + 1 storer warp
 
 struct LaunchPlan {
   int32_t n_chunks;         // chunks per env map (1 => per-env reward finishes inside the block)

@@ -1,20 +1,20 @@
 // TMA-staged, warp-specialised, persistent variant of the map kernel (sm_100a).
 //
-// One CTA per SM walks the (env, chunk) work items.  A chunk is 640 quads (2560 cells): one quad per
-// consumer thread, so the 50x50 grid is a single chunk.  Shared memory holds two rings:
-//   * MAP slots (10 KB each, ~16 of them): one belief map of one item per slot;
-//   * ENV slots (4): the item's two measurement-code rows + its EnvMeta + the reward partial sums.
+// One CTA per SM walks the (env, chunk) work items.  A chunk is 640 quads (2560 cells) = 20 TILES of
+// 32 quads, so the 50x50 grid is a single chunk.  Shared memory holds two rings:
+//   * 16 MAP slots of 10 KB: one belief map of one item per slot;
+//   * 4 ENV slots: the item's two measurement-code rows + its EnvMeta + the reward partial sums.
 // Roles (no block-wide barrier anywhere after start-up; everything is mbarrier based):
 //   producer warp : per item, writes EnvMeta, bulk-loads the code rows (-> env_full) and then the
 //                   item's A+1 maps, each into the next free map slot (cp.async.bulk, SASS UBLKCP,
 //                   completion on map_full via expect_tx / complete_tx);
-//   20 consumer warps : thread q owns quad q of the item for ALL its maps: it decodes the codes once
-//                   (QuadCtx in registers), then for each map waits map_full, updates its quad in
-//                   place (ipp_cell.cuh) and the warp arrives on map_done — a warp never waits for
-//                   the other warps;
+//   consumer warps: pull (item, tile) tasks from a shared counter (dynamic load balance: footprints make
+//                   the work per tile very uneven).  A warp decodes the tile's codes once (QuadCtx in
+//                   registers), then for each of the item's maps waits map_full, updates its 32 quads
+//                   in place (ipp_cell.cuh) and arrives on map_done — it never waits for other warps;
 //   storer warp   : waits map_done, writes the slot back with cp.async.bulk shared->global, frees the
 //                   slot (map_empty) once the bulk engine has read it, and finishes the per-env
-//                   reward from the warps' partial sums.
+//                   reward from the tiles' partial sums.
 // HBM traffic is one read + one write of every belief map plus the code rows; all global addressing
 // is done by the TMA unit, so the SM issue slots go to the map arithmetic.
 #include "ipp_cell.cuh"
@@ -77,48 +77,40 @@ struct StageMeta {
   int32_t b, chunk, nq, pad;
 };
 
-// Ring position helper: slot index + phase parity of a monotonically increasing counter.
-struct Ring {
-  int32_t slot;
-  uint32_t phase;
-  int32_t depth;
-  __device__ __forceinline__ Ring(int32_t d) : slot(0), phase(0), depth(d) {}
-  __device__ __forceinline__ void advance() {
-    if (++slot == depth) {
-      slot = 0;
-      phase ^= 1u;
-    }
-  }
-};
-
+constexpr int TMA_D_MAP = 16;     // map slots (power of two: slot / phase of a counter by shift & mask)
+constexpr int TMA_D_ENV = 4;      // env slots
 constexpr int TMA_STORE_LAG = 2;  // bulk-store groups allowed in flight before a map slot is recycled
+constexpr int TMA_NT = TMA_QPC / 32;  // tiles per item
 
 // Shared-memory layout:
-//   [d_map][slot_bytes] map slots | [d_env][env_bytes] code rows | lut[n_alt*256] float4 | StageMeta[d_env] |
-//   mbarriers: map_full[d_map] map_done[d_map] map_empty[d_map] env_full[d_env] env_done[d_env] |
-//   reward partials [d_env][2][NW] double
+//   [D_MAP][slot_bytes] map slots | [D_ENV][env_bytes] code rows | lut[n_alt*256] float4 | StageMeta[D_ENV] |
+//   mbarriers: map_full[D_MAP] map_done[D_MAP] map_empty[D_MAP] env_full[D_ENV] env_done[D_ENV] |
+//   reward partials [D_ENV][2][NT] double | tile counter
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
                     const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
                     const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
                     float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks,
-                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes, const int32_t d_map,
-                    const int32_t d_env) {
+                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int NW = TMA_CONSUMERS / 32;
+  constexpr int NT = TMA_NT;
   constexpr int AP = A <= 4 ? 4 : 8;
-  constexpr int QPC = TMA_CONSUMERS;  // quads per chunk = one per consumer thread
+  constexpr int QPC = TMA_QPC;
+  constexpr int CONSUMER_THREADS = TMA_CONSUMER_WARPS * 32;
   unsigned char* map_slots = smem;
-  unsigned char* env_slots = map_slots + (size_t)d_map * slot_bytes;
-  float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)d_env * env_bytes);
+  unsigned char* env_slots = map_slots + (size_t)TMA_D_MAP * slot_bytes;
+  float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)TMA_D_ENV * env_bytes);
   StageMeta<A>* meta = reinterpret_cast<StageMeta<A>*>(lut + cfg.n_alt * 256);
-  uint64_t* map_full = reinterpret_cast<uint64_t*>(meta + d_env);
-  uint64_t* map_done = map_full + d_map;
-  uint64_t* map_empty = map_done + d_map;
-  uint64_t* env_full = map_empty + d_map;
-  uint64_t* env_done = env_full + d_env;
-  double* red = reinterpret_cast<double*>(env_done + d_env);  // [d_env][2][NW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + TMA_D_ENV);
+  double* red = reinterpret_cast<double*>(bars + 3 * TMA_D_MAP + 2 * TMA_D_ENV);  // [D_ENV][2][NT]
+  uint32_t* tile_counter = reinterpret_cast<uint32_t*>(red + TMA_D_ENV * 2 * NT);
+  // 32-bit shared addresses of the barrier arrays (8 bytes per barrier)
+  const uint32_t map_full = ptx::smem_u32(bars);
+  const uint32_t map_done = map_full + 8u * TMA_D_MAP;
+  const uint32_t map_empty = map_done + 8u * TMA_D_MAP;
+  const uint32_t env_full = map_empty + 8u * TMA_D_MAP;
+  const uint32_t env_done = env_full + 8u * TMA_D_ENV;
 
   const int32_t tid = threadIdx.x;
   const int32_t n_cells = cfg.gx * cfg.gy;
@@ -127,42 +119,44 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   const uint32_t code_row = (uint32_t)QPC * AP;
 
   if (tid == 0) {
-    for (int s = 0; s < d_map; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&map_full[s]), 1);    // producer's arrive.expect_tx
-      ptx::mbar_init(ptx::smem_u32(&map_done[s]), NW);   // one arrival per consumer warp
-      ptx::mbar_init(ptx::smem_u32(&map_empty[s]), 1);   // storer
+    for (int s = 0; s < TMA_D_MAP; ++s) {
+      ptx::mbar_init(map_full + 8u * s, 1);    // producer's arrive.expect_tx
+      ptx::mbar_init(map_done + 8u * s, NT);   // one arrival per tile
+      ptx::mbar_init(map_empty + 8u * s, 1);   // storer
     }
-    for (int s = 0; s < d_env; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&env_full[s]), 1);        // producer
-      ptx::mbar_init(ptx::smem_u32(&env_done[s]), NW + 1);   // consumer warps + storer
+    for (int s = 0; s < TMA_D_ENV; ++s) {
+      ptx::mbar_init(env_full + 8u * s, 1);       // producer
+      ptx::mbar_init(env_done + 8u * s, NT + 1);  // tiles + storer
     }
+    *tile_counter = 0u;
     ptx::fence_mbar_init();
   }
   for (int32_t i = tid; i < cfg.n_alt * 256; i += TMA_THREADS) lut[i] = lut_g[i];
   __syncthreads();
 
-  if (tid >= TMA_CONSUMERS + 32) {
+  if (tid >= CONSUMER_THREADS + 32) {
     // ================================================================== storer warp (one lane)
-    if (tid != TMA_CONSUMERS + 32) return;
-    Ring er(d_env), mr(d_map), freed(d_map);
-    int32_t n_committed = 0, n_freed = 0;  // bulk-store groups committed / map slots handed back
-    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-      ptx::mbar_wait(ptx::smem_u32(&env_full[er.slot]), er.phase);
-      const StageMeta<A>& sm = meta[er.slot];
+    if (tid != CONSUMER_THREADS + 32) return;
+    uint32_t k = 0, g = 0, n_freed = 0;  // items done, bulk-store groups committed, map slots handed back
+    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
+      ptx::mbar_wait(env_full + 8u * es, pe);
+      const StageMeta<A>& sm = meta[es];
       const int32_t b = sm.b, chunk = sm.chunk;
       const uint32_t map_bytes = (uint32_t)sm.nq * 16u;
       const int64_t cell0 = (int64_t)chunk * QPC * 4;
 #pragma unroll 1
       for (int m = 0; m <= A; ++m) {
-        ptx::mbar_wait(ptx::smem_u32(&map_done[mr.slot]), mr.phase);
+        const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
+        ptx::mbar_wait(map_done + 8u * ms, pm);
         float* dst;
         if (m == 0) {
-          const double* r = red + (size_t)er.slot * 2 * NW;
+          const double* r = red + (size_t)es * 2 * NT;
           double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-          for (int w = 0; w < NW; ++w) {
+          for (int w = 0; w < NT; ++w) {
             t1 += r[w];
-            t2 += r[NW + w];
+            t2 += r[NT + w];
           }
           if (n_chunks == 1) {
             write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
@@ -174,45 +168,51 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         } else {
           dst = st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
         }
-        ptx::bulk_store(dst, ptx::smem_u32(map_slots + (size_t)mr.slot * slot_bytes), map_bytes);
+        ptx::bulk_store(dst, ptx::smem_u32(map_slots + (size_t)ms * slot_bytes), map_bytes);
         ptx::bulk_commit();
-        ++n_committed;
-        mr.advance();
+        ++g;
         ptx::bulk_wait_read<TMA_STORE_LAG>();  // all but the newest LAG groups have been read out of smem
-        while (n_freed < n_committed - TMA_STORE_LAG) {
-          ptx::mbar_arrive(ptx::smem_u32(&map_empty[freed.slot]));
-          freed.advance();
+        while (n_freed + TMA_STORE_LAG < g) {
+          ptx::mbar_arrive(map_empty + 8u * (n_freed & (TMA_D_MAP - 1)));
           ++n_freed;
         }
       }
-      ptx::mbar_arrive(ptx::smem_u32(&env_done[er.slot]));
-      er.advance();
+      ptx::mbar_arrive(env_done + 8u * es);
     }
     ptx::bulk_wait_read<0>();
     ptx::bulk_wait<0>();  // all writes to global memory complete before the CTA retires
     return;
   }
 
-  if (tid >= TMA_CONSUMERS) {
+  if (tid >= CONSUMER_THREADS) {
     // ================================================================== producer warp
-    const int lane = tid - TMA_CONSUMERS;
-    Ring er(d_env), mr(d_map);
-    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-      ptx::mbar_wait(ptx::smem_u32(&env_done[er.slot]), er.phase ^ 1u);
+    const int lane = tid - CONSUMER_THREADS;
+    uint32_t k = 0, g = 0;
+    for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
+      ptx::mbar_wait(env_done + 8u * es, pe ^ 1u);
       const int32_t b = item / n_chunks;
       const int32_t chunk = item - b * n_chunks;
       const int32_t nq = min(QPC, n_quads - chunk * QPC);
-      load_env_meta<A>(cfg, &meta[er.slot].env, lane, b, pos_in, pos_out, comm, DO_OWN);
+      load_env_meta<A>(cfg, &meta[es].env, lane, b, pos_in, pos_out, comm, DO_OWN);
       if (lane == 0) {
-        meta[er.slot].b = b;
-        meta[er.slot].chunk = chunk;
-        meta[er.slot].nq = nq;
+        meta[es].b = b;
+        meta[es].chunk = chunk;
+        meta[es].nq = nq;
       }
       __syncwarp();
       if (lane == 0) {
-        const uint32_t efull = ptx::smem_u32(&env_full[er.slot]);
+        // Consumers pick (item, tile) tasks dynamically, so a warp may skip whole items and then wait on a
+        // map slot by phase PARITY.  That is only sound if the slot's previous use has already been loaded:
+        // before publishing item k, make sure every map load of items <= k-2 has landed (they were issued
+        // two items ago, so this never stalls in practice).  Covers A <= 7 with 16 slots; A = 8 is static.
+        if (k >= 2) {
+          for (uint32_t gg = (k - 2) * (A + 1); gg < (k - 1) * (A + 1); ++gg)
+            ptx::mbar_wait(map_full + 8u * (gg & (TMA_D_MAP - 1)), (gg / TMA_D_MAP) & 1u);
+        }
+        const uint32_t efull = env_full + 8u * es;
         const uint32_t code_bytes = ((uint32_t)nq * AP + 15u) & ~15u;
-        const uint32_t edst = ptx::smem_u32(env_slots + (size_t)er.slot * env_bytes);
+        const uint32_t edst = ptx::smem_u32(env_slots + (size_t)es * env_bytes);
         const int64_t code0 = (int64_t)chunk * QPC * AP;
         ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u));
         ptx::bulk_load(edst, st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
@@ -224,74 +224,93 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         const uint32_t map_bytes = (uint32_t)nq * 16u;
         const int64_t cell0 = (int64_t)chunk * QPC * 4;
 #pragma unroll 1
-        for (int m = 0; m <= A; ++m) {
-          ptx::mbar_wait(ptx::smem_u32(&map_empty[mr.slot]), mr.phase ^ 1u);
-          const uint32_t mfull = ptx::smem_u32(&map_full[mr.slot]);
+        for (int m = 0; m <= A; ++m, ++g) {
+          const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
+          ptx::mbar_wait(map_empty + 8u * ms, pm ^ 1u);
           const float* src = (m == 0) ? st.global_map + (int64_t)b * stride + cell0
                                       : st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
-          ptx::mbar_arrive_expect_tx(mfull, map_bytes);
-          ptx::bulk_load(ptx::smem_u32(map_slots + (size_t)mr.slot * slot_bytes), src, map_bytes, mfull);
-          mr.advance();
+          ptx::mbar_arrive_expect_tx(map_full + 8u * ms, map_bytes);
+          ptx::bulk_load(ptx::smem_u32(map_slots + (size_t)ms * slot_bytes), src, map_bytes, map_full + 8u * ms);
         }
       }
-      er.advance();
     }
     return;
   }
 
   // ==================================================================== consumer warps
-  const int lane = tid & 31, warp = tid >> 5;
-  Ring er(d_env), mr(d_map);
-  for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    ptx::mbar_wait(ptx::smem_u32(&env_full[er.slot]), er.phase);
-    const StageMeta<A>& sm = meta[er.slot];
-    const bool have = tid < sm.nq;
-    const unsigned char* code_prev = env_slots + (size_t)er.slot * env_bytes;
+  const int lane = tid & 31;
+  const uint32_t my_items = (blockIdx.x < (uint32_t)n_items)
+                                ? (uint32_t)(n_items - (int32_t)blockIdx.x + (int32_t)gridDim.x - 1) / gridDim.x
+                                : 0u;
+  const uint32_t total_tiles = my_items * NT;
+  constexpr bool kDynamic = (2 * A <= 14);  // see the producer's comment on phase parity
+  const uint32_t warp = (uint32_t)tid >> 5;
+  uint32_t n_static = warp;
+  while (true) {
+    uint32_t n;
+    if (kDynamic) {
+      n = 0;
+      if (lane == 0) n = atomicAdd(tile_counter, 1u);
+      n = __shfl_sync(0xFFFFFFFFu, n, 0);
+    } else {  // warp w owns tile w of every item (warps >= NT idle): every barrier is waited in order
+      if (warp >= (uint32_t)NT) break;
+      n = n_static;
+      n_static += NT;
+    }
+    if (n >= total_tiles) break;
+    const uint32_t k = n / NT, tile = n - k * NT;
+    const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
+    ptx::mbar_wait(env_full + 8u * es, pe);
+    const StageMeta<A>& sm = meta[es];
+    const int32_t ql = (int32_t)tile * 32 + lane;
+    const bool have = ql < sm.nq;
+    const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
     const unsigned char* code_next = code_prev + code_row;
     QuadCtx<A> qc;
     CodeWord<A> next;
     uint32_t valid = 0;
     if (have) {
-      make_quad_ctx<A>(cfg, sm.env, load_code<A>(code_prev, tid), lut, qc);
-      if (DO_OWN) next = load_code<A>(code_next, tid);
-      valid = valid_mask4((sm.chunk * QPC + tid) << 2, n_cells);
+      make_quad_ctx<A>(cfg, sm.env, load_code<A>(code_prev, ql), lut, qc);
+      if (DO_OWN) next = load_code<A>(code_next, ql);
+      valid = valid_mask4((sm.chunk * QPC + ql) << 2, n_cells);
     }
+    uint32_t g = k * (A + 1);
     // ---- global map ----
     {
-      ptx::mbar_wait(ptx::smem_u32(&map_full[mr.slot]), mr.phase);
+      const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
+      ptx::mbar_wait(map_full + 8u * ms, pm);
       double s1 = 0.0, s2 = 0.0;
       if (have) {
-        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)mr.slot * slot_bytes) + tid;
+        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
         *mp = update_global_quad<A>(cfg, qc, *mp, valid, s1, s2);
       }
       s1 = warp_sum(s1);
       s2 = warp_sum(s2);
       if (lane == 0) {
-        double* r = red + (size_t)er.slot * 2 * NW;
-        r[warp] = s1;
-        r[NW + warp] = s2;
+        double* r = red + (size_t)es * 2 * NT;
+        r[tile] = s1;
+        r[NT + tile] = s2;
       }
       ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&map_done[mr.slot]));
-      mr.advance();
+      if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
+      ++g;
     }
     // ---- local maps ----
 #pragma unroll
-    for (int i = 0; i < A; ++i) {
-      ptx::mbar_wait(ptx::smem_u32(&map_full[mr.slot]), mr.phase);
+    for (int i = 0; i < A; ++i, ++g) {
+      const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
+      ptx::mbar_wait(map_full + 8u * ms, pm);
       if (have) {
-        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)mr.slot * slot_bytes) + tid;
+        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
         *mp = update_local_quad<A, DO_OWN>(cfg, sm.env, qc, i, DO_OWN ? next.byte(i) : 0u, lut, *mp);
       }
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&map_done[mr.slot]));
-      mr.advance();
+      if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
     }
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&env_done[er.slot]));
-    er.advance();
+    if (lane == 0) ptx::mbar_arrive(env_done + 8u * es);
   }
 }
 
@@ -314,19 +333,17 @@ TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
   const int A = cfg.n_agents;
   const int ap = A <= 4 ? 4 : 8;
   const int n_quads = (cfg.gx * cfg.gy + 3) >> 2;
-  p.quads_per_chunk = TMA_CONSUMERS;
-  p.n_chunks = (n_quads + TMA_CONSUMERS - 1) / TMA_CONSUMERS;
-  p.slot_bytes = TMA_CONSUMERS * 16;                              // 10 KB, 128-byte multiple
-  p.env_bytes = (2 * TMA_CONSUMERS * ap + 127) & ~127;
-  p.d_env = 4;
-  const int nw = TMA_CONSUMERS / 32;
-  const int fixed = cfg.n_alt * 256 * 16 + p.d_env * (p.env_bytes + (int)stage_meta_bytes(A) + 2 * nw * 8 + 16) + 256;
-  int d_map = (max_smem_optin - fixed) / (p.slot_bytes + 3 * 8);
-  if (d_map > 24) d_map = 24;
-  p.d_map = d_map;
-  p.smem_bytes = fixed + d_map * (p.slot_bytes + 3 * 8);
-  // at least one whole item + the store lag + one slot of prefetch
-  p.ok = d_map >= (A + 1) + TMA_STORE_LAG + 1 && p.smem_bytes <= max_smem_optin;
+  p.quads_per_chunk = TMA_QPC;
+  p.n_chunks = (n_quads + TMA_QPC - 1) / TMA_QPC;
+  p.slot_bytes = TMA_QPC * 16;  // 10 KB, 128-byte multiple
+  p.env_bytes = (2 * TMA_QPC * ap + 127) & ~127;
+  p.d_env = TMA_D_ENV;
+  p.d_map = TMA_D_MAP;
+  p.smem_bytes = TMA_D_MAP * p.slot_bytes + TMA_D_ENV * p.env_bytes + cfg.n_alt * 256 * 16 +
+                 TMA_D_ENV * (int)stage_meta_bytes(A) + (3 * TMA_D_MAP + 2 * TMA_D_ENV) * 8 +
+                 TMA_D_ENV * 2 * TMA_NT * 8 + 16 + 128;
+  // one whole item + the store lag + at least one slot of prefetch must fit in the map ring
+  p.ok = TMA_D_MAP >= (A + 1) + TMA_STORE_LAG + 1 && p.smem_bytes <= max_smem_optin;
   return p;
 }
 
@@ -344,8 +361,7 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
   const int n_items = cfg.n_envs * plan.n_chunks;
   const int grid = n_items < n_sm ? n_items : n_sm;
   kern<<<grid, TMA_THREADS, plan.smem_bytes, s>>>(cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs,
-                                                   partials, plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes,
-                                                   plan.d_map, plan.d_env);
+                                                   partials, plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes);
   return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@ namespace ipp {
 template <int A>
 struct EnvMeta {
   uint32_t comm[A];      // bit j: agent i fuses agent j's measurement (own bit cleared)
+  uint32_t comm4[A];     // the same, one nibble (0xF) per enabled peer: mask for QuadCtx::in_prev
   uint32_t lut_prev[A];  // float4 index of the LUT row (altitude) of agent j's communicated measurement
   uint32_t lut_next[A];  // same for the measurement after the move
 };
@@ -39,7 +40,12 @@ __device__ __forceinline__ void load_env_meta(const ipp_config& cfg, EnvMeta<A>*
   if (lane_or_tid < A) {
     const int a = lane_or_tid;
     m->lut_prev[a] = lut_row(cfg, pos_in + ((int64_t)b * A + a) * 3);
-    m->comm[a] = (uint32_t)comm[(int64_t)b * A + a] & ~(1u << a);  // own measurement already used
+    const uint32_t en = (uint32_t)comm[(int64_t)b * A + a] & ~(1u << a);  // own measurement already used
+    uint32_t en4 = 0;
+    for (int j = 0; j < A; ++j)
+      if ((en >> j) & 1u) en4 |= 0xFu << (4 * j);
+    m->comm[a] = en;
+    m->comm4[a] = en4;
   } else if (lane_or_tid < 2 * A) {
     const int a = lane_or_tid - A;
     m->lut_next[a] = do_own ? lut_row(cfg, pos_out + ((int64_t)b * A + a) * 3) : 0u;
@@ -178,14 +184,15 @@ __device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMe
 // ------------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadCtx<A>& q, const F4 p,
-                                              const uint32_t en, const uint32_t own, const F4 k_own, F4& pc_out,
-                                              uint32_t& touched) {
+                                              const uint32_t en, const uint32_t en4, const uint32_t own,
+                                              const F4 k_own, F4& pc_out, uint32_t& touched) {
   const bool kout_one = (cfg.k_out == 1.0f);
   const bool any_fuse = en != 0u;
-  uint32_t t = own;
-#pragma unroll
-  for (int j = 0; j < A; ++j)
-    if ((en >> j) & 1u) t |= (q.in_prev >> (4 * j)) & 0xFu;
+  uint32_t x = q.in_prev & en4;  // footprint nibbles of the enabled passes, OR-folded into one nibble
+  if (A > 4) x |= x >> 16;
+  if (A > 2) x |= x >> 8;
+  if (A > 1) x |= x >> 4;
+  uint32_t t = (x & 0xFu) | own;
   if (any_fuse && !kout_one) t = 0xFu;
   touched = t;
   if (t == 0u && !any_fuse) {  // nothing happens to this quad of this map
@@ -245,7 +252,7 @@ __device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, cons
   F4 pc;
   uint32_t touched;
   const F4 p = f4_from(p4);
-  const F4 pn = update_map_quad<A>(cfg, q, p, (1u << A) - 1u, 0u, f4_splat(1.0f), pc, touched);
+  const F4 pn = update_map_quad<A>(cfg, q, p, (1u << A) - 1u, 0xFFFFFFFFu, 0u, f4_splat(1.0f), pc, touched);
   float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -278,7 +285,7 @@ __device__ __forceinline__ float4 update_local_quad(const ipp_config& cfg, const
   }
   F4 pc;
   uint32_t touched;
-  return f4_to(update_map_quad<A>(cfg, q, f4_from(p4), meta.comm[i], own, k_own, pc, touched));
+  return f4_to(update_map_quad<A>(cfg, q, f4_from(p4), meta.comm[i], meta.comm4[i], own, k_own, pc, touched));
 }
 
 __device__ __forceinline__ uint32_t valid_mask4(int32_t c0, int32_t n_cells) {

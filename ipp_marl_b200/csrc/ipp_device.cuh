@@ -85,30 +85,41 @@ __device__ __forceinline__ uint32_t rect_mask4(const Meas& m, int32_t x0, int32_
   return mask;
 }
 
+// 4-bit "seen as 1" mask of the quad starting at cell c0 (c0 % 4 == 0) for measurement stream `key`:
+// one hash per quad + one xor/multiply per cell (oracle/noise.py::noise_word), then the flip test
+// against the altitude's threshold and the ground truth (mapping/simulations.py:53-65).
+__device__ __forceinline__ uint32_t seen_mask4(uint32_t key, uint32_t thresh, int32_t c0, uint32_t g4) {
+  const uint32_t h = cell_hash(key, (uint32_t)c0 >> 2);
+  const uint32_t w0 = h * 0x9E3779B1u, w1 = (h ^ 0x85EBCA6Bu) * 0x85EBCA77u;
+  const uint32_t w2 = (h ^ 0xC2B2AE35u) * 0xC2B2AE3Du, w3 = (h ^ 0x27D4EB2Fu) * 0x27D4EB2Fu;
+  uint32_t seen = 0;
+  seen |= ((((g4)&0xFFu) != 0u) != (w0 < thresh)) ? 1u : 0u;
+  seen |= ((((g4 >> 8) & 0xFFu) != 0u) != (w1 < thresh)) ? 2u : 0u;
+  seen |= ((((g4 >> 16) & 0xFFu) != 0u) != (w2 < thresh)) ? 4u : 0u;
+  seen |= ((((g4 >> 24) & 0xFFu) != 0u) != (w3 < thresh)) ? 8u : 0u;
+  return seen;
+}
+
+// noise word of one cell (used where cells are visited one by one: facade measure kernel)
+__host__ __device__ __forceinline__ uint32_t noise_word(uint32_t key, uint32_t cell) {
+  const uint32_t h = cell_hash(key, cell >> 2);
+  switch (cell & 3u) {
+    case 0: return h * 0x9E3779B1u;
+    case 1: return (h ^ 0x85EBCA6Bu) * 0x85EBCA77u;
+    case 2: return (h ^ 0xC2B2AE35u) * 0xC2B2AE3Du;
+    default: return (h ^ 0x27D4EB2Fu) * 0x27D4EB2Fu;
+  }
+}
+
 // Measurement code byte of quad (cells c0..c0+3) for measurement m: low nibble = cell inside the
-// footprint, high nibble = cell seen as 1 (mapping/simulations.py:42-65 with the hash noise).
+// footprint, high nibble = cell seen as 1.
 __device__ __forceinline__ uint32_t meas_code_byte(const ipp_config& c, const Meas& m, int32_t c0, uint32_t g4) {
   const int32_t x0 = c0 / c.gy, y0 = c0 - x0 * c.gy;
   const int32_t left = c.gx * c.gy - c0;
   const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
   const uint32_t in = rect_mask4(m, x0, y0, min(4, c.gy - y0)) & valid;
   if (in == 0u) return 0u;
-  uint32_t seen = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool wrong = cell_hash(m.key, (uint32_t)(c0 + k)) < m.thresh;
-    const bool one = (((g4 >> (8 * k)) & 0xFFu) != 0u) != wrong;
-    seen |= (one ? 1u : 0u) << k;
-  }
-  return in | ((seen & in) << 4);
-}
-
-// Odds multiplier of this measurement at a cell inside its rect:
-// mapping/simulations.py:42-65 (value = accuracy if the cell is seen as 1 else 1-accuracy).
-__device__ __forceinline__ float meas_k(const Meas& m, uint32_t cell, uint32_t gt) {
-  const bool wrong = cell_hash(m.key, cell) < m.thresh;
-  const bool seen_one = (gt != 0u) != wrong;
-  return seen_one ? m.k_hi : m.k_lo;
+  return in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -86,7 +86,7 @@ __global__ void measure_kernel(const __grid_constant__ ipp_config cfg, const uin
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int32_t x = xl + i / w, y = yu + i % w;
     const uint32_t cell = (uint32_t)(x * cfg.gy + y);
-    const bool wrong = cell_hash(key, cell) < thresh;
+    const bool wrong = noise_word(key, cell) < thresh;
     const bool seen_one = (gt[cell] != 0) != wrong;
     out[i] = seen_one ? y_hi : y_lo;
   }

@@ -28,19 +28,6 @@ __device__ __forceinline__ uint32_t bounds_mask(const ipp_config& c, const int32
   return m;
 }
 
-// One already-moved lower-id agent q against p: every rule is guarded by "more than one action
-// still allowed", evaluated before the zeroing (action_space.py:328-344) => order dependent.
-__device__ __forceinline__ uint32_t collide(const ipp_config& c, uint32_t m, const int32_t* p, const int32_t* q) {
-  const int32_t dx = q[0] / c.spacing - p[0] / c.spacing;
-  const int32_t dy = q[1] / c.spacing - p[1] / c.spacing;
-  if (dx == 0 && dy == 0 && __popc(m) > 1) m &= ~((1u << 0) | (1u << 5));
-  if (dx == -1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 1);
-  if (dx == 0 && dy == -1 && __popc(m) > 1) m &= ~(1u << 2);
-  if (dx == 0 && dy == 1 && __popc(m) > 1) m &= ~(1u << 3);
-  if (dx == 1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 4);
-  return m;
-}
-
 __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
   for (int32_t a = 0; a < IPP_N_ACTIONS; ++a) {
     if ((m >> a) & 1u) {
@@ -51,34 +38,32 @@ __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
   return -1;
 }
 
-// comm matrix + sequential moves of one env (one thread)
+// Sequential masks / action choice / moves of one env (one thread; agents act in id order and agent i
+// sees the NEW positions of agents < i: agent/agent.py:73-104, coma_wrapper.py:97-104).
 __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_t ep, const ipp_step_io& io,
-                           const int32_t t, const bool do_comm, const bool do_move, int32_t (*npos)[3]) {
+                           const int32_t t, int32_t (*npos)[3]) {
   const int32_t A = cfg.n_agents;
   int32_t pos[IPP_MAX_AGENTS][3];
-  for (int32_t a = 0; a < A; ++a)
+  int32_t ix[IPP_MAX_AGENTS], iy[IPP_MAX_AGENTS], nix[IPP_MAX_AGENTS], niy[IPP_MAX_AGENTS];  // lattice indices
+  for (int32_t a = 0; a < A; ++a) {
     for (int32_t d = 0; d < 3; ++d) pos[a][d] = io.pos_in[((int64_t)b * A + a) * 3 + d];
-
-  if (do_comm && io.comm_out != nullptr) {
-    for (int32_t i = 0; i < A; ++i) {
-      const uint32_t key = stream_key(cfg.seed, ep, i, (uint32_t)t, PURPOSE_COMM);
-      uint32_t row = 0;
-      for (int32_t j = 0; j < A; ++j) {
-        const int32_t dx = pos[i][0] - pos[j][0], dy = pos[i][1] - pos[j][1], dz = pos[i][2] - pos[j][2];
-        const int32_t d2 = dx * dx + dy * dy + dz * dz;
-        const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;  // drawn for every ordered pair (:46)
-        const bool ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
-        row |= (ok ? 1u : 0u) << j;
-      }
-      io.comm_out[(int64_t)b * A + i] = (uint8_t)row;
-    }
+    ix[a] = pos[a][0] / cfg.spacing;
+    iy[a] = pos[a][1] / cfg.spacing;
   }
-  if (!do_move) return;
-
   uint32_t stuck = 0;
   for (int32_t a = 0; a < A; ++a) {
-    uint32_t m = bounds_mask(cfg, pos[a]);
-    for (int32_t j = 0; j < a; ++j) m = collide(cfg, m, pos[a], npos[j]);
+    const uint32_t bounds = bounds_mask(cfg, pos[a]);
+    uint32_t m = bounds;
+    // One already-moved lower-id agent j against a: every rule is guarded by "more than one action still
+    // allowed", evaluated before the zeroing (action_space.py:328-344) => order dependent.
+    for (int32_t j = 0; j < a; ++j) {
+      const int32_t dx = nix[j] - ix[a], dy = niy[j] - iy[a];
+      if (dx == 0 && dy == 0 && __popc(m) > 1) m &= ~((1u << 0) | (1u << 5));
+      if (dx == -1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 1);
+      if (dx == 0 && dy == -1 && __popc(m) > 1) m &= ~(1u << 2);
+      if (dx == 0 && dy == 1 && __popc(m) > 1) m &= ~(1u << 3);
+      if (dx == 1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 4);
+    }
     const int32_t cnt = __popc(m);
     int32_t act = -1;
     if (io.actions_in != nullptr) {
@@ -86,7 +71,7 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
       // leave the lattice is turned into "stay" and flagged, so positions always index the tables
       act = io.actions_in[(int64_t)b * A + a];
       if (act < -1 || act >= IPP_N_ACTIONS) act = -1;
-      if (act >= 0 && !((bounds_mask(cfg, pos[a]) >> act) & 1u)) {
+      if (act >= 0 && !((bounds >> act) & 1u)) {
         act = -1;
         stuck |= 2u;
       }
@@ -124,54 +109,56 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
       }
     }
     if (cnt == 0) stuck |= 1u;  // the reference raises here; we stay in place and flag
-    int32_t off[3] = {0, 0, 0};
-    if (act == 0) off[2] = cfg.spacing;
-    if (act == 1) off[0] = -cfg.spacing;
-    if (act == 2) off[1] = -cfg.spacing;
-    if (act == 3) off[1] = cfg.spacing;
-    if (act == 4) off[0] = cfg.spacing;
-    if (act == 5) off[2] = -cfg.spacing;
-    for (int32_t d = 0; d < 3; ++d) {
-      npos[a][d] = pos[a][d] + off[d];
-      io.pos_out[((int64_t)b * A + a) * 3 + d] = npos[a][d];
-    }
+    const int32_t ox = (act == 4) - (act == 1), oy = (act == 3) - (act == 2), oz = (act == 0) - (act == 5);
+    nix[a] = ix[a] + ox;
+    niy[a] = iy[a] + oy;
+    npos[a][0] = pos[a][0] + ox * cfg.spacing;
+    npos[a][1] = pos[a][1] + oy * cfg.spacing;
+    npos[a][2] = pos[a][2] + oz * cfg.spacing;
+    for (int32_t d = 0; d < 3; ++d) io.pos_out[((int64_t)b * A + a) * 3 + d] = npos[a][d];
     if (io.actions_out != nullptr) io.actions_out[(int64_t)b * A + a] = act;
     if (io.mask_out != nullptr) io.mask_out[(int64_t)b * A + a] = (uint8_t)m;
   }
   if (io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)stuck;
 }
 
-// OR the code bits of measurement `m` (agent a) into this env's (zeroed) code row.  One task per
-// (footprint row, quad overlapping that row): it contributes the bits of THAT row only, so a quad
-// that straddles two grid rows simply receives two contributions.
-__device__ __forceinline__ void or_meas_codes(const ipp_config& cfg, const Meas& m, const int a, const int ap,
-                                              const uint8_t* __restrict__ gt, uint32_t* __restrict__ codes32,
-                                              const int lane) {
+// Write the code bytes of measurement `m` (agent a) into this env's zeroed code row: one task per
+// (footprint row, quad overlapping that row); the byte always describes the WHOLE quad, so a quad
+// straddling two grid rows is simply written twice with the same value (plain byte stores, no atomics).
+__device__ __forceinline__ void write_meas_codes(const ipp_config& cfg, const Meas& m, const int a, const int ap,
+                                                 const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
+                                                 const int lane) {
   const int32_t h = m.xr - m.xl, w = m.yd - m.yu;
   if (h <= 0 || w <= 0) return;
-  const int32_t per_row = (w + 3) / 4 + 1;  // upper bound of quads overlapping one footprint row
-  const int32_t word_per_quad = ap >> 2, word_of_a = a >> 2, shift = 8 * (a & 3);
-  for (int32_t task = lane; task < h * per_row; task += 32) {
-    const int32_t r = task / per_row, k = task - r * per_row;
-    const int32_t first = (m.xl + r) * cfg.gy + m.yu, last = first + w - 1;
-    const int32_t q = (first >> 2) + k;
-    if (q > (last >> 2)) continue;
-    const int32_t c0 = q << 2;
-    const int32_t lo = max(first - c0, 0), hi = min(last + 1 - c0, 4);
-    const uint32_t in = (1u << hi) - (1u << lo);
-    const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
-    uint32_t seen = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool wrong = cell_hash(m.key, (uint32_t)(c0 + c)) < m.thresh;
-      const bool one = (((g4 >> (8 * c)) & 0xFFu) != 0u) != wrong;
-      seen |= (one ? 1u : 0u) << c;
+  const int32_t per_row = (w + 3) / 4 + 1;                // upper bound of quads overlapping one footprint row
+  const uint32_t inv = (65536u + per_row - 1) / per_row;  // task / per_row by multiply-shift (small footprints)
+  const int32_t n_tasks = h * per_row;
+  const int32_t n_cells = cfg.gx * cfg.gy;
+  for (int32_t task = lane; task < n_tasks; task += 32) {
+    int32_t r, k;
+    if (n_tasks * per_row < 65536) {  // exactness bound of the 16-bit reciprocal: task * (per_row-1) < 2^16
+      r = (int32_t)(((uint32_t)task * inv) >> 16);
+      k = task - r * per_row;
+    } else {
+      r = task / per_row;
+      k = task - r * per_row;
     }
-    atomicOr(&codes32[(int64_t)q * word_per_quad + word_of_a], (in | ((seen & in) << 4)) << shift);
+    const int32_t x = m.xl + r;
+    const int32_t row0 = x * cfg.gy;
+    const int32_t q = ((row0 + m.yu) >> 2) + k;
+    if (q > ((row0 + m.yd - 1) >> 2)) continue;
+    const int32_t c0 = q << 2;
+    const int32_t x0 = (c0 >= row0) ? x : x - 1;  // the quad starts in this row or at the end of the previous one
+    const int32_t y0 = c0 - x0 * cfg.gy;
+    const int32_t left = n_cells - c0;
+    const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
+    const uint32_t in = rect_mask4(m, x0, y0, min(4, cfg.gy - y0)) & valid;
+    const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
+    codes[(int64_t)q * ap + a] = (uint8_t)(in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4));
   }
 }
 
-constexpr int PLAN_WARPS = 8;  // envs per block: one warp plans one env, no block-level barrier
+constexpr int PLAN_WARPS = 4;  // envs per block: one warp plans one env, no block-level barrier
 
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
@@ -181,6 +168,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
   if (b >= cfg.n_envs) return;
   const int32_t A = cfg.n_agents;
   __shared__ int32_t s_npos[PLAN_WARPS][IPP_MAX_AGENTS][3];
+  __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
   const uint32_t ep = st.episodes[b];
   // codes of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
   uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
@@ -209,16 +197,14 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
         io.comm_out[(int64_t)b * A + row0 + lane] = (uint8_t)((bits >> (lane * A)) & ((1u << A) - 1u));
     }
   }
-  if (lane == 0) plan_moves(cfg, b, ep, io, t, false, do_move != 0, s_npos[warp]);
   if (!do_move) return;
-  __threadfence();  // the zeroed row is visible before any lane ORs into it
+  if (lane == 0) plan_moves(cfg, b, ep, io, t, s_npos[warp]);
+  __syncwarp();  // orders the zeroed row and s_npos before the other lanes' accesses
+  if (lane < A) s_meas[warp][lane] = make_meas(cfg, s_npos[warp][lane], ep, (uint32_t)lane, (uint32_t)t + 1u);
   __syncwarp();
   const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
   const int ap = A <= 4 ? 4 : 8;
-  for (int a = 0; a < A; ++a) {
-    const Meas m = make_meas(cfg, s_npos[warp][a], ep, (uint32_t)a, (uint32_t)t + 1u);
-    or_meas_codes(cfg, m, a, ap, gt, reinterpret_cast<uint32_t*>(codes), lane);
-  }
+  for (int a = 0; a < A; ++a) write_meas_codes(cfg, s_meas[warp][a], a, ap, gt, codes, lane);
 }
 
 // =================================================================================================

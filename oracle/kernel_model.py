@@ -143,7 +143,7 @@ class KernelModelEnv:
         if self.noiseless:
             wrong = np.zeros(inr.shape, dtype=bool)
         else:
-            h = hn.cell_hash(key[:, None, None], self._cell)
+            h = hn.noise_word(key[:, None, None], self._cell)
             wrong = h < tab.thresh[iz][:, None, None]
         seen_one = (self.gt != 0) ^ wrong
         k = np.where(seen_one, tab.k_hi[iz][:, None, None], tab.k_lo[iz][:, None, None]).astype(F32)

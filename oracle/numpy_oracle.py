@@ -110,7 +110,7 @@ def measurement(geo, gt, altitude, rect, key, noiseless=False):
     if noiseless:
         wrong = np.zeros(section.shape, dtype=bool)
     else:
-        wrong = hn.cell_hash(key, xs * geo.gy + ys) < hn.flip_threshold(sensor_noise)
+        wrong = hn.noise_word(key, xs * geo.gy + ys) < hn.flip_threshold(sensor_noise)
     accuracy = 1 - sensor_noise
     seen = np.where(wrong, 1 - section, section)
     value = np.where(seen == 1, accuracy, 1 - accuracy)

@@ -161,7 +161,7 @@ def _patched_get_measurement(self, altitude, footprint, mode):
         key = hn.stream_key(
             NoiseContext.seed, NoiseContext.episode, NoiseContext.agent, NoiseContext.index, hn.PURPOSE_NOISE
         )
-        h = hn.cell_hash(key, cells)
+        h = hn.noise_word(key, cells)
         correctness = (h >= hn.flip_threshold(sensor_noise)).astype(np.int64)
     accuracy = 1 - sensor_noise
     value = section.copy()

@@ -68,15 +68,17 @@ def _cpu_worker(args):
     return steps, time.perf_counter() - t0, gen
 
 
-def cpu_baseline(params, seconds, procs):
+def cpu_baseline(params, seconds, procs, pool=None):
     """env-steps/s of `procs` independent single-env numpy processes (the reference is
-    single-threaded numpy, so "all cores" = one process per core)."""
+    single-threaded numpy, so "all cores" = one process per core).  `pool`: reuse a worker pool."""
     import multiprocessing as mp
 
-    ctx = mp.get_context("fork")
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(params, 1 + 1000 * i, seconds) for i in range(procs)])
+    if pool is None:
+        with mp.get_context("fork").Pool(procs) as own:
+            res = own.map(_cpu_worker, [(params, 1 + 1000 * i, seconds) for i in range(procs)], chunksize=1)
+    else:
+        res = pool.map(_cpu_worker, [(params, 1 + 1000 * i, seconds) for i in range(procs)], chunksize=1)
     wall = time.perf_counter() - t0
     steps = sum(r[0] for r in res)
     rate = sum(r[0] / r[1] for r in res)
@@ -153,15 +155,18 @@ def run_reference(args):
     procs = os.cpu_count() or 1
     # a "step" of this arm = a bounded sample: `sample_s` seconds of all-core numpy work
     per_step_s = min(args.ref_seconds, 90.0 / max(args.steps, 1))  # whole arm stays within ~2 minutes
-    for _ in range(args.warmup):
-        cpu_baseline(params, min(0.3, per_step_s), procs)
-    t0 = time.perf_counter()
-    total_steps, rates = 0, []
-    for _ in range(args.steps):
-        r = cpu_baseline(params, per_step_s, procs)
-        total_steps += r["steps"]
-        rates.append(r["value"])
-    wall = time.perf_counter() - t0
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(procs) as pool:  # one pool for the whole run: no fork cost per step
+        for _ in range(args.warmup):
+            cpu_baseline(params, min(0.1, per_step_s), procs, pool)
+        t0 = time.perf_counter()
+        total_steps, rates = 0, []
+        for _ in range(args.steps):
+            r = cpu_baseline(params, per_step_s, procs, pool)
+            total_steps += r["steps"]
+            rates.append(r["value"])
+        wall = time.perf_counter() - t0
     value = sum(rates) / len(rates)
     import numpy
 

@@ -274,6 +274,13 @@ def run_gpu(args):
     torch.cuda.synchronize()
     kern_ms = sum(evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(len(evs) // 2)) / (len(evs) // 2)
     peak, peak_src = measured_peak()
+    traffic = None  # dram bytes per launch of the map kernel, from the committed ncu capture of this workload
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if (tj["envs"], tj["agents"], tj["grid"]) == (B, A, G):
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     alg = bytes_per_env_step(G, A) * B
     achieved = alg / (kern_ms * 1e-3) / 1e9
 
@@ -318,7 +325,7 @@ def run_gpu(args):
                             "memory and rewards+actions copied back every step"},
             "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "%s<%d,true>" % ("step_tma_kernel" if env.step_variant == "tma" else
                                                     "step_dense_kernel", A), "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg,

@@ -122,39 +122,57 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
   if (io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)stuck;
 }
 
-// Write the code bytes of measurement `m` (agent a) into this env's zeroed code row: one task per
-// (footprint row, quad overlapping that row); the byte always describes the WHOLE quad, so a quad
-// straddling two grid rows is simply written twice with the same value (plain byte stores, no atomics).
-__device__ __forceinline__ void write_meas_codes(const ipp_config& cfg, const Meas& m, const int a, const int ap,
-                                                 const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
-                                                 const int lane) {
-  const int32_t h = m.xr - m.xl, w = m.yd - m.yu;
-  if (h <= 0 || w <= 0) return;
-  const int32_t per_row = (w + 3) / 4 + 1;                // upper bound of quads overlapping one footprint row
-  const uint32_t inv = (65536u + per_row - 1) / per_row;  // task / per_row by multiply-shift (small footprints)
-  const int32_t n_tasks = h * per_row;
-  const int32_t n_cells = cfg.gx * cfg.gy;
-  for (int32_t task = lane; task < n_tasks; task += 32) {
-    int32_t r, k;
-    if (n_tasks * per_row < 65536) {  // exactness bound of the 16-bit reciprocal: task * (per_row-1) < 2^16
-      r = (int32_t)(((uint32_t)task * inv) >> 16);
-      k = task - r * per_row;
-    } else {
-      r = task / per_row;
-      k = task - r * per_row;
+// Write the code byte of quad q (cells 4q..4q+3, first cell in grid row x) for measurement m.
+__device__ __forceinline__ void write_code_byte(const ipp_config& cfg, const Meas& m, const int a, const int ap,
+                                                const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
+                                                const int32_t q, const int32_t x, const int32_t row0) {
+  const int32_t c0 = q << 2;
+  const int32_t y0 = c0 - row0;
+  const int32_t left = cfg.gx * cfg.gy - c0;
+  const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
+  const uint32_t in = rect_mask4(m, x, y0, min(4, cfg.gy - y0)) & valid;
+  const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
+  codes[(int64_t)q * ap + a] = (uint8_t)(in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4));
+}
+
+// Write the code bytes of all A measurements into this env's zeroed code row.  One lane per
+// (agent, grid row) pair — the rows of the footprint plus the row just above it, whose last quad may wrap
+// into the footprint.  A lane walks the quads that START in its row, left to right, so every quad of a
+// footprint is written by exactly one lane: plain byte stores, no atomics, no per-task division.
+template <int MAXA>
+__device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Meas* meas, const int A, const int ap,
+                                                const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
+                                                const int lane) {
+  int32_t total = 0;
+  for (int a = 0; a < A; ++a) {
+    const int32_t h = meas[a].xr - meas[a].xl, w = meas[a].yd - meas[a].yu;
+    total += (h > 0 && w > 0) ? h + 1 : 0;
+  }
+  const int32_t gy = cfg.gy;
+  for (int32_t idx = lane; idx < total; idx += 32) {
+    int a = 0;
+    int32_t rr = idx;
+    for (; a < A; ++a) {  // which agent does this (agent, row) pair belong to
+      const int32_t h = meas[a].xr - meas[a].xl, w = meas[a].yd - meas[a].yu;
+      const int32_t n = (h > 0 && w > 0) ? h + 1 : 0;
+      if (rr < n) break;
+      rr -= n;
     }
-    const int32_t x = m.xl + r;
-    const int32_t row0 = x * cfg.gy;
-    const int32_t q = ((row0 + m.yu) >> 2) + k;
-    if (q > ((row0 + m.yd - 1) >> 2)) continue;
-    const int32_t c0 = q << 2;
-    const int32_t x0 = (c0 >= row0) ? x : x - 1;  // the quad starts in this row or at the end of the previous one
-    const int32_t y0 = c0 - x0 * cfg.gy;
-    const int32_t left = n_cells - c0;
-    const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
-    const uint32_t in = rect_mask4(m, x0, y0, min(4, cfg.gy - y0)) & valid;
-    const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
-    codes[(int64_t)q * ap + a] = (uint8_t)(in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4));
+    const Meas m = meas[a];
+    const int32_t h = m.xr - m.xl;
+    const int32_t x = m.xl - 1 + rr;  // this lane owns the quads whose first cell lies in grid row x
+    if (x < 0) continue;
+    const int32_t row0 = x * gy, row1 = row0 + gy;
+    const int32_t q_first = (row0 + 3) >> 2, q_last = (row1 - 1) >> 2;
+    int32_t qa = q_last + 1, qb = q_last;  // run of quads overlapping the footprint cells of row x (empty if rr == 0)
+    if (rr >= 1) {
+      qa = max(q_first, (row0 + m.yu) >> 2);
+      qb = min(q_last, (row0 + m.yd - 1) >> 2);
+    }
+    for (int32_t q = qa; q <= qb; ++q) write_code_byte(cfg, m, a, ap, gt, codes, q, x, row0);
+    // the last quad of the row may wrap into row x+1: footprint cells there have y < n1
+    const int32_t n1 = (q_last << 2) + 4 - row1;
+    if (rr < h && n1 > 0 && m.yu < n1 && qb < q_last) write_code_byte(cfg, m, a, ap, gt, codes, q_last, x, row0);
   }
 }
 
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
   __syncwarp();
   const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
   const int ap = A <= 4 ? 4 : 8;
-  for (int a = 0; a < A; ++a) write_meas_codes(cfg, s_meas[warp][a], a, ap, gt, codes, lane);
+  write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, codes, lane);
 }
 
 // =================================================================================================

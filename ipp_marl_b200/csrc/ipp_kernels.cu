@@ -41,12 +41,12 @@ __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
 // Sequential masks / action choice / moves of one env (one thread; agents act in id order and agent i
 // sees the NEW positions of agents < i: agent/agent.py:73-104, coma_wrapper.py:97-104).
 __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_t ep, const ipp_step_io& io,
-                           const int32_t t, int32_t (*npos)[3]) {
+                           const int32_t t, const int32_t* spos, int32_t (*npos)[3]) {
   const int32_t A = cfg.n_agents;
   int32_t pos[IPP_MAX_AGENTS][3];
   int32_t ix[IPP_MAX_AGENTS], iy[IPP_MAX_AGENTS], nix[IPP_MAX_AGENTS], niy[IPP_MAX_AGENTS];  // lattice indices
   for (int32_t a = 0; a < A; ++a) {
-    for (int32_t d = 0; d < 3; ++d) pos[a][d] = io.pos_in[((int64_t)b * A + a) * 3 + d];
+    for (int32_t d = 0; d < 3; ++d) pos[a][d] = spos[a * 3 + d];
     ix[a] = pos[a][0] / cfg.spacing;
     iy[a] = pos[a][1] / cfg.spacing;
   }
@@ -164,7 +164,7 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
     if (x < 0) continue;
     const int32_t row0 = x * gy, row1 = row0 + gy;
     const int32_t q_first = (row0 + 3) >> 2, q_last = (row1 - 1) >> 2;
-    int32_t qa = q_last + 1, qb = q_last;  // run of quads overlapping the footprint cells of row x (empty if rr == 0)
+    int32_t qa = q_last + 1, qb = q_last - 1;  // run of quads overlapping the footprint cells of row x (empty if rr == 0)
     if (rr >= 1) {
       qa = max(q_first, (row0 + m.yu) >> 2);
       qb = min(q_last, (row0 + m.yd - 1) >> 2);
@@ -178,22 +178,36 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
 
 constexpr int PLAN_WARPS = 4;  // envs per block: one warp plans one env, no block-level barrier
 
+// All global reads of the env (positions, ground truth) are issued up front into shared memory so that a
+// warp pays the memory latency once; everything after the first __syncwarp runs out of shared memory.
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
-                const int32_t do_comm, const int32_t do_move) {
+                const int32_t do_comm, const int32_t do_move, const int32_t stage_gt) {
+  extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride] when stage_gt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t b = blockIdx.x * PLAN_WARPS + warp;
   if (b >= cfg.n_envs) return;
   const int32_t A = cfg.n_agents;
+  __shared__ int32_t s_pos[PLAN_WARPS][IPP_MAX_AGENTS * 3];
   __shared__ int32_t s_npos[PLAN_WARPS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
   const uint32_t ep = st.episodes[b];
+  if (lane < 3 * A) s_pos[warp][lane] = io.pos_in[(int64_t)b * A * 3 + lane];
+  const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
+  if (do_move && stage_gt) {
+    uint4* dst = reinterpret_cast<uint4*>(plan_smem + (size_t)warp * cfg.gt_stride);
+    const uint4* src = reinterpret_cast<const uint4*>(gt);
+    for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
+    gt = reinterpret_cast<const uint8_t*>(dst);
+  }
   // codes of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
   uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
   if (do_move) {
     uint4* cz = reinterpret_cast<uint4*>(codes);
     for (int32_t i = lane; i < (cfg.code_stride >> 4); i += 32) cz[i] = make_uint4(0u, 0u, 0u, 0u);
   }
+  __syncwarp();
+  const int32_t* spos = s_pos[warp];
   if (do_comm && io.comm_out != nullptr) {
     // comm matrix, one ordered pair (i, j) per lane: agent/communication_log.py:39-58
     const int32_t rows_per_round = 32 / A;  // whole rows of the A x A matrix per ballot
@@ -202,9 +216,8 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
       bool ok = false;
       if (lane < rows_here * A) {
         const int32_t i = row0 + lane / A, j = lane % A;
-        const int32_t* pi = io.pos_in + ((int64_t)b * A + i) * 3;
-        const int32_t* pj = io.pos_in + ((int64_t)b * A + j) * 3;
-        const int32_t dx = pi[0] - pj[0], dy = pi[1] - pj[1], dz = pi[2] - pj[2];
+        const int32_t dx = spos[i * 3] - spos[j * 3], dy = spos[i * 3 + 1] - spos[j * 3 + 1],
+                      dz = spos[i * 3 + 2] - spos[j * 3 + 2];
         const int32_t d2 = dx * dx + dy * dy + dz * dz;
         const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)i, (uint32_t)t, PURPOSE_COMM);
         const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;  // drawn for every ordered pair (:46)
@@ -216,11 +229,10 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
     }
   }
   if (!do_move) return;
-  if (lane == 0) plan_moves(cfg, b, ep, io, t, s_npos[warp]);
+  if (lane == 0) plan_moves(cfg, b, ep, io, t, spos, s_npos[warp]);
   __syncwarp();  // orders the zeroed row and s_npos before the other lanes' accesses
   if (lane < A) s_meas[warp][lane] = make_meas(cfg, s_npos[warp][lane], ep, (uint32_t)lane, (uint32_t)t + 1u);
   __syncwarp();
-  const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
   const int ap = A <= 4 ? 4 : 8;
   write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, codes, lane);
 }
@@ -504,8 +516,10 @@ __global__ void __launch_bounds__(STEP_THREADS)
 
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, cudaStream_t s) {
-  plan_kernel<<<(cfg.n_envs + PLAN_WARPS - 1) / PLAN_WARPS, PLAN_WARPS * 32, 0, s>>>(cfg, st, io, t, do_comm,
-                                                                                     do_move);
+  const int stage_gt = (do_move && cfg.gt_stride <= 8192) ? 1 : 0;  // ground truth staged in shared memory
+  const size_t smem = stage_gt ? (size_t)PLAN_WARPS * cfg.gt_stride : 0;
+  plan_kernel<<<(cfg.n_envs + PLAN_WARPS - 1) / PLAN_WARPS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
+                                                                                        do_move, stage_gt);
   return cudaGetLastError();
 }
 

@@ -41,15 +41,31 @@ __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
 // Sequential masks / action choice / moves of one env (one thread; agents act in id order and agent i
 // sees the NEW positions of agents < i: agent/agent.py:73-104, coma_wrapper.py:97-104).
 __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_t ep, const ipp_step_io& io,
-                           const int32_t t, const int32_t* spos, int32_t (*npos)[3]) {
+                           const int32_t t, const bool do_comm, const bool do_move, int32_t (*npos)[3]) {
   const int32_t A = cfg.n_agents;
   int32_t pos[IPP_MAX_AGENTS][3];
   int32_t ix[IPP_MAX_AGENTS], iy[IPP_MAX_AGENTS], nix[IPP_MAX_AGENTS], niy[IPP_MAX_AGENTS];  // lattice indices
   for (int32_t a = 0; a < A; ++a) {
-    for (int32_t d = 0; d < 3; ++d) pos[a][d] = spos[a * 3 + d];
+    for (int32_t d = 0; d < 3; ++d) pos[a][d] = io.pos_in[((int64_t)b * A + a) * 3 + d];
     ix[a] = pos[a][0] / cfg.spacing;
     iy[a] = pos[a][1] / cfg.spacing;
   }
+  if (do_comm && io.comm_out != nullptr) {
+    // comm matrix: agent/communication_log.py:39-58 (one uniform draw per ordered pair, used or not, :46)
+    for (int32_t i = 0; i < A; ++i) {
+      const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)i, (uint32_t)t, PURPOSE_COMM);
+      uint32_t row = 0;
+      for (int32_t j = 0; j < A; ++j) {
+        const int32_t dx = pos[i][0] - pos[j][0], dy = pos[i][1] - pos[j][1], dz = pos[i][2] - pos[j][2];
+        const int32_t d2 = dx * dx + dy * dy + dz * dz;
+        const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;
+        const bool ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
+        row |= (ok ? 1u : 0u) << j;
+      }
+      io.comm_out[(int64_t)b * A + i] = (uint8_t)row;
+    }
+  }
+  if (!do_move) return;
   uint32_t stuck = 0;
   for (int32_t a = 0; a < A; ++a) {
     const uint32_t bounds = bounds_mask(cfg, pos[a]);
@@ -169,72 +185,60 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
       qa = max(q_first, (row0 + m.yu) >> 2);
       qb = min(q_last, (row0 + m.yd - 1) >> 2);
     }
-    for (int32_t q = qa; q <= qb; ++q) write_code_byte(cfg, m, a, ap, gt, codes, q, x, row0);
+    if (qa <= qb) write_code_byte(cfg, m, a, ap, gt, codes, qa, x, row0);
+    for (int32_t q = qa + 1; q < qb; ++q) {  // strictly inside the run: all 4 cells are footprint cells of row x
+      const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + (q << 2));
+      codes[(int64_t)q * ap + a] = (uint8_t)(0xFu | (seen_mask4(m.key, m.thresh, q << 2, g4) << 4));
+    }
+    if (qb > qa) write_code_byte(cfg, m, a, ap, gt, codes, qb, x, row0);
     // the last quad of the row may wrap into row x+1: footprint cells there have y < n1
     const int32_t n1 = (q_last << 2) + 4 - row1;
     if (rr < h && n1 > 0 && m.yu < n1 && qb < q_last) write_code_byte(cfg, m, a, ap, gt, codes, q_last, x, row0);
   }
 }
 
-constexpr int PLAN_WARPS = 4;  // envs per block: one warp plans one env, no block-level barrier
+constexpr int PLAN_WARPS = 4;   // warps per block
+constexpr int PLAN_ENVS = 16;   // envs per block
 
-// All global reads of the env (positions, ground truth) are issued up front into shared memory so that a
-// warp pays the memory latency once; everything after the first __syncwarp runs out of shared memory.
+// Phase 1: warp 0 plans the moves of the block's 16 envs, one LANE per env (the sequential-in-agent logic is
+// scalar work: a whole warp per env would idle 31 lanes); the other warps zero the envs' new code rows.
+// Phase 2: each warp writes the measurement codes of 4 envs (ground truth staged in shared memory).
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
                 const int32_t do_comm, const int32_t do_move, const int32_t stage_gt) {
   extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride] when stage_gt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int32_t b = blockIdx.x * PLAN_WARPS + warp;
-  if (b >= cfg.n_envs) return;
+  const int32_t e0 = blockIdx.x * PLAN_ENVS;
+  const int32_t n_here = min(PLAN_ENVS, cfg.n_envs - e0);
   const int32_t A = cfg.n_agents;
-  __shared__ int32_t s_pos[PLAN_WARPS][IPP_MAX_AGENTS * 3];
-  __shared__ int32_t s_npos[PLAN_WARPS][IPP_MAX_AGENTS][3];
+  __shared__ int32_t s_npos[PLAN_ENVS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
-  const uint32_t ep = st.episodes[b];
-  if (lane < 3 * A) s_pos[warp][lane] = io.pos_in[(int64_t)b * A * 3 + lane];
-  const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
-  if (do_move && stage_gt) {
-    uint4* dst = reinterpret_cast<uint4*>(plan_smem + (size_t)warp * cfg.gt_stride);
-    const uint4* src = reinterpret_cast<const uint4*>(gt);
-    for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
-    gt = reinterpret_cast<const uint8_t*>(dst);
-  }
-  // codes of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
-  uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
-  if (do_move) {
-    uint4* cz = reinterpret_cast<uint4*>(codes);
-    for (int32_t i = lane; i < (cfg.code_stride >> 4); i += 32) cz[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  __syncwarp();
-  const int32_t* spos = s_pos[warp];
-  if (do_comm && io.comm_out != nullptr) {
-    // comm matrix, one ordered pair (i, j) per lane: agent/communication_log.py:39-58
-    const int32_t rows_per_round = 32 / A;  // whole rows of the A x A matrix per ballot
-    for (int32_t row0 = 0; row0 < A; row0 += rows_per_round) {
-      const int32_t rows_here = min(rows_per_round, A - row0);
-      bool ok = false;
-      if (lane < rows_here * A) {
-        const int32_t i = row0 + lane / A, j = lane % A;
-        const int32_t dx = spos[i * 3] - spos[j * 3], dy = spos[i * 3 + 1] - spos[j * 3 + 1],
-                      dz = spos[i * 3 + 2] - spos[j * 3 + 2];
-        const int32_t d2 = dx * dx + dy * dy + dz * dz;
-        const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)i, (uint32_t)t, PURPOSE_COMM);
-        const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;  // drawn for every ordered pair (:46)
-        ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
-      }
-      const uint32_t bits = __ballot_sync(0xFFFFFFFFu, ok);
-      if (lane < rows_here)  // lane r writes row row0 + r
-        io.comm_out[(int64_t)b * A + row0 + lane] = (uint8_t)((bits >> (lane * A)) & ((1u << A) - 1u));
-    }
+  if (warp == 0) {
+    if (lane < n_here) plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane]);
+  } else if (do_move) {
+    // code rows of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer (contiguous)
+    uint4* cz = reinterpret_cast<uint4*>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + e0) * cfg.code_stride);
+    const int32_t n16 = n_here * (cfg.code_stride >> 4);
+    for (int32_t i = threadIdx.x - 32; i < n16; i += (PLAN_WARPS - 1) * 32) cz[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (!do_move) return;
-  if (lane == 0) plan_moves(cfg, b, ep, io, t, spos, s_npos[warp]);
-  __syncwarp();  // orders the zeroed row and s_npos before the other lanes' accesses
-  if (lane < A) s_meas[warp][lane] = make_meas(cfg, s_npos[warp][lane], ep, (uint32_t)lane, (uint32_t)t + 1u);
-  __syncwarp();
+  __syncthreads();  // new positions + zeroed rows visible to the whole block
   const int ap = A <= 4 ? 4 : 8;
-  write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, codes, lane);
+  for (int32_t e = warp; e < n_here; e += PLAN_WARPS) {
+    const int32_t b = e0 + e;
+    const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
+    if (stage_gt) {
+      uint4* dst = reinterpret_cast<uint4*>(plan_smem + (size_t)warp * cfg.gt_stride);
+      const uint4* src = reinterpret_cast<const uint4*>(gt);
+      for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
+      gt = reinterpret_cast<const uint8_t*>(dst);
+    }
+    if (lane < A) s_meas[warp][lane] = make_meas(cfg, s_npos[e][lane], st.episodes[b], (uint32_t)lane, (uint32_t)t + 1u);
+    __syncwarp();
+    uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
+    write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, codes, lane);
+    __syncwarp();  // s_meas / staged ground truth are reused by the next env of this warp
+  }
 }
 
 // =================================================================================================
@@ -518,8 +522,8 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
                         int do_move, cudaStream_t s) {
   const int stage_gt = (do_move && cfg.gt_stride <= 8192) ? 1 : 0;  // ground truth staged in shared memory
   const size_t smem = stage_gt ? (size_t)PLAN_WARPS * cfg.gt_stride : 0;
-  plan_kernel<<<(cfg.n_envs + PLAN_WARPS - 1) / PLAN_WARPS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
-                                                                                        do_move, stage_gt);
+  plan_kernel<<<(cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
+                                                                                      do_move, stage_gt);
   return cudaGetLastError();
 }
 

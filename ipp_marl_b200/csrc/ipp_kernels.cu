@@ -197,7 +197,7 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
   }
 }
 
-constexpr int PLAN_WARPS = 4;   // warps per block
+constexpr int PLAN_WARPS = 16;  // warps per block: one env per warp in phase 2
 constexpr int PLAN_ENVS = 16;   // envs per block
 
 // Phase 1: warp 0 plans the moves of the block's 16 envs, one LANE per env (the sequential-in-agent logic is

@@ -201,43 +201,58 @@ constexpr int PLAN_WARPS = 16;  // warps per block: one env per warp in phase 2
 constexpr int PLAN_ENVS = 16;   // envs per block
 
 // Phase 1: warp 0 plans the moves of the block's 16 envs, one LANE per env (the sequential-in-agent logic is
-// scalar work: a whole warp per env would idle 31 lanes); the other warps zero the envs' new code rows.
-// Phase 2: each warp writes the measurement codes of 4 envs (ground truth staged in shared memory).
+// scalar work: a whole warp per env would idle 31 lanes).
+// Phase 2: one warp per env builds the env's new code row.  When it fits (stage != 0) the row is assembled in
+// SHARED memory next to a staged copy of the ground truth and written out with coalesced 16-byte stores:
+// scattering one byte per (quad, agent) straight to global memory costs one L2 write transaction per byte
+// (7.4 M per launch at 8192 envs — that, not the arithmetic, bounded earlier versions of this kernel).
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
-                const int32_t do_comm, const int32_t do_move, const int32_t stage_gt) {
-  extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride] when stage_gt
+                const int32_t do_comm, const int32_t do_move, const int32_t stage) {
+  extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride + code_stride] when stage
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t e0 = blockIdx.x * PLAN_ENVS;
   const int32_t n_here = min(PLAN_ENVS, cfg.n_envs - e0);
   const int32_t A = cfg.n_agents;
   __shared__ int32_t s_npos[PLAN_ENVS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
-  if (warp == 0) {
-    if (lane < n_here) plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane]);
-  } else if (do_move) {
-    // code rows of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer (contiguous)
-    uint4* cz = reinterpret_cast<uint4*>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + e0) * cfg.code_stride);
-    const int32_t n16 = n_here * (cfg.code_stride >> 4);
-    for (int32_t i = threadIdx.x - 32; i < n16; i += (PLAN_WARPS - 1) * 32) cz[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  if (warp == 0 && lane < n_here)
+    plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane]);
   if (!do_move) return;
-  __syncthreads();  // new positions + zeroed rows visible to the whole block
   const int ap = A <= 4 ? 4 : 8;
+  const int32_t n16 = cfg.code_stride >> 4;
+  unsigned char* my_smem = plan_smem + (size_t)warp * (cfg.gt_stride + cfg.code_stride);
+  // work that does not depend on the moves: stage the ground truth, clear the row (env of the first round)
+  if (stage && warp < n_here) {
+    const uint4* src = reinterpret_cast<const uint4*>(st.ground_truth + (int64_t)(e0 + warp) * cfg.gt_stride);
+    uint4* dst = reinterpret_cast<uint4*>(my_smem);
+    for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
+  }
+  __syncthreads();  // new positions visible to the whole block
   for (int32_t e = warp; e < n_here; e += PLAN_WARPS) {
     const int32_t b = e0 + e;
+    // code row of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
+    uint4* grow = reinterpret_cast<uint4*>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride);
     const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
-    if (stage_gt) {
-      uint4* dst = reinterpret_cast<uint4*>(plan_smem + (size_t)warp * cfg.gt_stride);
-      const uint4* src = reinterpret_cast<const uint4*>(gt);
-      for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
-      gt = reinterpret_cast<const uint8_t*>(dst);
+    uint8_t* row = reinterpret_cast<uint8_t*>(grow);
+    if (stage) {
+      if (e != warp) {  // later rounds (PLAN_ENVS > PLAN_WARPS): stage this env's ground truth now
+        const uint4* src = reinterpret_cast<const uint4*>(gt);
+        uint4* dst = reinterpret_cast<uint4*>(my_smem);
+        for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
+      }
+      gt = my_smem;
+      row = my_smem + cfg.gt_stride;
     }
+    uint4* rz = reinterpret_cast<uint4*>(row);
+    for (int32_t i = lane; i < n16; i += 32) rz[i] = make_uint4(0u, 0u, 0u, 0u);
     if (lane < A) s_meas[warp][lane] = make_meas(cfg, s_npos[e][lane], st.episodes[b], (uint32_t)lane, (uint32_t)t + 1u);
+    __syncwarp();  // zeroed row, staged ground truth and s_meas visible to all lanes
+    write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, row, lane);
     __syncwarp();
-    uint8_t* codes = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
-    write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, codes, lane);
-    __syncwarp();  // s_meas / staged ground truth are reused by the next env of this warp
+    if (stage)
+      for (int32_t i = lane; i < n16; i += 32) grow[i] = rz[i];
+    __syncwarp();  // shared buffers are reused by the next env of this warp
   }
 }
 
@@ -520,8 +535,15 @@ __global__ void __launch_bounds__(STEP_THREADS)
 
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, cudaStream_t s) {
-  const int stage_gt = (do_move && cfg.gt_stride <= 8192) ? 1 : 0;  // ground truth staged in shared memory
-  const size_t smem = stage_gt ? (size_t)PLAN_WARPS * cfg.gt_stride : 0;
+  // ground truth + new code row of one env per warp in shared memory (falls back to global for big grids)
+  const int stage_gt = (do_move && (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) <= 96 * 1024) ? 1 : 0;
+  const size_t smem = stage_gt ? (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   plan_kernel<<<(cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
                                                                                       do_move, stage_gt);
   return cudaGetLastError();

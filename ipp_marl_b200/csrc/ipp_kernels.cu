@@ -8,6 +8,8 @@
 //   reset_prep / reset_fill   episode reset (MT19937-compatible start positions + ground truth)
 //
 // Arithmetic specification: oracle/kernel_model.py (bit-exact for belief maps).
+#include <cstdlib>
+
 #include "ipp_cell.cuh"
 #include "ipp_launch.h"
 
@@ -216,14 +218,24 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
   const int32_t A = cfg.n_agents;
   __shared__ int32_t s_npos[PLAN_ENVS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
-  if (warp == 0 && lane < n_here)
-    plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane]);
+  if (warp == 0 && lane < n_here) {
+    if (stage & 2) {  // debug: no planning, agents stay
+      for (int a = 0; a < A; ++a)
+        for (int d = 0; d < 3; ++d) {
+          s_npos[lane][a][d] = io.pos_in[((int64_t)(e0 + lane) * A + a) * 3 + d];
+          io.pos_out[((int64_t)(e0 + lane) * A + a) * 3 + d] = s_npos[lane][a][d];
+        }
+    } else {
+      plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane]);
+    }
+  }
   if (!do_move) return;
+  if (stage & 4) return;  // debug: no code generation
   const int ap = A <= 4 ? 4 : 8;
   const int32_t n16 = cfg.code_stride >> 4;
   unsigned char* my_smem = plan_smem + (size_t)warp * (cfg.gt_stride + cfg.code_stride);
   // work that does not depend on the moves: stage the ground truth, clear the row (env of the first round)
-  if (stage && warp < n_here) {
+  if ((stage & 1) && warp < n_here) {
     const uint4* src = reinterpret_cast<const uint4*>(st.ground_truth + (int64_t)(e0 + warp) * cfg.gt_stride);
     uint4* dst = reinterpret_cast<uint4*>(my_smem);
     for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
     uint4* grow = reinterpret_cast<uint4*>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride);
     const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
     uint8_t* row = reinterpret_cast<uint8_t*>(grow);
-    if (stage) {
+    if (stage & 1) {
       if (e != warp) {  // later rounds (PLAN_ENVS > PLAN_WARPS): stage this env's ground truth now
         const uint4* src = reinterpret_cast<const uint4*>(gt);
         uint4* dst = reinterpret_cast<uint4*>(my_smem);
@@ -250,7 +262,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
     __syncwarp();  // zeroed row, staged ground truth and s_meas visible to all lanes
     write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, row, lane);
     __syncwarp();
-    if (stage)
+    if (stage & 1)
       for (int32_t i = lane; i < n16; i += 32) grow[i] = rz[i];
     __syncwarp();  // shared buffers are reused by the next env of this warp
   }
@@ -538,6 +550,8 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
   // ground truth + new code row of one env per warp in shared memory (falls back to global for big grids)
   const int stage_gt = (do_move && (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) <= 96 * 1024) ? 1 : 0;
   const size_t smem = stage_gt ? (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) : 0;
+  int dbg = 0;
+  if (const char* v = getenv("IPP_PLAN_DEBUG")) dbg = atoi(v) & 6;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -545,7 +559,7 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
     attr_set = true;
   }
   plan_kernel<<<(cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
-                                                                                      do_move, stage_gt);
+                                                                                      do_move, stage_gt | dbg);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,8 @@ typedef struct ipp_config {
   float o_min, o_max;      /* same clamp in odds space                                             */
   int32_t radius_x[IPP_MAX_ALT], radius_y[IPP_MAX_ALT]; /* sensors/cameras.py:62-67 per altitude   */
   float k_hi[IPP_MAX_ALT], k_lo[IPP_MAX_ALT]; /* odds multipliers of a cell seen as 1 / as 0       */
+  float y_hi[IPP_MAX_ALT], y_lo[IPP_MAX_ALT]; /* measurement values themselves (simulations.py:47-50): */
+                                              /* float32(round(1-noise, 3)) and float32(round(noise, 3)) */
   uint32_t flip_thresh[IPP_MAX_ALT];          /* cell measured wrongly iff hash < flip_thresh      */
   int32_t cell_x[IPP_MAX_LATTICE], cell_y[IPP_MAX_LATTICE]; /* floor(pos/res_x): cameras.py:66     */
 } ipp_config;
@@ -158,6 +160,23 @@ int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_ste
  * and the measurement update at the new positions. */
 int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
 int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
+
+/*
+ * Network-input feature builders (split mode only: call between ipp_observe and
+ * ipp_act / after ipp_act of the same timestep t).
+ * ipp_features_actor : actor/transformations.py:14-59 -> obs_out [n_envs, n_agents, px, py, 7] float32
+ *   (budget, agent id, ego-centred position map, w-entropy of the area-pooled fused local map, w-entropy of
+ *   the pooled footprint image, pooled fused local map, pooled footprint-ownership map); needs io->pos_in
+ *   and the comm bits written by ipp_observe (io->comm_out, or NULL to use the handle's copy).
+ * ipp_features_critic: critic/transformations.py:17-67 -> state_out [n_envs, n_agents, px, py, 12] float32
+ *   = obs (7) + global position map, w-entropy / area-pooled global map, union footprint, other agents'
+ *   action map; needs pos_in (pre-move positions), actions [n_envs, n_agents] and obs_in.
+ * Area pooling follows cv2.resize(INTER_AREA) (utils/state.py:22-41) with host-built tap tables.
+ */
+int ipp_features_actor(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, float* obs_out,
+                       void* stream);
+int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int32_t* pos_in, const int32_t* actions,
+                        const float* obs_in, float* state_out, void* stream);
 
 /* ---- single-map entry points used by the drop-in facade (host pointers, synchronous) -------- */
 

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libipp_b200.so")
 STAMP = os.path.join(LIBDIR, "libipp_b200.stamp")
-SOURCES = ["ipp_kernels.cu", "ipp_step_tma.cu", "ipp_facade_kernels.cu", "ipp_abi.cu"]
+SOURCES = ["ipp_kernels.cu", "ipp_step_tma.cu", "ipp_features.cu", "ipp_facade_kernels.cu", "ipp_abi.cu"]
 HEADERS = ["ipp_device.cuh", "ipp_cell.cuh", "ipp_launch.h", os.path.join("..", "..", "include", "ipp_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

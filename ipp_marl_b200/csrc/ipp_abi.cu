@@ -18,6 +18,7 @@ struct ipp_handle {
   int32_t* gt_params;   // [n_envs, 4]
   uint8_t* comm;        // [n_envs, n_agents] when the caller does not ask for comm_out
   float4* lut;          // [n_alt, 256] odds multipliers of a quad for every measurement code byte
+  ipp::PoolTables pool; // cv2.INTER_AREA tap tables of the feature builders
   // facade scratch (grown on demand)
   void* fbuf;
   size_t fbuf_bytes;
@@ -178,6 +179,10 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
       return IPP_ERR_CUDA;
     }
   }
+  if (ipp::build_pool_tables(h->cfg, &h->pool) != cudaSuccess) {
+    ipp_destroy(h);
+    return IPP_ERR_ALLOC;
+  }
   h->scratch_bytes = (int64_t)(pb + gb + cb + lb);
   *out = h;
   return IPP_OK;
@@ -189,6 +194,7 @@ int ipp_destroy(ipp_handle* h) {
   if (h->gt_params) cudaFree(h->gt_params);
   if (h->comm) cudaFree(h->comm);
   if (h->lut) cudaFree(h->lut);
+  ipp::free_pool_tables(&h->pool);
   if (h->fbuf) cudaFree(h->fbuf);
   delete h;
   return IPP_OK;
@@ -261,6 +267,29 @@ int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io
   cudaStream_t s = (cudaStream_t)stream;
   IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, *io, t, 0, 1, s));
   IPP_CUDA(h, ipp::launch_own_update(h->cfg, *st, h->lut, io->pos_out, t, s));
+  return IPP_OK;
+}
+
+int ipp_features_actor(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, float* obs_out,
+                       void* stream) {
+  if (h == nullptr || io == nullptr || io->pos_in == nullptr || obs_out == nullptr) return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  if (t < 0 || t > 0xFFFE || h->cfg.px < 6 || h->cfg.py < 6) return IPP_ERR_INVALID_ARG;  // window around index 5
+  const uint8_t* comm = io->comm_out != nullptr ? io->comm_out : h->comm;
+  IPP_CUDA(h, ipp::launch_features_actor(h->cfg, *st, h->pool, io->pos_in, comm, t, obs_out, (cudaStream_t)stream));
+  return IPP_OK;
+}
+
+int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int32_t* pos_in, const int32_t* actions,
+                        const float* obs_in, float* state_out, void* stream) {
+  if (h == nullptr || pos_in == nullptr || actions == nullptr || obs_in == nullptr || state_out == nullptr)
+    return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
+  IPP_CUDA(h, ipp::launch_features_critic(h->cfg, *st, h->pool, pos_in, actions, t, obs_in, state_out,
+                                          (cudaStream_t)stream));
   return IPP_OK;
 }
 

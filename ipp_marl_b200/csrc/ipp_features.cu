@@ -1,0 +1,345 @@
+// Network-input feature builders: the actor observation
+// [P, P, 7] (actor/transformations.py:14-176) and the critic state [P, P, 12]
+// (critic/transformations.py:17-132), batched over envs x agents.
+//
+// The lattice-sized maps are area-pooled exactly like cv2.resize(INTER_AREA) does it
+// (utils/state.py:22-41): separable tap tables built on the host by the same rule as OpenCV's
+// computeResizeAreaTab (fractional-overlap box filter when shrinking; the INTER_AREA flavour of
+// bilinear when the source is smaller than the lattice, e.g. the 10x10 footprint image at 5 m).
+// Everything about the latest measurements comes from the code bytes (ipp_cell.cuh) and the positions.
+#include <cmath>
+#include <vector>
+
+#include "ipp_cell.cuh"
+#include "ipp_launch.h"
+
+namespace ipp {
+
+// ------------------------------------------------------------------------------------------------
+// host: tap tables
+// ------------------------------------------------------------------------------------------------
+static void area_taps(int ssize, int dsize, std::vector<std::vector<std::pair<int, float>>>& out) {
+  out.assign(dsize, {});
+  const double scale = (double)ssize / dsize;
+  if (scale >= 1.0) {  // OpenCV computeResizeAreaTab
+    for (int dx = 0; dx < dsize; ++dx) {
+      const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+      const double cell = std::min(scale, ssize - fsx1);
+      int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+      sx2 = std::min(sx2, ssize - 1);
+      sx1 = std::min(sx1, sx2);
+      if (sx1 - fsx1 > 1e-3) out[dx].push_back({sx1 - 1, (float)((sx1 - fsx1) / cell)});
+      for (int sx = sx1; sx < sx2; ++sx) out[dx].push_back({sx, (float)(1.0 / cell)});
+      if (fsx2 - sx2 > 1e-3) out[dx].push_back({sx2, (float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell)});
+    }
+  } else {  // source smaller than the lattice: OpenCV's linear path with the INTER_AREA coefficient rule
+    const double inv = (double)dsize / ssize;
+    for (int dx = 0; dx < dsize; ++dx) {
+      int sx = (int)std::floor(dx * scale);
+      float fx = (float)((dx + 1) - (sx + 1) * inv);
+      fx = fx <= 0 ? 0.f : fx - std::floor(fx);
+      if (sx < 0) { fx = 0; sx = 0; }
+      if (sx >= ssize - 1) { fx = 0; sx = ssize - 1; }
+      out[dx].push_back({sx, 1.f - fx});
+      if (sx + 1 < ssize) out[dx].push_back({sx + 1, fx});
+    }
+  }
+}
+
+// table ids: 0 map-x (gx -> px), 1 map-y (gy -> py), 2+2a axis-0 of the footprint image at altitude a
+// (size 2*ry -> px), 3+2a axis-1 (size 2*rx -> py)   [mapping/mappings.py:41-43: the image is (yd-yu) x (xr-xl)]
+cudaError_t build_pool_tables(const ipp_config& cfg, PoolTables* pt) {
+  const int n_tabs = 2 + 2 * cfg.n_alt;
+  std::vector<std::vector<std::vector<std::pair<int, float>>>> taps(n_tabs);
+  area_taps(cfg.gx, cfg.px, taps[0]);
+  area_taps(cfg.gy, cfg.py, taps[1]);
+  for (int a = 0; a < cfg.n_alt; ++a) {
+    area_taps(std::max(2 * cfg.radius_y[a], 1), cfg.px, taps[2 + 2 * a]);
+    area_taps(std::max(2 * cfg.radius_x[a], 1), cfg.py, taps[3 + 2 * a]);
+  }
+  int maxt = 1;
+  for (auto& tab : taps)
+    for (auto& row : tab) maxt = std::max<int>(maxt, (int)row.size());
+  const int pmax = IPP_MAX_LATTICE;
+  std::vector<int32_t> ints((size_t)n_tabs * pmax * 2, 0);
+  std::vector<float> w((size_t)n_tabs * pmax * maxt, 0.f);
+  for (int k = 0; k < n_tabs; ++k)
+    for (size_t d = 0; d < taps[k].size(); ++d) {
+      const auto& row = taps[k][d];
+      ints[((size_t)k * pmax + d) * 2 + 0] = row.empty() ? 0 : row[0].first;
+      ints[((size_t)k * pmax + d) * 2 + 1] = (int32_t)row.size();
+      for (size_t i = 0; i < row.size(); ++i) {
+        // taps are consecutive source indices (both rules produce runs)
+        w[((size_t)k * pmax + d) * maxt + i] = row[i].second;
+      }
+    }
+  pt->maxt = maxt;
+  pt->n_tabs = n_tabs;
+  cudaError_t e = cudaMalloc(&pt->ints, ints.size() * sizeof(int32_t));
+  if (e != cudaSuccess) return e;
+  e = cudaMalloc(&pt->w, w.size() * sizeof(float));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(pt->ints, ints.data(), ints.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(pt->w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
+}
+
+void free_pool_tables(PoolTables* pt) {
+  if (pt->ints) cudaFree(pt->ints);
+  if (pt->w) cudaFree(pt->w);
+  pt->ints = nullptr;
+  pt->w = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+struct Tab {
+  const int32_t* ints;  // [pmax][2] start, count
+  const float* w;       // [pmax][maxt]
+  int maxt;
+  __device__ __forceinline__ int start(int d) const { return ints[2 * d]; }
+  __device__ __forceinline__ int count(int d) const { return ints[2 * d + 1]; }
+  __device__ __forceinline__ float weight(int d, int i) const { return w[d * maxt + i]; }
+};
+
+__device__ __forceinline__ Tab get_tab(const PoolTables& pt, int k) {
+  return Tab{pt.ints + (size_t)k * IPP_MAX_LATTICE * 2, pt.w + (size_t)k * IPP_MAX_LATTICE * pt.maxt, pt.maxt};
+}
+
+// utils/state.py:67-76 + 118-121 on a pooled value: (w * H(clamp(v)), clamp(v))
+__device__ __forceinline__ float2 w_entropy(const ipp_config& cfg, float v) {
+  const float w = v > 0.501f ? 1.0f : (v < 0.499f ? 0.0f : 0.5f);
+  const float c = fminf(fmaxf(v, cfg.p_min), cfg.p_max);
+  const float h = -c * log2f(c) - (1.0f - c) * log2f(1.0f - c);
+  return make_float2(w * h, c);
+}
+
+struct AgentGeo {
+  int32_t ix, iy, iz;      // lattice indices (iz = altitude level, 0-based: index of the host tables)
+  int32_t zi;              // agent/state_space.py:56: position[2] // spacing - 1 (what the features use)
+  int32_t xl, xr, yu, yd;  // clipped footprint (half-open)
+  int32_t rxl, ryu;        // raw footprint origin
+  int32_t rx2, ry2;        // raw footprint extents 2*rx, 2*ry
+};
+
+__device__ __forceinline__ AgentGeo agent_geo(const ipp_config& c, const int32_t* pos) {
+  AgentGeo g;
+  g.ix = clampi(pos[0] / c.spacing, 0, c.px - 1);
+  g.iy = clampi(pos[1] / c.spacing, 0, c.py - 1);
+  g.iz = clampi(pos[2] / c.spacing - c.min_altitude / c.spacing, 0, c.n_alt - 1);
+  g.zi = pos[2] / c.spacing - 1;
+  const int32_t cx = c.cell_x[g.ix], cy = c.cell_y[g.iy], rx = c.radius_x[g.iz], ry = c.radius_y[g.iz];
+  g.rxl = cx - rx;
+  g.ryu = cy - ry;
+  g.rx2 = 2 * rx;
+  g.ry2 = 2 * ry;
+  g.xl = clampi(cx - rx, 0, c.gx - 1);
+  g.xr = clampi(cx + rx, 0, c.gx - 1);
+  g.yu = clampi(cy - ry, 0, c.gy - 1);
+  g.yd = clampi(cy + ry, 0, c.gy - 1);
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// actor observation: one block per (env, agent)
+// ------------------------------------------------------------------------------------------------
+template <int A>
+__global__ void __launch_bounds__(128)
+    features_actor_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
+                          const int32_t* __restrict__ pos_in, const uint8_t* __restrict__ comm, const int32_t t,
+                          float* __restrict__ obs_out) {
+  const int32_t b = blockIdx.x / A, i = blockIdx.x - b * A;
+  __shared__ AgentGeo s_geo[A];
+  if (threadIdx.x < A) s_geo[threadIdx.x] = agent_geo(cfg, pos_in + ((int64_t)b * A + threadIdx.x) * 3);
+  __syncthreads();
+  const uint32_t received = comm[(int64_t)b * A + i];  // includes the agent itself (communication_log.py:47)
+  const AgentGeo me = s_geo[i];
+  const float* local = st.local_maps + ((int64_t)b * A + i) * cfg.map_stride;
+  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
+  const Tab fx = get_tab(pt, 2 + 2 * me.iz), fy = get_tab(pt, 3 + 2 * me.iz);
+  // where the clipped measurement block sits inside the raw footprint image (utils/utils.py:79-98);
+  // the image is (yd-yu) x (xr-xl) but is indexed [x-block, y-block] (mapping/mappings.py:41-43,72-76)
+  const int32_t h = me.ry2, w = me.rx2;
+  int32_t b_yu = 0, b_yd = h, b_xl = 0, b_xr = w;
+  if (me.yu > me.ryu) b_yu = h - (me.yd - me.yu);
+  if (me.yd < me.ryu + me.ry2) b_yd = me.yd - me.yu;
+  if (me.xr < me.rxl + me.rx2) b_xr = me.xr - me.xl;
+  if (me.xl > me.rxl) b_xl = w - (me.xr - me.xl);
+  const float y_hi = cfg.y_hi[me.iz], y_lo = cfg.y_lo[me.iz];
+  const float budget = (float)(cfg.budget - t) / (float)cfg.budget;   // transformations.py:91-93
+  const float agent_id = (float)(i + 1) / (float)A;                   // :86-88
+  const float own_alt = (float)(me.zi + 1) / (float)(cfg.n_alt + 1);  // :125-131
+
+  for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
+    const int32_t li = c / cfg.py, lj = c - li * cfg.py;
+    // ---- pooled fused local map and pooled footprint-ownership map (taps over the G x G grid) ----
+    float pl = 0.0f, pf_own = 0.0f;
+    {
+      const int32_t x0 = tx.start(li), nx = tx.count(li), y0 = ty.start(lj), ny = ty.count(lj);
+      for (int32_t a = 0; a < nx; ++a) {
+        const float wx = tx.weight(li, a);
+        const int32_t x = x0 + a;
+        float row_l = 0.0f, row_o = 0.0f;
+        for (int32_t k = 0; k < ny; ++k) {
+          const int32_t y = y0 + k;
+          const int32_t cell = x * cfg.gy + y;
+          const CodeWord<A> cw = load_code<A>(codes, cell >> 2);
+          const uint32_t bit = 1u << (cell & 3);
+          // actor/transformations.py:62-83: own measured cells 1, received peers' cells 0, else 0.5
+          float o = 0.5f;
+#pragma unroll
+          for (int j = 0; j < A; ++j)
+            if (j != i && ((received >> j) & 1u) && (cw.byte(j) & bit)) o = 0.0f;
+          if (cw.byte(i) & bit) o = 1.0f;
+          const float wy = ty.weight(lj, k);
+          row_l += wy * local[cell];
+          row_o += wy * o;
+        }
+        pl += wx * row_l;
+        pf_own += wx * row_o;
+      }
+    }
+    // ---- pooled footprint image (taps over the raw footprint window) ----
+    float pimg = 0.0f;
+    {
+      const int32_t u0 = fx.start(li), nu = fx.count(li), v0 = fy.start(lj), nv = fy.count(lj);
+      for (int32_t a = 0; a < nu; ++a) {
+        const int32_t u = u0 + a;
+        float row = 0.0f;
+        for (int32_t k = 0; k < nv; ++k) {
+          const int32_t v = v0 + k;
+          float val = 0.5f;
+          if (u >= b_xl && u < b_xr && v >= b_yu && v < b_yd) {
+            const int32_t cell = (me.xl + (u - b_xl)) * cfg.gy + (me.yu + (v - b_yu));
+            const uint32_t byte = load_code<A>(codes, cell >> 2).byte(i);
+            val = ((byte >> (4 + (cell & 3))) & 1u) ? y_hi : y_lo;
+          }
+          row += fy.weight(lj, k) * val;
+        }
+        pimg += fx.weight(li, a) * row;
+      }
+    }
+    // ---- ego-centred position map: actor/transformations.py:110-176 (window hard-wired around index 5) ----
+    float pm = 1.0f;
+    if (me.ix < 5 && li < 5 - me.ix) pm = 0.0f;
+    if (me.iy < 5 && lj < 5 - me.iy) pm = 0.0f;
+    if (me.ix > 5 && li >= cfg.px - 1 - (me.ix - 6)) pm = 0.0f;
+    if (me.iy > 5 && lj >= cfg.py - 1 - (me.iy - 6)) pm = 0.0f;
+    if (li == 5 && lj == 5) pm = own_alt;  // only written when inside [0, px) x [0, px): (5,5) always is
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      if (j == i || !((received >> j) & 1u)) continue;
+      const int32_t ri = s_geo[j].ix - me.ix + 5, rj = s_geo[j].iy - me.iy + 5;
+      if (ri >= 0 && ri < cfg.px && rj >= 0 && rj < cfg.px && ri == li && rj == lj)
+        pm = (float)(s_geo[j].zi + 1) / (float)(cfg.n_alt + 1);
+    }
+    const float2 wl = w_entropy(cfg, pl);
+    const float2 wf = w_entropy(cfg, pimg);
+    float* o = obs_out + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 7;
+    o[0] = budget;
+    o[1] = agent_id;
+    o[2] = pm;
+    o[3] = wl.x;
+    o[4] = wf.x;
+    o[5] = wl.y;
+    o[6] = pf_own;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// critic state: one block per env
+// ------------------------------------------------------------------------------------------------
+template <int A>
+__global__ void __launch_bounds__(128)
+    features_critic_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
+                           const int32_t* __restrict__ pos_in, const int32_t* __restrict__ actions, const int32_t t,
+                           const float* __restrict__ obs_in, float* __restrict__ state_out) {
+  const int32_t b = blockIdx.x;
+  __shared__ AgentGeo s_geo[A];
+  __shared__ int32_t s_act[A];
+  if (threadIdx.x < A) {
+    s_geo[threadIdx.x] = agent_geo(cfg, pos_in + ((int64_t)b * A + threadIdx.x) * 3);
+    s_act[threadIdx.x] = actions[(int64_t)b * A + threadIdx.x];
+  }
+  __syncthreads();
+  const float* glob = st.global_map + (int64_t)b * cfg.map_stride;
+  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
+  for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
+    const int32_t li = c / cfg.py, lj = c - li * cfg.py;
+    float pg = 0.0f, pu = 0.0f;
+    const int32_t x0 = tx.start(li), nx = tx.count(li), y0 = ty.start(lj), ny = ty.count(lj);
+    for (int32_t a = 0; a < nx; ++a) {
+      const int32_t x = x0 + a;
+      float row_g = 0.0f, row_u = 0.0f;
+      for (int32_t k = 0; k < ny; ++k) {
+        const int32_t cell = x * cfg.gy + (y0 + k);
+        const CodeWord<A> cw = load_code<A>(codes, cell >> 2);
+        const uint32_t bit = 1u << (cell & 3);
+        float u = 0.5f;  // critic/transformations.py:91-108: any agent's measured cell -> 1, else 0.5
+#pragma unroll
+        for (int j = 0; j < A; ++j)
+          if (cw.byte(j) & bit) u = 1.0f;
+        const float wy = ty.weight(lj, k);
+        row_g += wy * glob[cell];
+        row_u += wy * u;
+      }
+      pg += tx.weight(li, a) * row_g;
+      pu += tx.weight(li, a) * row_u;
+    }
+    const float2 wg = w_entropy(cfg, pg);
+    float posv = 0.0f;  // critic/transformations.py:70-88 (later agents overwrite earlier ones)
+#pragma unroll
+    for (int j = 0; j < A; ++j)
+      if (s_geo[j].ix == li && s_geo[j].iy == lj) posv = (float)(s_geo[j].zi + 1) / (float)cfg.n_alt;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      float actv = 0.0f;  // :111-132: the other agents' actions at their PRE-move cells
+#pragma unroll
+      for (int j = 0; j < A; ++j)
+        if (j != i && s_geo[j].ix == li && s_geo[j].iy == lj) actv = (float)(s_act[j] + 1) / (float)IPP_N_ACTIONS;
+      const float* o = obs_in + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 7;
+      float* s = state_out + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 12;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s[k] = o[k];
+      s[7] = posv;
+      s[8] = wg.x;
+      s[9] = wg.y;
+      s[10] = pu;
+      s[11] = actv;
+    }
+  }
+}
+
+#define IPP_FEAT_DISPATCH(A_, CALL)                \
+  switch (A_) {                                    \
+    case 1: { constexpr int kA = 1; CALL; } break; \
+    case 2: { constexpr int kA = 2; CALL; } break; \
+    case 3: { constexpr int kA = 3; CALL; } break; \
+    case 4: { constexpr int kA = 4; CALL; } break; \
+    case 5: { constexpr int kA = 5; CALL; } break; \
+    case 6: { constexpr int kA = 6; CALL; } break; \
+    case 7: { constexpr int kA = 7; CALL; } break; \
+    case 8: { constexpr int kA = 8; CALL; } break; \
+    default: return cudaErrorInvalidValue;         \
+  }
+
+cudaError_t launch_features_actor(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                  const int32_t* pos_in, const uint8_t* comm, int32_t t, float* obs_out,
+                                  cudaStream_t s) {
+  IPP_FEAT_DISPATCH(cfg.n_agents, (features_actor_kernel<kA><<<(unsigned)cfg.n_envs * kA, 128, 0, s>>>(
+                                      cfg, st, pt, pos_in, comm, t, obs_out)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_features_critic(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                   const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
+                                   float* state_out, cudaStream_t s) {
+  IPP_FEAT_DISPATCH(cfg.n_agents, (features_critic_kernel<kA><<<(unsigned)cfg.n_envs, 128, 0, s>>>(
+                                      cfg, st, pt, pos_in, actions, t, obs_in, state_out)));
+  return cudaGetLastError();
+}
+
+}  // namespace ipp

@@ -24,6 +24,21 @@ struct TmaPlan {
 
 TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin);
 
+// cv2.INTER_AREA tap tables of the feature builders (device memory, owned by the handle)
+struct PoolTables {
+  int32_t* ints;  // [n_tabs][IPP_MAX_LATTICE][2]: first source index, tap count
+  float* w;       // [n_tabs][IPP_MAX_LATTICE][maxt]
+  int32_t maxt, n_tabs;
+};
+cudaError_t build_pool_tables(const ipp_config& cfg, PoolTables* pt);
+void free_pool_tables(PoolTables* pt);
+cudaError_t launch_features_actor(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                  const int32_t* pos_in, const uint8_t* comm, int32_t t, float* obs_out,
+                                  cudaStream_t s);
+cudaError_t launch_features_critic(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                   const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
+                                   float* state_out, cudaStream_t s);
+
 // lut: device table [n_alt][256] float4 = odds multipliers of the 4 cells of a quad for a code byte
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, cudaStream_t s);

@@ -185,6 +185,29 @@ class BatchedIPPEnv:
         self.t += 1
         return self.actions, done
 
+    # ---- network-input features (split mode) --------------------------------------------------
+    def features_actor(self, out=None):
+        """Actor observations [B, A, px, py, 7] of the current timestep (call after observe())."""
+        if not self._observed:
+            raise N.IppError("features_actor() must follow observe() in the same timestep")
+        t = self.tables
+        if out is None:
+            out = torch.empty((self.B, self.A, t.px, t.py, 7), dtype=torch.float32, device=self.device)
+        io = self._io(None, None, False)
+        rc = self.lib.ipp_features_actor(self._h, C.byref(self._state), self.t, C.byref(io), _ptr(out), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_features_actor")
+        return out
+
+    def features_critic(self, obs, out=None):
+        """Critic states [B, A, px, py, 12] of the timestep that act() just finished."""
+        t = self.tables
+        if out is None:
+            out = torch.empty((self.B, self.A, t.px, t.py, 12), dtype=torch.float32, device=self.device)
+        rc = self.lib.ipp_features_critic(self._h, C.byref(self._state), self.t - 1, _ptr(self.positions[self.t - 1]),
+                                          _ptr(self.actions), _ptr(obs.contiguous()), _ptr(out), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_features_critic")
+        return out
+
     # ---- sizes for the roofline (SURVEY.md section 8d contract figure) --------------------------
     def algorithmic_bytes_per_env_step(self):
         t = self.tables

@@ -76,6 +76,8 @@ class HostTables:
         l_p = np.log(self.prior / (1 - self.prior))
         self.k_hi = np.zeros(self.n_alt, np.float32)
         self.k_lo = np.zeros(self.n_alt, np.float32)
+        self.y_hi = np.zeros(self.n_alt, np.float32)
+        self.y_lo = np.zeros(self.n_alt, np.float32)
         self.flip_thresh = np.zeros(self.n_alt, np.uint32)
         self.noise = np.zeros(self.n_alt, np.float64)
         for i, z in enumerate(self.altitudes):
@@ -86,6 +88,7 @@ class HostTables:
             with np.errstate(divide="ignore"):
                 l_hi = np.log(y_hi / (1 - y_hi))
                 l_lo = np.log(y_lo / (1 - y_lo))
+            self.y_hi[i], self.y_lo[i] = y_hi, y_lo
             self.k_hi[i] = np.float32(np.exp(np.float64(l_hi) - l_p))
             self.k_lo[i] = np.float32(np.exp(np.float64(l_lo) - l_p))
             self.flip_thresh[i] = np.uint32(int(np.floor(float(noise) * 4294967296.0)))
@@ -152,6 +155,8 @@ def make_config(tables, n_envs):
         c.radius_y[i] = int(t.radius_y[i])
         c.k_hi[i] = float(t.k_hi[i])
         c.k_lo[i] = float(t.k_lo[i])
+        c.y_hi[i] = float(t.y_hi[i])
+        c.y_lo[i] = float(t.y_lo[i])
         c.flip_thresh[i] = int(t.flip_thresh[i])
     for i in range(t.px):
         c.cell_x[i] = int(t.cell_x[i])

@@ -38,11 +38,18 @@ def _pack_episode(rec, keep_steps=None, maps=True):
     if maps:
         for key in ("global", "local_fused", "local_after_move"):
             out[key] = np.stack([rec["steps"][t][key] for t in steps])
+    if "obs" in rec["steps"][0]:  # network-input features, every step
+        out["obs"] = np.stack([s["obs"] for s in rec["steps"]])      # [T, A, P, P, 7] float64
+        out["state"] = np.stack([s["state"] for s in rec["steps"]])  # [T, A, P, P, 12] float32
     # checksums of every step (cheap, lets big configs be pinned without storing maps)
     for key in ("global", "local_fused", "local_after_move"):
         out[key + "_sum"] = np.array([rec["steps"][t][key].sum() for t in range(T)])
         out[key + "_sumsq"] = np.array([(rec["steps"][t][key] ** 2).sum() for t in range(T)])
     return out
+
+
+def x_of(params):
+    return params["environment"]["x_dim"]
 
 
 def episodes():
@@ -56,7 +63,7 @@ def episodes():
     ]
     for name, params, eps, keep in cases:
         for ep in eps:
-            rec = rh.run_reference_episode(params, ep)
+            rec = rh.run_reference_episode(params, ep, features=(x_of(params) == 50))
             out = _pack_episode(rec, keep)
             out["params_json"] = np.array(json.dumps(params))
             out["episode"] = np.array(ep)
@@ -66,7 +73,7 @@ def episodes():
             print("wrote", path, os.path.getsize(path))
     # reference default (G = 493): rewards, moves, checksums and the final global map only
     params = rh.default_params()
-    rec = rh.run_reference_episode(params, 1)
+    rec = rh.run_reference_episode(params, 1, features=True)
     out = _pack_episode(rec, keep_steps=(14,), maps=False)
     out["global_final_f32"] = rec["steps"][-1]["global"].astype(np.float32)
     out["params_json"] = np.array(json.dumps(params))

@@ -236,8 +236,30 @@ def uniform_policy_action(mask, seed, episode, agent, t):
     return int(valid[k])
 
 
-def run_reference_episode(params, episode, actions=None, noiseless=False, n_steps=None, record_maps=True):
+class _ListMemory:
+    """Minimal stand-in for BatchMemory (batch_memory.py:25-115): the feature builders only use
+    add(observation=...), insert(-1, state=... / action=...), get(-1, agent, "observation" | "action")."""
+
+    def __init__(self, n_agents):
+        self.rows = {a: [] for a in range(n_agents)}
+
+    def add(self, agent_id, **kw):
+        self.rows[agent_id].append(dict(kw))
+
+    def insert(self, t, agent_id, **kw):
+        self.rows[agent_id][t].update({k: v for k, v in kw.items() if v is not None})
+
+    def get(self, t, agent_id, name):
+        return self.rows[agent_id][t].get(name)
+
+
+def run_reference_episode(params, episode, actions=None, noiseless=False, n_steps=None, record_maps=True,
+                          features=False):
     """One episode of the reference env loop; returns per-step records.
+
+    ``features``: also call the reference's observation / critic-state builders
+    (actor/transformations.py:14-59, critic/transformations.py:17-67) exactly where coma_wrapper.py:57-68
+    and :135-144 call them and record their outputs ("obs" [A,P,P,7] float64, "state" [A,P,P,12] float32).
 
     ``actions``: optional int array [T, A]; default = uniform_policy_action.
     Records (per step t): positions before the moves, comm matrix, fused local
@@ -259,7 +281,11 @@ def run_reference_episode(params, episode, actions=None, noiseless=False, n_step
     mapping = ns.Mapping(grid_map, sensor, params, episode)
     ass = ns.AgentStateSpace(params)
     actor = _StubActor()
-    memory = _StubMemory()
+    memory = _ListMemory(n_agents) if features else _StubMemory()
+    if features:
+        import torch  # noqa: F401  (the builders return torch tensors)
+        from actor.transformations import get_network_input as get_actor_input
+        from critic.transformations import get_network_input as get_critic_input
     agents = [ns.Agent(actor, params, mapping, a, ass) for a in range(n_agents)]
     global_map = agents[0].local_map.copy()
     rec = {
@@ -278,12 +304,19 @@ def run_reference_episode(params, episode, actions=None, noiseless=False, n_step
             step["local_after_init"] = np.array([np.asarray(agents[a].local_map, dtype=np.float64) for a in range(n_agents)])
         comm = np.zeros((n_agents, n_agents), dtype=np.uint8)
         fused_local = []
+        obs = []
         for a in range(n_agents):
             with _comm_draws(seed, episode, a, t):
                 received, fused = agents[a].receive_messages(log, a, t)
             for j in received:
                 comm[a, j] = 1
             fused_local.append(np.asarray(fused, dtype=np.float64).copy())
+            if features:  # coma_wrapper.py:57-68
+                o = get_actor_input(received, fused, mapping.simulated_map, a, t, params, memory, ass)
+                memory.add(a, observation=o)
+                obs.append(o.numpy().copy())
+        if features:
+            step["obs"] = np.array(obs)
         step["comm"] = comm
         if record_maps:
             step["local_fused"] = np.array(fused_local)
@@ -299,10 +332,20 @@ def run_reference_episode(params, episode, actions=None, noiseless=False, n_step
             NoiseContext.agent, NoiseContext.index = a, t + 1
             # all-zero masks: reference would raise inside torch.multinomial; our stub returns -1
             # and action_to_position(pos, -1) leaves the offset at [0,0,0] (action_space.py:199-223).
+            if features:
+                import torch
+
+                _pol = actor.policy
+                actor.policy = lambda m, aid, tt, _p=_pol: torch.tensor(_p(m, aid, tt))  # .item() is called on it
             _, pos, _, action, _, _ = agents[a].step(a, t, episode, memory, None, moved)
             moved.append(pos)
             masks.append(actor.last_mask.copy())
             acts.append(int(action))
+        if features:  # coma_wrapper.py:135-144 (critic_map_knowledge = this step's fused global map)
+            step["state"] = np.array([
+                get_critic_input(t, info, next_global, memory, a, mapping.simulated_map, params).numpy().copy()
+                for a in range(n_agents)
+            ])
         _, rel, ab = ns.get_global_reward(
             global_map, next_global, "COMA", None, mapping.simulated_map, ass, acts, None, t, budget
         )

@@ -1,0 +1,72 @@
+"""Network-input features: actor observation [P,P,7] and critic state [P,P,12].
+
+CPU: the numpy restatement (oracle/numpy_features.py, cv2 pooling like the reference) reproduces the
+reference's own outputs in tests/golden bit for bit.
+GPU: ipp_features_actor / ipp_features_critic through BatchedIPPEnv vs the same golden outputs.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import golden_episodes, load_episode
+
+CASES = [p for p in golden_episodes() if "obs" in np.load(p).files]
+
+
+def test_feature_fixtures_present():
+    assert len(CASES) >= 5
+
+
+@pytest.mark.parametrize("path", CASES, ids=[p.split("episode_")[1] for p in CASES])
+def test_numpy_features_bit_exact(path):
+    from oracle import numpy_features as nf
+
+    g = load_episode(path)
+    env = nf.FeatureOracleEnv(g["params"], g["episode"])
+    T = len(g["reward_rel"]) if "g493" not in path else 3
+    for t in range(T):
+        _, _, _, obs = env.observe_features()
+        _, acts, states = env.act_features()
+        assert np.array_equal(acts, g["action"][t])
+        assert np.array_equal(obs, g["obs"][t]), t
+        assert np.array_equal(states, g["state"][t]), t
+
+
+def _feature_gate(ref, got, name, t):
+    """Entropy channels amplify belief differences by up to |log2((1-p)/p)| <= 13.3 and the 0/0.5/1 weights
+    are discontinuous at pooled values 0.499 / 0.501, so: atol 2e-4, and at most 0.1 % of lattice cells may
+    differ by a weight flip."""
+    d = np.abs(ref.astype(np.float64) - got.astype(np.float64))
+    bad = d > 2e-4 + 1e-5 * np.abs(ref)
+    assert bad.mean() <= 1e-3, (name, t, int(bad.sum()), float(d.max()))
+    return float(d[~bad].max()) if (~bad).any() else 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CASES, ids=[p.split("episode_")[1] for p in CASES])
+def test_gpu_features_vs_reference_golden(path):
+    import torch
+    from ipp_marl_b200 import BatchedIPPEnv
+
+    g = load_episode(path)
+    env = BatchedIPPEnv(g["params"], 1, device="cuda:0")
+    env.reset([g["episode"]])
+    T = len(g["reward_rel"])
+    worst = 0.0
+    for t in range(T):
+        env.observe()
+        obs = env.features_actor()
+        env.act(actions=g["action"][t][None])
+        state = env.features_critic(obs)
+        torch.cuda.synchronize()
+        assert np.array_equal(env.pos[0].cpu().numpy(), g["pos_next"][t])
+        o, s = obs[0].cpu().numpy(), state[0].cpu().numpy()
+        for ch in range(7):
+            worst = max(worst, _feature_gate(g["obs"][t][..., ch], o[..., ch], "obs%d" % ch, t))
+        for ch in range(12):
+            worst = max(worst, _feature_gate(g["state"][t][..., ch], s[..., ch], "state%d" % ch, t))
+        # exact channels: constants, position maps, action map
+        for ch in (0, 1, 2):
+            assert np.allclose(o[..., ch], g["obs"][t][..., ch], atol=1e-6), (t, ch)
+        for ch in (7, 11):
+            assert np.allclose(s[..., ch], g["state"][t][..., ch], atol=1e-6), (t, ch)
+    print("worst in-gate deviation", worst)

@@ -27,3 +27,20 @@ for (B, A), variant in itertools.product([(1024, 2), (8192, 2), (8192, 4), (6553
     byt = env.algorithmic_bytes_per_env_step()
     print(f"{variant:6s} B={B} A={A}: {ms/steps*1e3:.1f} us/step  {sps:.3e} env-steps/s  {sps*byt/1e9:.0f} GB/s algorithmic")
     del env
+
+# split mode with the network-input feature builders (observe -> features_actor -> act -> features_critic)
+params["experiment"]["missions"]["n_agents"] = 4
+env = BatchedIPPEnv(params, 8192, device="cuda:0")
+env.reset()
+obs = None
+for _ in range(15):
+    env.observe(); obs = env.features_actor(obs); env.act(); st = env.features_critic(obs)
+torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for ep in range(10):
+    env.reset()
+    for _ in range(15):
+        env.observe(); obs = env.features_actor(obs); env.act(); st = env.features_critic(obs, st)
+e1.record(); torch.cuda.synchronize()
+print(f"split+features B=8192 A=4: {e0.elapsed_time(e1)/150*1e3:.1f} us/step")

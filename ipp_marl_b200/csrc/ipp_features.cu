@@ -7,6 +7,7 @@
 // computeResizeAreaTab (fractional-overlap box filter when shrinking; the INTER_AREA flavour of
 // bilinear when the source is smaller than the lattice, e.g. the 10x10 footprint image at 5 m).
 // Everything about the latest measurements comes from the code bytes (ipp_cell.cuh) and the positions.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -313,6 +314,219 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// staged variants (grids whose map fits in shared memory): the map and the per-cell footprint values are
+// staged once with coalesced loads, then pooled separably (along y, then along x) out of shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pool_rows(const Tab& ty, const float* __restrict__ src, int32_t n_rows, int32_t src_w,
+                                          int32_t py, float* __restrict__ tmp) {
+  for (int32_t idx = threadIdx.x; idx < n_rows * py; idx += blockDim.x) {
+    const int32_t r = idx / py, lj = idx - r * py;
+    const int32_t y0 = ty.start(lj), ny = ty.count(lj);
+    float acc = 0.0f;
+    for (int32_t k = 0; k < ny; ++k) acc += ty.weight(lj, k) * src[r * src_w + y0 + k];
+    tmp[idx] = acc;
+  }
+}
+
+__device__ __forceinline__ float pool_col(const Tab& tx, const float* __restrict__ tmp, int32_t li, int32_t lj,
+                                          int32_t py) {
+  const int32_t x0 = tx.start(li), nx = tx.count(li);
+  float acc = 0.0f;
+  for (int32_t a = 0; a < nx; ++a) acc += tx.weight(li, a) * tmp[(x0 + a) * py + lj];
+  return acc;
+}
+
+template <int A>
+__global__ void __launch_bounds__(128)
+    features_actor_staged_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
+                                 const int32_t* __restrict__ pos_in, const uint8_t* __restrict__ comm,
+                                 const int32_t t, float* __restrict__ obs_out) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const int32_t n_cells = cfg.gx * cfg.gy, n_quads = (n_cells + 3) >> 2;
+  float* s_map = reinterpret_cast<float*>(fsm);           // [map_stride] fused local map
+  float* s_own = s_map + cfg.map_stride;                  // [map_stride] ownership values 0 / 0.5 / 1
+  float* s_tl = s_own + cfg.map_stride;                   // [gx][py]
+  float* s_to = s_tl + cfg.gx * cfg.py;                   // [gx][py]
+  float* s_img = s_to + cfg.gx * cfg.py;                  // [h][w] footprint image
+  const int32_t b = blockIdx.x / A, i = blockIdx.x - b * A;
+  __shared__ AgentGeo s_geo[A];
+  if (threadIdx.x < A) s_geo[threadIdx.x] = agent_geo(cfg, pos_in + ((int64_t)b * A + threadIdx.x) * 3);
+  __syncthreads();
+  const uint32_t received = comm[(int64_t)b * A + i];
+  const AgentGeo me = s_geo[i];
+  const float* local = st.local_maps + ((int64_t)b * A + i) * cfg.map_stride;
+  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
+  const Tab fx = get_tab(pt, 2 + 2 * me.iz), fy = get_tab(pt, 3 + 2 * me.iz);
+  const int32_t h = me.ry2, w = me.rx2;
+  float* s_ti = s_img + h * w;                            // [h][py]
+  int32_t b_yu = 0, b_yd = h, b_xl = 0, b_xr = w;
+  if (me.yu > me.ryu) b_yu = h - (me.yd - me.yu);
+  if (me.yd < me.ryu + me.ry2) b_yd = me.yd - me.yu;
+  if (me.xr < me.rxl + me.rx2) b_xr = me.xr - me.xl;
+  if (me.xl > me.rxl) b_xl = w - (me.xr - me.xl);
+  const float y_hi = cfg.y_hi[me.iz], y_lo = cfg.y_lo[me.iz];
+
+  for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
+    reinterpret_cast<float4*>(s_map)[q] = reinterpret_cast<const float4*>(local)[q];
+    const CodeWord<A> cw = load_code<A>(codes, q);
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t bit = 1u << c;
+      o[c] = 0.5f;
+#pragma unroll
+      for (int j = 0; j < A; ++j)
+        if (j != i && ((received >> j) & 1u) && (cw.byte(j) & bit)) o[c] = 0.0f;
+      if (cw.byte(i) & bit) o[c] = 1.0f;
+    }
+    reinterpret_cast<float4*>(s_own)[q] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  for (int32_t idx = threadIdx.x; idx < h * w; idx += blockDim.x) {
+    const int32_t u = idx / w, v = idx - u * w;
+    float val = 0.5f;
+    if (u >= b_xl && u < b_xr && v >= b_yu && v < b_yd) {
+      const int32_t cell = (me.xl + (u - b_xl)) * cfg.gy + (me.yu + (v - b_yu));
+      const uint32_t byte = load_code<A>(codes, cell >> 2).byte(i);
+      val = ((byte >> (4 + (cell & 3))) & 1u) ? y_hi : y_lo;
+    }
+    s_img[idx] = val;
+  }
+  __syncthreads();
+  pool_rows(ty, s_map, cfg.gx, cfg.gy, cfg.py, s_tl);
+  pool_rows(ty, s_own, cfg.gx, cfg.gy, cfg.py, s_to);
+  pool_rows(fy, s_img, h, w, cfg.py, s_ti);
+  __syncthreads();
+  const float budget = (float)(cfg.budget - t) / (float)cfg.budget;
+  const float agent_id = (float)(i + 1) / (float)A;
+  const float own_alt = (float)(me.zi + 1) / (float)(cfg.n_alt + 1);
+  for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
+    const int32_t li = c / cfg.py, lj = c - li * cfg.py;
+    const float pl = pool_col(tx, s_tl, li, lj, cfg.py);
+    const float pf_own = pool_col(tx, s_to, li, lj, cfg.py);
+    const float pimg = pool_col(fx, s_ti, li, lj, cfg.py);
+    float pm = 1.0f;
+    if (me.ix < 5 && li < 5 - me.ix) pm = 0.0f;
+    if (me.iy < 5 && lj < 5 - me.iy) pm = 0.0f;
+    if (me.ix > 5 && li >= cfg.px - 1 - (me.ix - 6)) pm = 0.0f;
+    if (me.iy > 5 && lj >= cfg.py - 1 - (me.iy - 6)) pm = 0.0f;
+    if (li == 5 && lj == 5) pm = own_alt;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      if (j == i || !((received >> j) & 1u)) continue;
+      const int32_t ri = s_geo[j].ix - me.ix + 5, rj = s_geo[j].iy - me.iy + 5;
+      if (ri >= 0 && ri < cfg.px && rj >= 0 && rj < cfg.px && ri == li && rj == lj)
+        pm = (float)(s_geo[j].zi + 1) / (float)(cfg.n_alt + 1);
+    }
+    const float2 wl = w_entropy(cfg, pl);
+    const float2 wf = w_entropy(cfg, pimg);
+    float* o = obs_out + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 7;
+    o[0] = budget;
+    o[1] = agent_id;
+    o[2] = pm;
+    o[3] = wl.x;
+    o[4] = wf.x;
+    o[5] = wl.y;
+    o[6] = pf_own;
+  }
+}
+
+template <int A>
+__global__ void __launch_bounds__(128)
+    features_critic_staged_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
+                                  const int32_t* __restrict__ pos_in, const int32_t* __restrict__ actions,
+                                  const int32_t t, const float* __restrict__ obs_in, float* __restrict__ state_out) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const int32_t n_cells = cfg.gx * cfg.gy, n_quads = (n_cells + 3) >> 2;
+  float* s_map = reinterpret_cast<float*>(fsm);  // global map
+  float* s_uni = s_map + cfg.map_stride;         // union footprint values 0.5 / 1
+  float* s_tg = s_uni + cfg.map_stride;
+  float* s_tu = s_tg + cfg.gx * cfg.py;
+  const int32_t b = blockIdx.x;
+  __shared__ AgentGeo s_geo[A];
+  __shared__ int32_t s_act[A];
+  if (threadIdx.x < A) {
+    s_geo[threadIdx.x] = agent_geo(cfg, pos_in + ((int64_t)b * A + threadIdx.x) * 3);
+    s_act[threadIdx.x] = actions[(int64_t)b * A + threadIdx.x];
+  }
+  const float* glob = st.global_map + (int64_t)b * cfg.map_stride;
+  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
+    reinterpret_cast<float4*>(s_map)[q] = reinterpret_cast<const float4*>(glob)[q];
+    const CodeWord<A> cw = load_code<A>(codes, q);
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < A; ++j) any |= cw.byte(j);
+    reinterpret_cast<float4*>(s_uni)[q] = make_float4((any & 1u) ? 1.0f : 0.5f, (any & 2u) ? 1.0f : 0.5f,
+                                                      (any & 4u) ? 1.0f : 0.5f, (any & 8u) ? 1.0f : 0.5f);
+  }
+  __syncthreads();
+  const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
+  pool_rows(ty, s_map, cfg.gx, cfg.gy, cfg.py, s_tg);
+  pool_rows(ty, s_uni, cfg.gx, cfg.gy, cfg.py, s_tu);
+  __syncthreads();
+  for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
+    const int32_t li = c / cfg.py, lj = c - li * cfg.py;
+    const float2 wg = w_entropy(cfg, pool_col(tx, s_tg, li, lj, cfg.py));
+    const float pu = pool_col(tx, s_tu, li, lj, cfg.py);
+    float posv = 0.0f;
+#pragma unroll
+    for (int j = 0; j < A; ++j)
+      if (s_geo[j].ix == li && s_geo[j].iy == lj) posv = (float)(s_geo[j].zi + 1) / (float)cfg.n_alt;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      float actv = 0.0f;
+#pragma unroll
+      for (int j = 0; j < A; ++j)
+        if (j != i && s_geo[j].ix == li && s_geo[j].iy == lj) actv = (float)(s_act[j] + 1) / (float)IPP_N_ACTIONS;
+      const float* o = obs_in + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 7;
+      float* sdst = state_out + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 12;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) sdst[k] = o[k];
+      sdst[7] = posv;
+      sdst[8] = wg.x;
+      sdst[9] = wg.y;
+      sdst[10] = pu;
+      sdst[11] = actv;
+    }
+  }
+}
+
+static size_t staged_actor_smem(const ipp_config& cfg) {
+  int hw = 0, hmax = 0;
+  for (int a = 0; a < cfg.n_alt; ++a) {
+    hw = std::max(hw, 4 * cfg.radius_x[a] * cfg.radius_y[a]);
+    hmax = std::max(hmax, 2 * cfg.radius_y[a]);
+  }
+  return sizeof(float) * ((size_t)2 * cfg.map_stride + 2 * (size_t)cfg.gx * cfg.py + hw + (size_t)hmax * cfg.py);
+}
+static size_t staged_critic_smem(const ipp_config& cfg) {
+  return sizeof(float) * ((size_t)2 * cfg.map_stride + 2 * (size_t)cfg.gx * cfg.py);
+}
+constexpr size_t FEAT_SMEM_LIMIT = 100 * 1024;
+
+template <int A>
+static cudaError_t actor_staged(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt, const int32_t* pos_in,
+                                const uint8_t* comm, int32_t t, float* obs_out, size_t smem, cudaStream_t s) {
+  auto kern = features_actor_staged_kernel<A>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)cfg.n_envs * A, 128, smem, s>>>(cfg, st, pt, pos_in, comm, t, obs_out);
+  return cudaGetLastError();
+}
+
+template <int A>
+static cudaError_t critic_staged(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                 const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
+                                 float* state_out, size_t smem, cudaStream_t s) {
+  auto kern = features_critic_staged_kernel<A>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)cfg.n_envs, 128, smem, s>>>(cfg, st, pt, pos_in, actions, t, obs_in, state_out);
+  return cudaGetLastError();
+}
+
 #define IPP_FEAT_DISPATCH(A_, CALL)                \
   switch (A_) {                                    \
     case 1: { constexpr int kA = 1; CALL; } break; \
@@ -329,6 +543,10 @@ __global__ void __launch_bounds__(128)
 cudaError_t launch_features_actor(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
                                   const int32_t* pos_in, const uint8_t* comm, int32_t t, float* obs_out,
                                   cudaStream_t s) {
+  const size_t smem = staged_actor_smem(cfg);
+  if (smem <= FEAT_SMEM_LIMIT) {
+    IPP_FEAT_DISPATCH(cfg.n_agents, return actor_staged<kA>(cfg, st, pt, pos_in, comm, t, obs_out, smem, s));
+  }
   IPP_FEAT_DISPATCH(cfg.n_agents, (features_actor_kernel<kA><<<(unsigned)cfg.n_envs * kA, 128, 0, s>>>(
                                       cfg, st, pt, pos_in, comm, t, obs_out)));
   return cudaGetLastError();
@@ -337,6 +555,11 @@ cudaError_t launch_features_actor(const ipp_config& cfg, const ipp_state& st, co
 cudaError_t launch_features_critic(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
                                    const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
                                    float* state_out, cudaStream_t s) {
+  const size_t smem = staged_critic_smem(cfg);
+  if (smem <= FEAT_SMEM_LIMIT) {
+    IPP_FEAT_DISPATCH(cfg.n_agents,
+                      return critic_staged<kA>(cfg, st, pt, pos_in, actions, t, obs_in, state_out, smem, s));
+  }
   IPP_FEAT_DISPATCH(cfg.n_agents, (features_critic_kernel<kA><<<(unsigned)cfg.n_envs, 128, 0, s>>>(
                                       cfg, st, pt, pos_in, actions, t, obs_in, state_out)));
   return cudaGetLastError();

@@ -1,0 +1,117 @@
+"""COMA learner arithmetic: vectorised TD(lambda), critic / actor losses and the
+network architectures vs values produced by the reference's own BatchMemory / CriticLearner / ActorLearner
+(tests/golden/coma_kats.npz, written by oracle/make_golden_coma.py).  CPU, float32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ipp_marl_b200 import coma
+
+K = np.load(os.path.join(os.path.dirname(__file__), "golden", "coma_kats.npz"))
+
+
+def _critic(seed):
+    torch.manual_seed(seed)
+    return coma.CriticNet()
+
+
+def test_architectures_and_seeded_init_match_reference():
+    seed = int(K["seed"])
+    critic = _critic(seed)
+    with torch.no_grad():
+        q0 = critic(torch.from_numpy(K["td_states"][0, 0])[None])[0]
+    assert np.allclose(q0.numpy(), K["critic_q0"], rtol=1e-5, atol=1e-6)
+    torch.manual_seed(seed + 1)
+    actor = coma.ActorNet()
+    with torch.no_grad():
+        p = actor(torch.from_numpy(K["lb_obs"]).float(), float(K["lb_eps"]))
+    assert np.allclose(p.numpy(), K["actor_probs0"], rtol=1e-5, atol=1e-6)
+    assert sum(x.numel() for x in actor.parameters()) == 2275846
+    assert sum(x.numel() for x in critic.parameters()) == 2307846
+
+
+def test_td_lambda_matches_reference_build_td_targets():
+    seed = int(K["seed"])
+    critic = _critic(seed)
+    states = torch.from_numpy(K["td_states"])            # [T, A, 11, 11, 12]
+    actions = torch.from_numpy(K["td_actions"])          # [T, A]
+    T, A = actions.shape
+    with torch.no_grad():
+        q = critic(states.flatten(0, 1)).view(T, A, 6)
+    q_taken = q.gather(2, actions[..., None]).squeeze(-1)             # [T, A]
+    rewards = torch.from_numpy(K["td_rewards"])[:, None].expand(T, A)
+    td = coma.td_lambda_targets(rewards.T.contiguous(), q_taken.T.contiguous(), 0.99, 0.8).T
+    assert np.allclose(td.numpy(), K["td_targets"], rtol=2e-5, atol=2e-6), np.abs(td.numpy() - K["td_targets"]).max()
+
+
+def test_critic_and_actor_losses_match_reference_learners():
+    seed = int(K["seed"])
+    torch.manual_seed(seed + 1)
+    actor = coma.ActorNet()
+    torch.manual_seed(seed + 2)
+    critic = coma.CriticNet()
+    st = torch.from_numpy(K["lb_state"])
+    act = torch.from_numpy(K["lb_act"])[:, 0]
+    td = torch.from_numpy(K["lb_td"])[:, 0]
+    q = critic(st)
+    assert np.allclose(q.detach().numpy(), K["critic_q_before"], rtol=1e-5, atol=1e-6)
+    loss_c = coma.coma_critic_loss(q, act, td)
+    assert abs(float(loss_c) - float(K["critic_loss"])) <= 1e-6 + 1e-5 * abs(float(K["critic_loss"]))
+    # one Adam step with the reference's learning rate reproduces its post-step Q values
+    opt = torch.optim.Adam(critic.parameters(), lr=1e-4)
+    opt.zero_grad()
+    loss_c.backward()
+    opt.step()
+    with torch.no_grad():
+        q_after = critic(st)
+    assert np.allclose(q_after.numpy(), K["critic_q_after"], rtol=1e-4, atol=1e-5)
+    probs = actor(torch.from_numpy(K["lb_obs"]).float(), float(K["lb_eps"]))
+    loss_a, adv = coma.coma_actor_loss(probs, torch.from_numpy(K["critic_q_after"]), act,
+                                       torch.from_numpy(K["lb_masks"]))
+    assert abs(float(loss_a) - float(K["actor_loss"])) <= 1e-6 + 1e-5 * abs(float(K["actor_loss"]))
+    assert abs(float(adv.mean()) - float(K["actor_adv_mean"])) <= 1e-6
+
+
+def test_flat_grad_allreduce_is_identity_without_process_group():
+    net = coma.CriticNet()
+    loss = net(torch.rand(2, 11, 11, 12)).sum()
+    loss.backward()
+    before = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+    coma.FlatGradAllReduce(net)()
+    after = [p.grad for p in net.parameters() if p.grad is not None]
+    assert all(torch.equal(a, b) for a, b in zip(before, after))
+
+
+def test_epsilon_schedule():
+    assert coma.epsilon(0) == 0.5 and coma.epsilon(20000) == 0.02
+    assert abs(coma.epsilon(5000) - (0.5 - 0.5 * 0.48)) < 1e-12
+
+
+@pytest.mark.gpu
+def test_trainer_runs_and_learns_signal():
+    """Two iterations of rollout + update on the GPU: finite losses, rewards identical to a policy-free
+    replay of the same actions (the env under the trainer is the parity-tested env)."""
+    import json
+
+    from ipp_marl_b200 import BatchedIPPEnv
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    params = json.load(open(os.path.join(root, "tests", "golden", "kats.json")))["synthetic50"]["params"]
+    env = BatchedIPPEnv(params, 64, device="cuda:0")
+    tr = coma.COMATrainer(env, params, minibatch=1024, data_passes=1)
+    r0 = tr.rollout(episodes=torch.arange(64) + 1)
+    acts = tr.buf_act.clone()
+    rew = tr.buf_rew.clone()
+    stats = tr.update()
+    assert all(torch.isfinite(v).all() for v in stats.values())
+    assert torch.isfinite(r0)
+    # replay: inject the recorded actions into a fresh env (fused step): same rewards
+    env2 = BatchedIPPEnv(params, 64, device="cuda:0")
+    env2.reset(torch.arange(64) + 1)
+    for t in range(env2.T):
+        rel, _, _ = env2.step(actions=acts[t])
+        assert torch.allclose(rel, rew[t], rtol=1e-5, atol=1e-5), t
+    r1 = tr.rollout(episodes=torch.arange(64) + 100)
+    assert torch.isfinite(r1)

@@ -318,26 +318,67 @@ __global__ void __launch_bounds__(128)
 // staged variants (grids whose map fits in shared memory): the map and the per-cell footprint values are
 // staged once with coalesced loads, then pooled separably (along y, then along x) out of shared memory.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pool_rows(const Tab& ty, const float* __restrict__ src, int32_t n_rows, int32_t src_w,
-                                          int32_t py, float* __restrict__ tmp) {
-  for (int32_t idx = threadIdx.x; idx < n_rows * py; idx += blockDim.x) {
-    const int32_t r = idx / py, lj = idx - r * py;
-    const int32_t y0 = ty.start(lj), ny = ty.count(lj);
-    float acc = 0.0f;
-    for (int32_t k = 0; k < ny; ++k) acc += ty.weight(lj, k) * src[r * src_w + y0 + k];
-    tmp[idx] = acc;
+// Fixed-tap pooling: the tap tables are zero padded to maxt <= MT, so a fully unrolled MT-tap loop with clamped
+// source offsets gives the same sums without per-tap loop control.  Thread (rr, lj) keeps the taps of lattice
+// column lj in registers and walks rows rr, rr + rpr, ...
+template <int MT>
+struct Taps {
+  float w[MT];
+  int32_t off[MT];
+  int32_t first;
+};
+
+template <int MT>
+__device__ __forceinline__ Taps<MT> load_taps(const Tab& t, int32_t d, int32_t extent) {
+  Taps<MT> r;
+  r.first = t.start(d);
+#pragma unroll
+  for (int k = 0; k < MT; ++k) {
+    r.w[k] = k < t.maxt ? t.weight(d, k) : 0.0f;
+    r.off[k] = min(k, extent - 1 - r.first);
+  }
+  return r;
+}
+
+template <int MT, int NMAP>
+__device__ __forceinline__ void pool_rows(const Taps<MT>& tp, const float* const (&src)[NMAP], float* const (&tmp)[NMAP],
+                                          int32_t n_rows, int32_t src_w, int32_t py, int32_t rr, int32_t rpr,
+                                          int32_t lj) {
+  if (rr >= rpr) return;
+  for (int32_t r = rr; r < n_rows; r += rpr) {
+    const int32_t base = r * src_w + tp.first;
+#pragma unroll
+    for (int m = 0; m < NMAP; ++m) {
+      const float* s = src[m] + base;
+      float acc = 0.0f;
+#pragma unroll
+      for (int k = 0; k < MT; ++k) acc = fmaf(tp.w[k], s[tp.off[k]], acc);
+      tmp[m][r * py + lj] = acc;
+    }
   }
 }
 
-__device__ __forceinline__ float pool_col(const Tab& tx, const float* __restrict__ tmp, int32_t li, int32_t lj,
-                                          int32_t py) {
-  const int32_t x0 = tx.start(li), nx = tx.count(li);
+template <int MT>
+__device__ __forceinline__ float pool_col(const Taps<MT>& tp, const float* __restrict__ tmp, int32_t lj, int32_t py) {
+  const float* s = tmp + tp.first * py + lj;
   float acc = 0.0f;
-  for (int32_t a = 0; a < nx; ++a) acc += tx.weight(li, a) * tmp[(x0 + a) * py + lj];
+#pragma unroll
+  for (int k = 0; k < MT; ++k) acc = fmaf(tp.w[k], s[tp.off[k] * py], acc);
   return acc;
 }
 
+// low nibbles (cell-in-footprint bits) of the bytes selected by `mask`, OR-folded into one nibble
 template <int A>
+__device__ __forceinline__ uint32_t fold_nibbles(const CodeWord<A>& cw, const uint32_t (&mask)[CodeWord<A>::WORDS]) {
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < CodeWord<A>::WORDS; ++k) x |= cw.w[k] & mask[k];
+  x |= x >> 16;
+  x |= x >> 8;
+  return x & 0xFu;
+}
+
+template <int A, int MT>
 __global__ void __launch_bounds__(128)
     features_actor_staged_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
                                  const int32_t* __restrict__ pos_in, const uint8_t* __restrict__ comm,
@@ -357,10 +398,10 @@ __global__ void __launch_bounds__(128)
   const AgentGeo me = s_geo[i];
   const float* local = st.local_maps + ((int64_t)b * A + i) * cfg.map_stride;
   const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
-  const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
-  const Tab fx = get_tab(pt, 2 + 2 * me.iz), fy = get_tab(pt, 3 + 2 * me.iz);
   const int32_t h = me.ry2, w = me.rx2;
   float* s_ti = s_img + h * w;                            // [h][py]
+  const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
+  const Tab fx = get_tab(pt, 2 + 2 * me.iz), fy = get_tab(pt, 3 + 2 * me.iz);
   int32_t b_yu = 0, b_yd = h, b_xl = 0, b_xr = w;
   if (me.yu > me.ryu) b_yu = h - (me.yd - me.yu);
   if (me.yd < me.ryu + me.ry2) b_yd = me.yd - me.yu;
@@ -368,44 +409,65 @@ __global__ void __launch_bounds__(128)
   if (me.xl > me.rxl) b_xl = w - (me.xr - me.xl);
   const float y_hi = cfg.y_hi[me.iz], y_lo = cfg.y_lo[me.iz];
 
+  uint32_t others_mask[CodeWord<A>::WORDS] = {}, own_mask[CodeWord<A>::WORDS] = {};
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    if (j == i) own_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
+    else if ((received >> j) & 1u) others_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
+  }
   for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
     reinterpret_cast<float4*>(s_map)[q] = reinterpret_cast<const float4*>(local)[q];
     const CodeWord<A> cw = load_code<A>(codes, q);
+    const uint32_t own = fold_nibbles<A>(cw, own_mask), oth = fold_nibbles<A>(cw, others_mask) & ~own;
     float o[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t bit = 1u << c;
-      o[c] = 0.5f;
-#pragma unroll
-      for (int j = 0; j < A; ++j)
-        if (j != i && ((received >> j) & 1u) && (cw.byte(j) & bit)) o[c] = 0.0f;
-      if (cw.byte(i) & bit) o[c] = 1.0f;
-    }
+    for (int c = 0; c < 4; ++c) o[c] = ((own >> c) & 1u) ? 1.0f : (((oth >> c) & 1u) ? 0.0f : 0.5f);
     reinterpret_cast<float4*>(s_own)[q] = make_float4(o[0], o[1], o[2], o[3]);
   }
-  for (int32_t idx = threadIdx.x; idx < h * w; idx += blockDim.x) {
-    const int32_t u = idx / w, v = idx - u * w;
-    float val = 0.5f;
-    if (u >= b_xl && u < b_xr && v >= b_yu && v < b_yd) {
-      const int32_t cell = (me.xl + (u - b_xl)) * cfg.gy + (me.yu + (v - b_yu));
-      const uint32_t byte = load_code<A>(codes, cell >> 2).byte(i);
-      val = ((byte >> (4 + (cell & 3))) & 1u) ? y_hi : y_lo;
+  {
+    // footprint image, element (u, v) walked without per-element divisions
+    const int32_t du = (int32_t)blockDim.x / w, dv = (int32_t)blockDim.x - du * w;
+    int32_t u = (int32_t)threadIdx.x / w, v = (int32_t)threadIdx.x - u * w;
+    for (int32_t idx = threadIdx.x; idx < h * w; idx += blockDim.x) {
+      float val = 0.5f;
+      if (u >= b_xl && u < b_xr && v >= b_yu && v < b_yd) {
+        const int32_t cell = (me.xl + (u - b_xl)) * cfg.gy + (me.yu + (v - b_yu));
+        const uint32_t byte = load_code<A>(codes, cell >> 2).byte(i);
+        val = ((byte >> (4 + (cell & 3))) & 1u) ? y_hi : y_lo;
+      }
+      s_img[idx] = val;
+      u += du;
+      v += dv;
+      if (v >= w) {
+        v -= w;
+        ++u;
+      }
     }
-    s_img[idx] = val;
   }
+  const int32_t rpr = (int32_t)blockDim.x / cfg.py;
+  const int32_t rr = (int32_t)threadIdx.x / cfg.py, lj_r = (int32_t)threadIdx.x - rr * cfg.py;
+  const Taps<MT> tap_y = load_taps<MT>(ty, lj_r, cfg.gy);
+  const Taps<MT> tap_fy = load_taps<MT>(fy, lj_r, w);
   __syncthreads();
-  pool_rows(ty, s_map, cfg.gx, cfg.gy, cfg.py, s_tl);
-  pool_rows(ty, s_own, cfg.gx, cfg.gy, cfg.py, s_to);
-  pool_rows(fy, s_img, h, w, cfg.py, s_ti);
+  {
+    const float* const src2[2] = {s_map, s_own};
+    float* const tmp2[2] = {s_tl, s_to};
+    pool_rows<MT, 2>(tap_y, src2, tmp2, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+    const float* const src1[1] = {s_img};
+    float* const tmp1[1] = {s_ti};
+    pool_rows<MT, 1>(tap_fy, src1, tmp1, h, w, cfg.py, rr, rpr, lj_r);
+  }
   __syncthreads();
   const float budget = (float)(cfg.budget - t) / (float)cfg.budget;
   const float agent_id = (float)(i + 1) / (float)A;
   const float own_alt = (float)(me.zi + 1) / (float)(cfg.n_alt + 1);
   for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
     const int32_t li = c / cfg.py, lj = c - li * cfg.py;
-    const float pl = pool_col(tx, s_tl, li, lj, cfg.py);
-    const float pf_own = pool_col(tx, s_to, li, lj, cfg.py);
-    const float pimg = pool_col(fx, s_ti, li, lj, cfg.py);
+    const Taps<MT> tap_x = load_taps<MT>(tx, li, cfg.gx);
+    const float pl = pool_col<MT>(tap_x, s_tl, lj, cfg.py);
+    const float pf_own = pool_col<MT>(tap_x, s_to, lj, cfg.py);
+    const Taps<MT> tap_fx = load_taps<MT>(fx, li, h);
+    const float pimg = pool_col<MT>(tap_fx, s_ti, lj, cfg.py);
     float pm = 1.0f;
     if (me.ix < 5 && li < 5 - me.ix) pm = 0.0f;
     if (me.iy < 5 && lj < 5 - me.iy) pm = 0.0f;
@@ -432,13 +494,14 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-template <int A>
+template <int A, int MT>
 __global__ void __launch_bounds__(128)
     features_critic_staged_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
                                   const int32_t* __restrict__ pos_in, const int32_t* __restrict__ actions,
                                   const int32_t t, const float* __restrict__ obs_in, float* __restrict__ state_out) {
   extern __shared__ __align__(16) unsigned char fsm[];
   const int32_t n_cells = cfg.gx * cfg.gy, n_quads = (n_cells + 3) >> 2;
+  const int32_t n_lat = cfg.px * cfg.py;
   float* s_map = reinterpret_cast<float*>(fsm);  // global map
   float* s_uni = s_map + cfg.map_stride;         // union footprint values 0.5 / 1
   float* s_tg = s_uni + cfg.map_stride;
@@ -452,24 +515,31 @@ __global__ void __launch_bounds__(128)
   }
   const float* glob = st.global_map + (int64_t)b * cfg.map_stride;
   const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  uint32_t all_mask[CodeWord<A>::WORDS] = {};
+#pragma unroll
+  for (int j = 0; j < A; ++j) all_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
   for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
     reinterpret_cast<float4*>(s_map)[q] = reinterpret_cast<const float4*>(glob)[q];
-    const CodeWord<A> cw = load_code<A>(codes, q);
-    uint32_t any = 0;
-#pragma unroll
-    for (int j = 0; j < A; ++j) any |= cw.byte(j);
+    const uint32_t any = fold_nibbles<A>(load_code<A>(codes, q), all_mask);
     reinterpret_cast<float4*>(s_uni)[q] = make_float4((any & 1u) ? 1.0f : 0.5f, (any & 2u) ? 1.0f : 0.5f,
                                                       (any & 4u) ? 1.0f : 0.5f, (any & 8u) ? 1.0f : 0.5f);
   }
-  __syncthreads();
   const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
-  pool_rows(ty, s_map, cfg.gx, cfg.gy, cfg.py, s_tg);
-  pool_rows(ty, s_uni, cfg.gx, cfg.gy, cfg.py, s_tu);
+  const int32_t rpr = (int32_t)blockDim.x / cfg.py;
+  const int32_t rr = (int32_t)threadIdx.x / cfg.py, lj_r = (int32_t)threadIdx.x - rr * cfg.py;
+  const Taps<MT> tap_y = load_taps<MT>(ty, lj_r, cfg.gy);
   __syncthreads();
-  for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
+  {
+    const float* const src2[2] = {s_map, s_uni};
+    float* const tmp2[2] = {s_tg, s_tu};
+    pool_rows<MT, 2>(tap_y, src2, tmp2, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+  }
+  __syncthreads();
+  for (int32_t c = threadIdx.x; c < n_lat; c += blockDim.x) {
     const int32_t li = c / cfg.py, lj = c - li * cfg.py;
-    const float2 wg = w_entropy(cfg, pool_col(tx, s_tg, li, lj, cfg.py));
-    const float pu = pool_col(tx, s_tu, li, lj, cfg.py);
+    const Taps<MT> tap_x = load_taps<MT>(tx, li, cfg.gx);
+    const float2 wg = w_entropy(cfg, pool_col<MT>(tap_x, s_tg, lj, cfg.py));
+    const float pu = pool_col<MT>(tap_x, s_tu, lj, cfg.py);
     float posv = 0.0f;
 #pragma unroll
     for (int j = 0; j < A; ++j)
@@ -480,15 +550,11 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
       for (int j = 0; j < A; ++j)
         if (j != i && s_geo[j].ix == li && s_geo[j].iy == lj) actv = (float)(s_act[j] + 1) / (float)IPP_N_ACTIONS;
-      const float* o = obs_in + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 7;
-      float* sdst = state_out + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 12;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) sdst[k] = o[k];
-      sdst[7] = posv;
-      sdst[8] = wg.x;
-      sdst[9] = wg.y;
-      sdst[10] = pu;
-      sdst[11] = actv;
+      const float* o = obs_in + (((int64_t)b * A + i) * n_lat + c) * 7;
+      float4* sdst = reinterpret_cast<float4*>(state_out + (((int64_t)b * A + i) * n_lat + c) * 12);  // 48 B cells
+      sdst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      sdst[1] = make_float4(o[4], o[5], o[6], posv);
+      sdst[2] = make_float4(wg.x, wg.y, pu, actv);
     }
   }
 }
@@ -506,13 +572,43 @@ static size_t staged_critic_smem(const ipp_config& cfg) {
 }
 constexpr size_t FEAT_SMEM_LIMIT = 100 * 1024;
 
+constexpr int FEAT_MAX_TAPS = 8;  // staged kernels are instantiated for 4 / 6 / 8 taps
+
+template <int A, int MT>
+static cudaError_t actor_staged_mt(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                   const int32_t* pos_in, const uint8_t* comm, int32_t t, float* obs_out, size_t smem,
+                                   cudaStream_t s) {
+  auto kern = features_actor_staged_kernel<A, MT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  kern<<<(unsigned)cfg.n_envs * A, 128, smem, s>>>(cfg, st, pt, pos_in, comm, t, obs_out);
+  return cudaGetLastError();
+}
+
 template <int A>
 static cudaError_t actor_staged(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt, const int32_t* pos_in,
                                 const uint8_t* comm, int32_t t, float* obs_out, size_t smem, cudaStream_t s) {
-  auto kern = features_actor_staged_kernel<A>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  kern<<<(unsigned)cfg.n_envs * A, 128, smem, s>>>(cfg, st, pt, pos_in, comm, t, obs_out);
+  if (pt.maxt <= 4) return actor_staged_mt<A, 4>(cfg, st, pt, pos_in, comm, t, obs_out, smem, s);
+  if (pt.maxt <= 6) return actor_staged_mt<A, 6>(cfg, st, pt, pos_in, comm, t, obs_out, smem, s);
+  return actor_staged_mt<A, 8>(cfg, st, pt, pos_in, comm, t, obs_out, smem, s);
+}
+
+template <int A, int MT>
+static cudaError_t critic_staged_mt(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
+                                    const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
+                                    float* state_out, size_t smem, cudaStream_t s) {
+  auto kern = features_critic_staged_kernel<A, MT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  kern<<<(unsigned)cfg.n_envs, 128, smem, s>>>(cfg, st, pt, pos_in, actions, t, obs_in, state_out);
   return cudaGetLastError();
 }
 
@@ -520,11 +616,9 @@ template <int A>
 static cudaError_t critic_staged(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,
                                  const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
                                  float* state_out, size_t smem, cudaStream_t s) {
-  auto kern = features_critic_staged_kernel<A>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
-  if (e != cudaSuccess) return e;
-  kern<<<(unsigned)cfg.n_envs, 128, smem, s>>>(cfg, st, pt, pos_in, actions, t, obs_in, state_out);
-  return cudaGetLastError();
+  if (pt.maxt <= 4) return critic_staged_mt<A, 4>(cfg, st, pt, pos_in, actions, t, obs_in, state_out, smem, s);
+  if (pt.maxt <= 6) return critic_staged_mt<A, 6>(cfg, st, pt, pos_in, actions, t, obs_in, state_out, smem, s);
+  return critic_staged_mt<A, 8>(cfg, st, pt, pos_in, actions, t, obs_in, state_out, smem, s);
 }
 
 #define IPP_FEAT_DISPATCH(A_, CALL)                \
@@ -544,7 +638,7 @@ cudaError_t launch_features_actor(const ipp_config& cfg, const ipp_state& st, co
                                   const int32_t* pos_in, const uint8_t* comm, int32_t t, float* obs_out,
                                   cudaStream_t s) {
   const size_t smem = staged_actor_smem(cfg);
-  if (smem <= FEAT_SMEM_LIMIT) {
+  if (smem <= FEAT_SMEM_LIMIT && pt.maxt <= FEAT_MAX_TAPS && cfg.py <= 128) {
     IPP_FEAT_DISPATCH(cfg.n_agents, return actor_staged<kA>(cfg, st, pt, pos_in, comm, t, obs_out, smem, s));
   }
   IPP_FEAT_DISPATCH(cfg.n_agents, (features_actor_kernel<kA><<<(unsigned)cfg.n_envs * kA, 128, 0, s>>>(
@@ -556,7 +650,8 @@ cudaError_t launch_features_critic(const ipp_config& cfg, const ipp_state& st, c
                                    const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
                                    float* state_out, cudaStream_t s) {
   const size_t smem = staged_critic_smem(cfg);
-  if (smem <= FEAT_SMEM_LIMIT) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(state_out) & 15u) == 0;  // float4 stores of the 48 B cells
+  if (smem <= FEAT_SMEM_LIMIT && pt.maxt <= FEAT_MAX_TAPS && cfg.py <= 128 && aligned) {
     IPP_FEAT_DISPATCH(cfg.n_agents,
                       return critic_staged<kA>(cfg, st, pt, pos_in, actions, t, obs_in, state_out, smem, s));
   }

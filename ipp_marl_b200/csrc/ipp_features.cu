@@ -13,6 +13,7 @@
 
 #include "ipp_cell.cuh"
 #include "ipp_launch.h"
+#include "ipp_ptx.cuh"
 
 namespace ipp {
 
@@ -112,7 +113,7 @@ __device__ __forceinline__ Tab get_tab(const PoolTables& pt, int k) {
 __device__ __forceinline__ float2 w_entropy(const ipp_config& cfg, float v) {
   const float w = v > 0.501f ? 1.0f : (v < 0.499f ? 0.0f : 0.5f);
   const float c = fminf(fmaxf(v, cfg.p_min), cfg.p_max);
-  const float h = -c * log2f(c) - (1.0f - c) * log2f(1.0f - c);
+  const float h = -c * __log2f(c) - (1.0f - c) * __log2f(1.0f - c);
   return make_float2(w * h, c);
 }
 
@@ -318,43 +319,41 @@ __global__ void __launch_bounds__(128)
 // staged variants (grids whose map fits in shared memory): the map and the per-cell footprint values are
 // staged once with coalesced loads, then pooled separably (along y, then along x) out of shared memory.
 // ------------------------------------------------------------------------------------------------
-// Fixed-tap pooling: the tap tables are zero padded to maxt <= MT, so a fully unrolled MT-tap loop with clamped
-// source offsets gives the same sums without per-tap loop control.  Thread (rr, lj) keeps the taps of lattice
-// column lj in registers and walks rows rr, rr + rpr, ...
+// Fixed-tap pooling: the tap tables are zero padded to maxt <= MT, so a fully unrolled MT-tap loop gives the same
+// sums without per-tap loop control.  A zero-weight tap may index up to MT-1 elements past the end of its source
+// array; the shared-memory layout puts finite data (zero pads or arrays already written) behind every pooled array,
+// so those taps contribute exactly +0.  Thread (rr, lj) keeps the taps of lattice column lj in registers and
+// walks rows rr, rr + rpr, ...
 template <int MT>
 struct Taps {
   float w[MT];
-  int32_t off[MT];
   int32_t first;
 };
 
 template <int MT>
-__device__ __forceinline__ Taps<MT> load_taps(const Tab& t, int32_t d, int32_t extent) {
+__device__ __forceinline__ Taps<MT> load_taps(const Tab& t, int32_t d) {
   Taps<MT> r;
   r.first = t.start(d);
 #pragma unroll
-  for (int k = 0; k < MT; ++k) {
-    r.w[k] = k < t.maxt ? t.weight(d, k) : 0.0f;
-    r.off[k] = min(k, extent - 1 - r.first);
-  }
+  for (int k = 0; k < MT; ++k) r.w[k] = k < t.maxt ? t.weight(d, k) : 0.0f;
   return r;
 }
 
-template <int MT, int NMAP>
-__device__ __forceinline__ void pool_rows(const Taps<MT>& tp, const float* const (&src)[NMAP], float* const (&tmp)[NMAP],
-                                          int32_t n_rows, int32_t src_w, int32_t py, int32_t rr, int32_t rpr,
-                                          int32_t lj) {
+__device__ __forceinline__ float tap_value(const float* s, int k) { return s[k]; }
+__device__ __forceinline__ float tap_value(const uint8_t* s, int k) { return (float)s[k]; }
+
+// tmp[r][lj] = scale * sum_k w[k] * src[r][first + k]
+template <int MT, typename T>
+__device__ __forceinline__ void pool_rows(const Taps<MT>& tp, const T* __restrict__ src, float scale,
+                                          float* __restrict__ tmp, int32_t n_rows, int32_t src_w, int32_t py,
+                                          int32_t rr, int32_t rpr, int32_t lj) {
   if (rr >= rpr) return;
   for (int32_t r = rr; r < n_rows; r += rpr) {
-    const int32_t base = r * src_w + tp.first;
+    const T* s = src + r * src_w + tp.first;
+    float acc = 0.0f;
 #pragma unroll
-    for (int m = 0; m < NMAP; ++m) {
-      const float* s = src[m] + base;
-      float acc = 0.0f;
-#pragma unroll
-      for (int k = 0; k < MT; ++k) acc = fmaf(tp.w[k], s[tp.off[k]], acc);
-      tmp[m][r * py + lj] = acc;
-    }
+    for (int k = 0; k < MT; ++k) acc = fmaf(tp.w[k], tap_value(s, k), acc);
+    tmp[r * py + lj] = acc * scale;
   }
 }
 
@@ -363,7 +362,7 @@ __device__ __forceinline__ float pool_col(const Taps<MT>& tp, const float* __res
   const float* s = tmp + tp.first * py + lj;
   float acc = 0.0f;
 #pragma unroll
-  for (int k = 0; k < MT; ++k) acc = fmaf(tp.w[k], s[tp.off[k] * py], acc);
+  for (int k = 0; k < MT; ++k) acc = fmaf(tp.w[k], s[k * py], acc);
   return acc;
 }
 
@@ -378,28 +377,59 @@ __device__ __forceinline__ uint32_t fold_nibbles(const CodeWord<A>& cw, const ui
   return x & 0xFu;
 }
 
+// bit c of a nibble -> byte c of a word (0 / 1)
+__device__ __forceinline__ uint32_t spread_nibble(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ unsigned char* align16(void* p) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15u) & ~(uintptr_t)15u);
+}
+
+constexpr int FEAT_PAD = 8;  // floats / bytes behind a row-pooled array (>= MT - 1)
+
 template <int A, int MT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 9)
     features_actor_staged_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const PoolTables pt,
                                  const int32_t* __restrict__ pos_in, const uint8_t* __restrict__ comm,
                                  const int32_t t, float* __restrict__ obs_out) {
   extern __shared__ __align__(16) unsigned char fsm[];
   const int32_t n_cells = cfg.gx * cfg.gy, n_quads = (n_cells + 3) >> 2;
-  float* s_map = reinterpret_cast<float*>(fsm);           // [map_stride] fused local map
-  float* s_own = s_map + cfg.map_stride;                  // [map_stride] ownership values 0 / 0.5 / 1
-  float* s_tl = s_own + cfg.map_stride;                   // [gx][py]
-  float* s_to = s_tl + cfg.gx * cfg.py;                   // [gx][py]
-  float* s_img = s_to + cfg.gx * cfg.py;                  // [h][w] footprint image
+  const int32_t n_lat = cfg.px * cfg.py;
   const int32_t b = blockIdx.x / A, i = blockIdx.x - b * A;
   __shared__ AgentGeo s_geo[A];
+  __shared__ __align__(8) uint64_t s_bar;
   if (threadIdx.x < A) s_geo[threadIdx.x] = agent_geo(cfg, pos_in + ((int64_t)b * A + threadIdx.x) * 3);
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(ptx::smem_u32(&s_bar), 1);
+    ptx::fence_mbar_init();
+  }
   __syncthreads();
-  const uint32_t received = comm[(int64_t)b * A + i];
   const AgentGeo me = s_geo[i];
-  const float* local = st.local_maps + ((int64_t)b * A + i) * cfg.map_stride;
-  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
   const int32_t h = me.ry2, w = me.rx2;
-  float* s_ti = s_img + h * w;                            // [h][py]
+  // layout (every pooled array is followed by finite data, see Taps):
+  //   s_map | pad | s_tl | s_to | s_ti | column pad | s_img | pad | s_own (bytes) | pad | codes
+  float* s_map = reinterpret_cast<float*>(fsm);      // [map_stride] fused local map, filled by the bulk copy
+  float* s_tl = s_map + cfg.map_stride + FEAT_PAD;   // [gx][py] row-pooled local map
+  float* s_to = s_tl + cfg.gx * cfg.py;              // [gx][py] row-pooled ownership
+  float* s_ti = s_to + cfg.gx * cfg.py;              // [h][py]  row-pooled footprint image
+  float* s_cpad = s_ti + h * cfg.py;                 // [MT][py] zeros
+  float* s_img = s_cpad + MT * cfg.py;               // [h][w]   footprint image
+  uint8_t* s_own = reinterpret_cast<uint8_t*>(s_img + h * w + FEAT_PAD);  // [4 n_quads] 2 own / 1 unseen / 0 others
+  unsigned char* codes = align16(s_own + 4 * n_quads + FEAT_PAD);         // [code_stride] this env's codes
+  if (threadIdx.x == 0) {  // map + code row by the bulk-copy engine while the block sets up its tap registers
+    const uint32_t bar = ptx::smem_u32(&s_bar), map_bytes = (uint32_t)n_quads * 16u;
+    ptx::mbar_arrive_expect_tx(bar, map_bytes + (uint32_t)cfg.code_stride);
+    ptx::bulk_load(ptx::smem_u32(s_map), st.local_maps + ((int64_t)b * A + i) * cfg.map_stride, map_bytes, bar);
+    ptx::bulk_load(ptx::smem_u32(codes),
+                   st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, (uint32_t)cfg.code_stride, bar);
+  }
+  // zero pads (disjoint from the bulk-copy destinations)
+  for (int32_t k = 4 * n_quads + (int32_t)threadIdx.x; k < cfg.map_stride + FEAT_PAD; k += blockDim.x) s_map[k] = 0.0f;
+  for (int32_t k = threadIdx.x; k < MT * cfg.py; k += blockDim.x) s_cpad[k] = 0.0f;
+  if (threadIdx.x < FEAT_PAD) {
+    s_img[h * w + threadIdx.x] = 0.0f;
+    s_own[4 * n_quads + threadIdx.x] = 0;
+  }
+  const uint32_t received = comm[(int64_t)b * A + i];
   const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
   const Tab fx = get_tab(pt, 2 + 2 * me.iz), fy = get_tab(pt, 3 + 2 * me.iz);
   int32_t b_yu = 0, b_yd = h, b_xl = 0, b_xr = w;
@@ -409,20 +439,24 @@ __global__ void __launch_bounds__(128)
   if (me.xl > me.rxl) b_xl = w - (me.xr - me.xl);
   const float y_hi = cfg.y_hi[me.iz], y_lo = cfg.y_lo[me.iz];
 
-  uint32_t others_mask[CodeWord<A>::WORDS] = {}, own_mask[CodeWord<A>::WORDS] = {};
+  uint32_t others_mask[CodeWord<A>::WORDS] = {};
 #pragma unroll
-  for (int j = 0; j < A; ++j) {
-    if (j == i) own_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
-    else if ((received >> j) & 1u) others_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
-  }
+  for (int j = 0; j < A; ++j)
+    if (j != i && ((received >> j) & 1u)) others_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
+  // thread (rr, lj_r): lattice column lj_r of rows rr, rr + rpr, ... in the row pass; lattice cell (rr, lj_r) in the
+  // column pass (first round)
+  const int32_t rpr = (int32_t)blockDim.x / cfg.py;
+  const int32_t rr = (int32_t)threadIdx.x / cfg.py, lj_r = (int32_t)threadIdx.x - rr * cfg.py;
+  const Taps<MT> tap_y = load_taps<MT>(ty, lj_r);
+  const Taps<MT> tap_fy = load_taps<MT>(fy, lj_r);
+  const int32_t li_r = min(rr, cfg.px - 1);
+  Taps<MT> tap_x = load_taps<MT>(tx, li_r);
+  Taps<MT> tap_fx = load_taps<MT>(fx, li_r);
+  ptx::mbar_wait(ptx::smem_u32(&s_bar), 0);
   for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
-    reinterpret_cast<float4*>(s_map)[q] = reinterpret_cast<const float4*>(local)[q];
     const CodeWord<A> cw = load_code<A>(codes, q);
-    const uint32_t own = fold_nibbles<A>(cw, own_mask), oth = fold_nibbles<A>(cw, others_mask) & ~own;
-    float o[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) o[c] = ((own >> c) & 1u) ? 1.0f : (((oth >> c) & 1u) ? 0.0f : 0.5f);
-    reinterpret_cast<float4*>(s_own)[q] = make_float4(o[0], o[1], o[2], o[3]);
+    const uint32_t own = cw.byte(i) & 0xFu, oth = fold_nibbles<A>(cw, others_mask) & ~own;
+    reinterpret_cast<uint32_t*>(s_own)[q] = 0x01010101u + spread_nibble(own) - spread_nibble(oth);
   }
   {
     // footprint image, element (u, v) walked without per-element divisions
@@ -444,29 +478,24 @@ __global__ void __launch_bounds__(128)
       }
     }
   }
-  const int32_t rpr = (int32_t)blockDim.x / cfg.py;
-  const int32_t rr = (int32_t)threadIdx.x / cfg.py, lj_r = (int32_t)threadIdx.x - rr * cfg.py;
-  const Taps<MT> tap_y = load_taps<MT>(ty, lj_r, cfg.gy);
-  const Taps<MT> tap_fy = load_taps<MT>(fy, lj_r, w);
   __syncthreads();
-  {
-    const float* const src2[2] = {s_map, s_own};
-    float* const tmp2[2] = {s_tl, s_to};
-    pool_rows<MT, 2>(tap_y, src2, tmp2, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
-    const float* const src1[1] = {s_img};
-    float* const tmp1[1] = {s_ti};
-    pool_rows<MT, 1>(tap_fy, src1, tmp1, h, w, cfg.py, rr, rpr, lj_r);
-  }
+  pool_rows<MT>(tap_y, s_map, 1.0f, s_tl, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+  pool_rows<MT>(tap_y, s_own, 0.5f, s_to, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+  pool_rows<MT>(tap_fy, s_img, 1.0f, s_ti, h, w, cfg.py, rr, rpr, lj_r);
   __syncthreads();
   const float budget = (float)(cfg.budget - t) / (float)cfg.budget;
   const float agent_id = (float)(i + 1) / (float)A;
   const float own_alt = (float)(me.zi + 1) / (float)(cfg.n_alt + 1);
-  for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
-    const int32_t li = c / cfg.py, lj = c - li * cfg.py;
-    const Taps<MT> tap_x = load_taps<MT>(tx, li, cfg.gx);
+  for (int32_t c = threadIdx.x; c < n_lat; c += blockDim.x) {
+    int32_t li = rr, lj = lj_r;
+    if (c != (int32_t)threadIdx.x) {
+      li = c / cfg.py;
+      lj = c - li * cfg.py;
+      tap_x = load_taps<MT>(tx, li);
+      tap_fx = load_taps<MT>(fx, li);
+    }
     const float pl = pool_col<MT>(tap_x, s_tl, lj, cfg.py);
     const float pf_own = pool_col<MT>(tap_x, s_to, lj, cfg.py);
-    const Taps<MT> tap_fx = load_taps<MT>(fx, li, h);
     const float pimg = pool_col<MT>(tap_fx, s_ti, lj, cfg.py);
     float pm = 1.0f;
     if (me.ix < 5 && li < 5 - me.ix) pm = 0.0f;
@@ -483,7 +512,7 @@ __global__ void __launch_bounds__(128)
     }
     const float2 wl = w_entropy(cfg, pl);
     const float2 wf = w_entropy(cfg, pimg);
-    float* o = obs_out + (((int64_t)b * A + i) * cfg.px * cfg.py + c) * 7;
+    float* o = obs_out + (((int64_t)b * A + i) * n_lat + c) * 7;
     o[0] = budget;
     o[1] = agent_id;
     o[2] = pm;
@@ -502,42 +531,58 @@ __global__ void __launch_bounds__(128)
   extern __shared__ __align__(16) unsigned char fsm[];
   const int32_t n_cells = cfg.gx * cfg.gy, n_quads = (n_cells + 3) >> 2;
   const int32_t n_lat = cfg.px * cfg.py;
-  float* s_map = reinterpret_cast<float*>(fsm);  // global map
-  float* s_uni = s_map + cfg.map_stride;         // union footprint values 0.5 / 1
-  float* s_tg = s_uni + cfg.map_stride;
-  float* s_tu = s_tg + cfg.gx * cfg.py;
+  // layout: s_map | pad | s_tg | s_tu | column pad | s_uni (bytes) | pad | codes
+  float* s_map = reinterpret_cast<float*>(fsm);     // [map_stride] global map, filled by the bulk copy
+  float* s_tg = s_map + cfg.map_stride + FEAT_PAD;  // [gx][py]
+  float* s_tu = s_tg + cfg.gx * cfg.py;             // [gx][py]
+  float* s_cpad = s_tu + cfg.gx * cfg.py;           // [MT][py] zeros
+  uint8_t* s_uni = reinterpret_cast<uint8_t*>(s_cpad + MT * cfg.py);  // [4 n_quads] 2 inside some footprint / 1
+  unsigned char* codes = align16(s_uni + 4 * n_quads + FEAT_PAD);     // [code_stride]
   const int32_t b = blockIdx.x;
   __shared__ AgentGeo s_geo[A];
   __shared__ int32_t s_act[A];
+  __shared__ __align__(8) uint64_t s_bar;
   if (threadIdx.x < A) {
     s_geo[threadIdx.x] = agent_geo(cfg, pos_in + ((int64_t)b * A + threadIdx.x) * 3);
     s_act[threadIdx.x] = actions[(int64_t)b * A + threadIdx.x];
   }
-  const float* glob = st.global_map + (int64_t)b * cfg.map_stride;
-  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(ptx::smem_u32(&s_bar), 1);
+    ptx::fence_mbar_init();
+    const uint32_t bar = ptx::smem_u32(&s_bar), map_bytes = (uint32_t)n_quads * 16u;
+    ptx::mbar_arrive_expect_tx(bar, map_bytes + (uint32_t)cfg.code_stride);
+    ptx::bulk_load(ptx::smem_u32(s_map), st.global_map + (int64_t)b * cfg.map_stride, map_bytes, bar);
+    ptx::bulk_load(ptx::smem_u32(codes),
+                   st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, (uint32_t)cfg.code_stride, bar);
+  }
+  for (int32_t k = 4 * n_quads + (int32_t)threadIdx.x; k < cfg.map_stride + FEAT_PAD; k += blockDim.x) s_map[k] = 0.0f;
+  for (int32_t k = threadIdx.x; k < MT * cfg.py; k += blockDim.x) s_cpad[k] = 0.0f;
+  if (threadIdx.x < FEAT_PAD) s_uni[4 * n_quads + threadIdx.x] = 0;
   uint32_t all_mask[CodeWord<A>::WORDS] = {};
 #pragma unroll
   for (int j = 0; j < A; ++j) all_mask[j >> 2] |= 0x0Fu << (8 * (j & 3));
-  for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
-    reinterpret_cast<float4*>(s_map)[q] = reinterpret_cast<const float4*>(glob)[q];
-    const uint32_t any = fold_nibbles<A>(load_code<A>(codes, q), all_mask);
-    reinterpret_cast<float4*>(s_uni)[q] = make_float4((any & 1u) ? 1.0f : 0.5f, (any & 2u) ? 1.0f : 0.5f,
-                                                      (any & 4u) ? 1.0f : 0.5f, (any & 8u) ? 1.0f : 0.5f);
-  }
   const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
   const int32_t rpr = (int32_t)blockDim.x / cfg.py;
   const int32_t rr = (int32_t)threadIdx.x / cfg.py, lj_r = (int32_t)threadIdx.x - rr * cfg.py;
-  const Taps<MT> tap_y = load_taps<MT>(ty, lj_r, cfg.gy);
-  __syncthreads();
-  {
-    const float* const src2[2] = {s_map, s_uni};
-    float* const tmp2[2] = {s_tg, s_tu};
-    pool_rows<MT, 2>(tap_y, src2, tmp2, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+  const Taps<MT> tap_y = load_taps<MT>(ty, lj_r);
+  Taps<MT> tap_x = load_taps<MT>(tx, min(rr, cfg.px - 1));
+  __syncthreads();  // s_bar initialised, s_geo / s_act visible
+  ptx::mbar_wait(ptx::smem_u32(&s_bar), 0);
+  for (int32_t q = threadIdx.x; q < n_quads; q += blockDim.x) {
+    const uint32_t any = fold_nibbles<A>(load_code<A>(codes, q), all_mask);
+    reinterpret_cast<uint32_t*>(s_uni)[q] = 0x01010101u + spread_nibble(any);
   }
   __syncthreads();
+  pool_rows<MT>(tap_y, s_map, 1.0f, s_tg, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+  pool_rows<MT>(tap_y, s_uni, 0.5f, s_tu, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);
+  __syncthreads();
   for (int32_t c = threadIdx.x; c < n_lat; c += blockDim.x) {
-    const int32_t li = c / cfg.py, lj = c - li * cfg.py;
-    const Taps<MT> tap_x = load_taps<MT>(tx, li, cfg.gx);
+    int32_t li = rr, lj = lj_r;
+    if (c != (int32_t)threadIdx.x) {
+      li = c / cfg.py;
+      lj = c - li * cfg.py;
+      tap_x = load_taps<MT>(tx, li);
+    }
     const float2 wg = w_entropy(cfg, pool_col<MT>(tap_x, s_tg, lj, cfg.py));
     const float pu = pool_col<MT>(tap_x, s_tu, lj, cfg.py);
     float posv = 0.0f;
@@ -559,20 +604,26 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+constexpr int FEAT_MAX_TAPS = 8;  // staged kernels are instantiated for 4 / 6 / 8 taps
+
 static size_t staged_actor_smem(const ipp_config& cfg) {
   int hw = 0, hmax = 0;
   for (int a = 0; a < cfg.n_alt; ++a) {
     hw = std::max(hw, 4 * cfg.radius_x[a] * cfg.radius_y[a]);
     hmax = std::max(hmax, 2 * cfg.radius_y[a]);
   }
-  return sizeof(float) * ((size_t)2 * cfg.map_stride + 2 * (size_t)cfg.gx * cfg.py + hw + (size_t)hmax * cfg.py);
+  const size_t n_quads = ((size_t)cfg.gx * cfg.gy + 3) / 4;
+  return sizeof(float) * ((size_t)cfg.map_stride + FEAT_PAD + 2 * (size_t)cfg.gx * cfg.py + (size_t)hmax * cfg.py +
+                          (size_t)FEAT_MAX_TAPS * cfg.py + hw + FEAT_PAD) +
+         4 * n_quads + FEAT_PAD + 16 + (size_t)cfg.code_stride;
 }
 static size_t staged_critic_smem(const ipp_config& cfg) {
-  return sizeof(float) * ((size_t)2 * cfg.map_stride + 2 * (size_t)cfg.gx * cfg.py);
+  const size_t n_quads = ((size_t)cfg.gx * cfg.gy + 3) / 4;
+  return sizeof(float) * ((size_t)cfg.map_stride + FEAT_PAD + 2 * (size_t)cfg.gx * cfg.py +
+                          (size_t)FEAT_MAX_TAPS * cfg.py) +
+         4 * n_quads + FEAT_PAD + 16 + (size_t)cfg.code_stride;
 }
 constexpr size_t FEAT_SMEM_LIMIT = 100 * 1024;
-
-constexpr int FEAT_MAX_TAPS = 8;  // staged kernels are instantiated for 4 / 6 / 8 taps
 
 template <int A, int MT>
 static cudaError_t actor_staged_mt(const ipp_config& cfg, const ipp_state& st, const PoolTables& pt,

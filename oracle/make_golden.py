@@ -183,7 +183,36 @@ def kats():
     print("wrote", path, os.path.getsize(path))
 
 
+def ig_episodes():
+    """The reference's IG-greedy baseline (IG_baseline.py) run unmodified: per-step gains, utilities, argmax
+    actions and the entropy / F1 curves."""
+    cases = [
+        ("g50_a4", rh.synthetic_params(50, 4), 2),
+        ("g50_a3_comm15_fail30", rh.synthetic_params(50, 3, comm_range=15, failure_rate=0.3), 5),
+        ("g50_a2", rh.synthetic_params(50, 2), 7),
+        ("g100_a8", rh.synthetic_params(100, 8), 1),
+        ("default_g493_a4", rh.default_params(), 1),
+    ]
+    for name, params, ep in cases:
+        rec = rh.run_reference_ig(params, ep)
+        out = {k: rec[k] for k in ("pos", "gains", "util", "action", "entropy", "f1")}
+        out["gt_sum"] = np.array(int(rec["gt"].sum()))
+        out["communication"] = np.array(bool(params["experiment"]["baselines"]["information_gain"]["communication"]))
+        out["params_json"] = np.array(json.dumps(params))
+        out["episode"] = np.array(ep)
+        out["versions_json"] = np.array(json.dumps(_versions()))
+        path = os.path.join(OUT, "ig_%s_ep%d.npz" % (name, ep))
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    kats()
-    episodes()
+    import sys
+
+    if "ig" in sys.argv[1:]:
+        ig_episodes()
+    else:
+        kats()
+        episodes()
+        ig_episodes()

@@ -362,3 +362,82 @@ def run_reference_episode(params, episode, actions=None, noiseless=False, n_step
         global_map = next_global
         rec["steps"].append(step)
     return rec
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's information-gain greedy baseline (IG_baseline.py), unmodified, with the same noise /
+# communication streams as run_reference_episode
+# ----------------------------------------------------------------------------------------------
+def run_reference_ig(params, episode):
+    """Run ``IG_baseline(params, writer, episode).execute()`` and record what it computes per step:
+    individual gains, final utilities, chosen actions, and the entropy / F1 curves it returns."""
+    ns = load()
+    install_noise_patch()
+    import marl_framework.IG_baseline as ig_mod  # noqa: E402
+
+    agent_cls = ig_mod.Agent  # the bare-alias class IG_baseline.py:15 imports (SURVEY.md 8c "harness trap")
+
+    seed = params["environment"]["seed"]
+    n_agents = params["experiment"]["missions"]["n_agents"]
+    NoiseContext.seed = seed
+    NoiseContext.episode = episode
+    NoiseContext.noiseless = False
+
+    base = ig_mod.IG_baseline(params, _Stub("writer"), episode)
+    rec = {"gains": [], "util": [], "action": [], "pos": []}
+
+    # every measurement goes through mapping.update_grid_map, in agent order: A calls at t = 0 from
+    # Agent.communicate (stream index 0), then A calls per planning step t (stream index t + 1)
+    calls = {"n": 0}
+    real_update = base.mapping.update_grid_map
+
+    def update_grid_map(*a, **k):
+        NoiseContext.agent = calls["n"] % n_agents
+        NoiseContext.index = calls["n"] // n_agents
+        calls["n"] += 1
+        return real_update(*a, **k)
+
+    base.mapping.update_grid_map = update_grid_map
+
+    real_receive = agent_cls.receive_messages
+
+    def receive_messages(self, log, agent_id, t):
+        with _comm_draws(seed, episode, agent_id, t):
+            return real_receive(self, log, agent_id, t)
+
+    real_ind, real_util, real_sel = base.get_individual_ig, base.get_cell_utilities, base.select_action
+    step = {}
+
+    def get_individual_ig(position, mask, map_state):
+        out = real_ind(position, mask, map_state)
+        step.setdefault("pos", []).append(np.array(position))
+        step.setdefault("gains", []).append([float(v) for v in out[1]])
+        return out
+
+    def get_cell_utilities(plist, rel):
+        out = real_util(plist, rel)
+        return out
+
+    def select_action(util):
+        a = real_sel(util)
+        step.setdefault("util", []).append([float(v) for v in util])
+        step.setdefault("action", []).append(int(a))
+        if len(step["action"]) == n_agents:
+            for k in ("gains", "util", "action", "pos"):
+                rec[k].append(np.array(step[k]))
+            step.clear()
+        return a
+
+    base.get_individual_ig, base.get_cell_utilities, base.select_action = get_individual_ig, get_cell_utilities, select_action
+    agent_cls.receive_messages = receive_messages
+    try:
+        rel_sum, abs_sum, altitudes, entropies, f1s = base.execute()
+    finally:
+        agent_cls.receive_messages = real_receive
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["entropy"] = np.array([float(v) for v in entropies])
+    out["f1"] = np.array([float(v) for v in f1s])
+    out["reward_rel_sum"] = float(rel_sum)
+    out["reward_abs_sum"] = float(abs_sum)
+    out["gt"] = np.asarray(base.mapping.simulated_map).copy()
+    return out

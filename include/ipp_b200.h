@@ -178,6 +178,27 @@ int ipp_features_actor(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_
 int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int32_t* pos_in, const int32_t* actions,
                         const float* obs_in, float* state_out, void* stream);
 
+/*
+ * Batched information-gain greedy planner (IG_baseline.py:127-135,222-325), split mode:
+ * call after ipp_observe of timestep t, then hand actions_out to ipp_act as injected actions.  Per env and
+ * agent: action mask (bounds + collision rules against the CURRENT positions of the lower-id agents), expected
+ * entropy reduction of the agent's fused local map over the footprint of every allowed candidate position
+ * (get_individual_ig), per-agent normalisation (get_relative_ig), with `communication` != 0 the sequential
+ * discount of candidates other agents can reach too (get_cell_utilities), argmax (select_action).
+ * pos_in [n_envs, n_agents, 3]; actions_out [n_envs, n_agents] int32; optional (may be NULL): mask_out
+ * [n_envs, n_agents] uint8, gains_out / util_out [n_envs, n_agents, 6] float64 (0 for masked actions).
+ */
+int ipp_ig_plan(ipp_handle* h, const ipp_state* st, const int32_t* pos_in, int32_t communication,
+                int32_t* actions_out, uint8_t* mask_out, double* gains_out, double* util_out, void* stream);
+
+/*
+ * Evaluation metrics of the accumulated global map (IG_baseline.py:81-100,191-210):
+ * entropy_out [n_envs] float64 = mean Shannon entropy over the ground-truth-occupied cells
+ * (utils/state.py:53-121 "eval" branch), f1_out [n_envs] float64 = F1 score of class 1 of the thresholded map
+ * (utils/utils.py:43-76, `get_wrmse`).
+ */
+int ipp_eval_metrics(ipp_handle* h, const ipp_state* st, double* entropy_out, double* f1_out, void* stream);
+
 /* ---- single-map entry points used by the drop-in facade (host pointers, synchronous) -------- */
 
 /* Camera.project_field_of_view (sensors/cameras.py:46-79): position[3] metres ->

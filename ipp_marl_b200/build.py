@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libipp_b200.so")
 STAMP = os.path.join(LIBDIR, "libipp_b200.stamp")
-SOURCES = ["ipp_kernels.cu", "ipp_step_tma.cu", "ipp_features.cu", "ipp_facade_kernels.cu", "ipp_abi.cu"]
+SOURCES = ["ipp_kernels.cu", "ipp_step_tma.cu", "ipp_features.cu", "ipp_planner.cu", "ipp_facade_kernels.cu", "ipp_abi.cu"]
 HEADERS = ["ipp_device.cuh", "ipp_cell.cuh", "ipp_launch.h", os.path.join("..", "..", "include", "ipp_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,8 +34,18 @@ def nvcc_path():
     return cand if os.path.exists(cand) else None
 
 
+def _compile_one(args):
+    nvcc, src, obj, verbose = args
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    return src, res.returncode, res.stdout, res.stderr
+
+
 def build(force=False, verbose=False):
-    """Compile if sources changed; returns the library path.  Raises if nvcc fails."""
+    """Compile if sources changed; returns the library path.  Raises if nvcc fails.
+
+    Each .cu is compiled to its own object (in parallel, cached by content digest under _lib/obj/) and the
+    objects are linked into one shared library."""
     os.makedirs(LIBDIR, exist_ok=True)
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
@@ -47,12 +57,37 @@ def build(force=False, verbose=False):
         if os.path.exists(LIB):
             return LIB  # box without a toolkit: use the prebuilt library shipped with the snapshot
         raise RuntimeError("nvcc not found and no prebuilt %s" % LIB)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hh = hashlib.sha256()
+    for name in HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            hh.update(f.read())
+    hh.update(" ".join(NVCC_FLAGS).encode())
+    jobs, objs = [], []
+    for src in SOURCES:
+        h = hh.copy()
+        with open(os.path.join(CSRC, src), "rb") as f:
+            h.update(f.read())
+        obj = os.path.join(objdir, "%s.%s.o" % (src[:-3], h.hexdigest()[:16]))
+        objs.append(obj)
+        if force or verbose or not os.path.exists(obj):
+            for stale in os.listdir(objdir):
+                if stale.startswith(src[:-3] + "."):
+                    os.remove(os.path.join(objdir, stale))
+            jobs.append((nvcc, src, obj, verbose))
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            for src, rc, out, err in pool.map(_compile_one, jobs):
+                if rc != 0:
+                    raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, out, err))
+                if verbose:
+                    print(err)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
     with open(STAMP, "w") as f:
         f.write(digest)
     return LIB

@@ -293,6 +293,24 @@ int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int
   return IPP_OK;
 }
 
+int ipp_ig_plan(ipp_handle* h, const ipp_state* st, const int32_t* pos_in, int32_t communication,
+                int32_t* actions_out, uint8_t* mask_out, double* gains_out, double* util_out, void* stream) {
+  if (h == nullptr || pos_in == nullptr || actions_out == nullptr) return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  IPP_CUDA(h, ipp::launch_ig_plan(h->cfg, *st, pos_in, communication != 0, actions_out, mask_out, gains_out, util_out,
+                                  (cudaStream_t)stream));
+  return IPP_OK;
+}
+
+int ipp_eval_metrics(ipp_handle* h, const ipp_state* st, double* entropy_out, double* f1_out, void* stream) {
+  if (h == nullptr || entropy_out == nullptr || f1_out == nullptr) return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  IPP_CUDA(h, ipp::launch_eval_metrics(h->cfg, *st, entropy_out, f1_out, (cudaStream_t)stream));
+  return IPP_OK;
+}
+
 int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, int32_t* clipped) {
   if (h == nullptr || position == nullptr || raw == nullptr || clipped == nullptr) return IPP_ERR_INVALID_ARG;
   const ipp_config& c = h->cfg;

@@ -55,6 +55,13 @@ cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const 
 cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
                          int32_t* pos_out, int32_t* gt_params, cudaStream_t s);
 
+// IG-greedy planner + evaluation metrics (ipp_planner.cu)
+cudaError_t launch_ig_plan(const ipp_config& cfg, const ipp_state& st, const int32_t* pos_in, int communication,
+                           int32_t* actions_out, uint8_t* mask_out, double* gains_out, double* util_out,
+                           cudaStream_t s);
+cudaError_t launch_eval_metrics(const ipp_config& cfg, const ipp_state& st, double* entropy_out, double* f1_out,
+                                cudaStream_t s);
+
 // single-map helpers used by the facade entry points (device pointers)
 cudaError_t launch_update_cells(const ipp_config& cfg, float* x, const float* y, int y_is_scalar, float y_scalar,
                                 int64_t n, float* out, cudaStream_t s);

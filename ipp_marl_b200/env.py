@@ -54,6 +54,8 @@ class BatchedIPPEnv:
                                  _ptr(self._codes))
         self.t = 0
         self._observed = False
+        self._folded = False
+        self._ig_actions = None
 
     # ---- views in the reference's array convention: [.., gx, gy], first axis = world x ----------
     def _view(self, flat):
@@ -113,13 +115,14 @@ class BatchedIPPEnv:
         self.episodes.copy_(ep32, non_blocking=True)
         self.t = 0
         self._observed = False
+        self._folded = False
         rc = self.lib.ipp_reset(self._h, C.byref(self._state), _ptr(self.positions[0]), self._stream())
         N.check(self.lib, self._h, rc, "ipp_reset")
 
     def _io(self, actions, probs, greedy):
         io = N.IppStepIO()
         io.pos_in = _ptr(self.positions[self.t])
-        io.pos_out = _ptr(self.positions[self.t + 1])
+        io.pos_out = _ptr(self.positions[self.t + 1]) if self.t < self.T else C.c_void_p(0)
         io.actions_in = _ptr(actions)
         io.probs_in = _ptr(probs)
         io.greedy = 1 if greedy else 0
@@ -162,19 +165,24 @@ class BatchedIPPEnv:
         return self.reward_rel, self.reward_abs, done
 
     # ---- the same timestep split around a policy network --------------------------------------
-    def observe(self):
-        """Fuse local + global maps and compute the reward (everything before the actor forward)."""
-        if self.t >= self.T:
+    def observe(self, final=False):
+        """Fuse local + global maps and compute the reward (everything before the actor forward).
+
+        ``final=True`` is the fold of the LAST measurements after the episode's last move (IG_baseline.py:171-175
+        evaluates its metrics on that map); no act() can follow it."""
+        if self.t >= self.T and (not final or self._folded):
             raise N.IppError("episode finished: call reset()")
         io = self._io(None, None, False)
         rc = self.lib.ipp_observe(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
         N.check(self.lib, self._h, rc, "ipp_observe")
         self._observed = True
+        if self.t == self.T:
+            self._folded = True  # terminal fold done: only reset() may follow
         return self.reward_rel, self.reward_abs
 
     def act(self, actions=None, probs=None, greedy=False):
         """Masks, action choice, moves and the measurement at the new positions."""
-        if not self._observed:
+        if not self._observed or self.t >= self.T:
             raise N.IppError("act() must follow observe() in the same timestep")
         actions, probs = self._prep(actions, probs)
         io = self._io(actions, probs, greedy)
@@ -207,6 +215,34 @@ class BatchedIPPEnv:
                                           _ptr(self.actions), _ptr(obs.contiguous()), _ptr(out), self._stream())
         N.check(self.lib, self._h, rc, "ipp_features_critic")
         return out
+
+    # ---- IG-greedy planner + evaluation metrics --------------------
+    def ig_plan(self, communication=True, return_scores=False):
+        """IG_baseline.py:127-135,222-325 for the whole batch (call after observe(); feed the result to
+        act(actions=...)).  Returns actions [B, A] int32, with ``return_scores`` also (gains, utilities)
+        [B, A, 6] float64."""
+        if not self._observed or self.t >= self.T:
+            raise N.IppError("ig_plan() must follow observe() in the same timestep")
+        if self._ig_actions is None:
+            self._ig_actions = torch.empty((self.B, self.A), dtype=torch.int32, device=self.device)
+        gains = util = None
+        if return_scores:
+            gains = torch.empty((self.B, self.A, 6), dtype=torch.float64, device=self.device)
+            util = torch.empty_like(gains)
+        rc = self.lib.ipp_ig_plan(self._h, C.byref(self._state), _ptr(self.positions[self.t]),
+                                  1 if communication else 0, _ptr(self._ig_actions), _ptr(self.masks), _ptr(gains),
+                                  _ptr(util), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_ig_plan")
+        return (self._ig_actions, gains, util) if return_scores else self._ig_actions
+
+    def eval_metrics(self):
+        """(masked entropy, F1 of class 1) of the accumulated global map, float64 [B] each
+        (IG_baseline.py:81-100,191-210)."""
+        ent = torch.empty((self.B,), dtype=torch.float64, device=self.device)
+        f1 = torch.empty_like(ent)
+        rc = self.lib.ipp_eval_metrics(self._h, C.byref(self._state), _ptr(ent), _ptr(f1), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_eval_metrics")
+        return ent, f1
 
     # ---- sizes for the roofline (SURVEY.md section 8d contract figure) --------------------------
     def algorithmic_bytes_per_env_step(self):

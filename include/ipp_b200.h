@@ -15,6 +15,10 @@
  *   belief maps   float32 [..., map_stride], cell (x, y) at x * gy + y  — first array axis is
  *                 world x exactly as in the reference (mapping/mappings.py:46-61); map_stride >=
  *                 gx*gy is a multiple of 4 cells so every map starts 16-byte aligned.
+ *                 The resident state holds each cell's ODDS o = p / (1 - p), not p: one Bayes pass
+ *                 (mapping/mappings.py:106-124) is then a clamp and a multiply per cell.  Probabilities —
+ *                 what Agent.local_map holds in the reference — are produced by ipp_export_beliefs
+ *                 (p = o/(1+o)); every other entry point converts on the fly where it needs p.
  *   ground truth  uint8   [n_envs, gt_stride]    (mapping/ground_truths.py:42-56 half-plane field)
  *   positions     int32   [n_envs, n_agents, 3]  metres (x, y, z), as agent/agent.py keeps them
  *   episodes      uint32  [n_envs]               episode number of each env (seeds + random streams)
@@ -78,8 +82,8 @@ typedef struct ipp_config {
 /* Device-resident state of the batch (struct-of-arrays form of agent/agent.py:13-38 per UAV and of
  * the accumulated global map of missions/episode_generator.py:47,53). */
 typedef struct ipp_state {
-  float* local_maps;   /* [n_envs, n_agents, map_stride]  Agent.local_map                          */
-  float* global_map;   /* [n_envs, map_stride]            accumulated_map_knowledge                */
+  float* local_maps;   /* [n_envs, n_agents, map_stride]  Agent.local_map, as odds                 */
+  float* global_map;   /* [n_envs, map_stride]            accumulated_map_knowledge, as odds       */
   uint8_t* ground_truth; /* [n_envs, gt_stride]           Mapping.simulated_map                    */
   uint32_t* episodes;  /* [n_envs]                                                                  */
   uint8_t* meas_codes; /* [2, n_envs, code_stride] compact form of Agent.map2communicate: one byte per   */
@@ -177,6 +181,14 @@ int ipp_features_actor(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_
                        void* stream);
 int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int32_t* pos_in, const int32_t* actions,
                         const float* obs_in, float* state_out, void* stream);
+
+/*
+ * The belief maps as probabilities (what Agent.local_map / accumulated_map_knowledge hold in the reference:
+ * agent/agent.py:35, missions/episode_generator.py:47).  local_out [n_envs, n_agents, map_stride] and
+ * global_out [n_envs, map_stride] float32 device buffers; either may be NULL.  p = o/(1+o) for o < 1, else
+ * 1 - 1/(1+o), in IEEE float32 (keeps the accuracy of 1-p near p = 1).
+ */
+int ipp_export_beliefs(ipp_handle* h, const ipp_state* st, float* local_out, float* global_out, void* stream);
 
 /*
  * Batched information-gain greedy planner (IG_baseline.py:127-135,222-325), split mode:

@@ -293,6 +293,22 @@ int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int
   return IPP_OK;
 }
 
+int ipp_export_beliefs(ipp_handle* h, const ipp_state* st, float* local_out, float* global_out, void* stream) {
+  if (h == nullptr) return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  if ((reinterpret_cast<uintptr_t>(local_out) & 15) || (reinterpret_cast<uintptr_t>(global_out) & 15))
+    return IPP_ERR_INVALID_ARG;
+  const int64_t per_env = h->cfg.map_stride;
+  if (local_out != nullptr)
+    IPP_CUDA(h, ipp::launch_export_beliefs(st->local_maps, local_out, per_env * h->cfg.n_agents * h->cfg.n_envs,
+                                           (cudaStream_t)stream));
+  if (global_out != nullptr)
+    IPP_CUDA(h, ipp::launch_export_beliefs(st->global_map, global_out, per_env * h->cfg.n_envs,
+                                           (cudaStream_t)stream));
+  return IPP_OK;
+}
+
 int ipp_ig_plan(ipp_handle* h, const ipp_state* st, const int32_t* pos_in, int32_t communication,
                 int32_t* actions_out, uint8_t* mask_out, double* gains_out, double* util_out, void* stream) {
   if (h == nullptr || pos_in == nullptr || actions_out == nullptr) return IPP_ERR_INVALID_ARG;

@@ -3,17 +3,18 @@
 // utils/reward.py:68-82 + utils/state.py:53-76,118-121 (reward terms).
 // Specification: oracle/kernel_model.py::_apply / _reward  (belief maps bit-exact).
 //
-// The map kernels are issue-bound (ALU pipe), not HBM-bound, unless this code is lean (profiles/):
+// The belief maps live in HBM as float32 ODDS o = p/(1-p) (include/ipp_b200.h), so one Bayes pass is
+// o = min(max(o, o_min), o_max) * k: no division, no transcendental on the belief path.  What keeps the
+// map kernels off the issue limit (profiles/):
 //   * everything geometric / random about a measurement (footprint test, noise hash, ground truth) is
 //     done once per step by plan_kernel, rect-sparse, and handed over as one CODE BYTE per (quad, agent):
 //     low nibble = cell inside the footprint, high nibble = cell seen as 1.  The map kernels turn a
 //     code byte into the 4 odds multipliers with ONE 16-byte table load (lut[altitude][byte]);
-//   * the 4 cells of a quad are processed branch-free, two cells per instruction with the sm_100
-//     packed-float32 FFMA2 / FMUL2 forms (IEEE per lane => still bit-exact);
-//   * divisions use the fast path of div.rn.f32 (MUFU.RCP + 5 FMAs) without its range check —
-//     every operand here is a normal number in [1e-4, 1.1e4] (clamped probabilities / odds);
+//   * the 4 cells of a quad are processed branch-free, the multiplies two cells per instruction with the
+//     sm_100 packed-float32 FMUL2 form (IEEE per lane => still bit-exact);
 //   * a fuse pass whose footprint touches no cell of the whole warp degenerates to a clamp, clamps
-//     are idempotent, so such passes are skipped warp-uniformly and one clamp is applied instead.
+//     are idempotent, so such passes are skipped warp-uniformly and one clamp is applied instead;
+//   * only the reward needs more: H(p) of the global map's cells from their odds (1 MUFU.RCP + 2 MUFU.LG2).
 #pragma once
 #include "ipp_device.cuh"
 
@@ -86,41 +87,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-// a / b, given b and nb = -b: instruction-for-instruction the fast path nvcc emits for div.rn.f32
-// (MUFU.RCP, one Newton step on the reciprocal, quotient, one remainder correction), i.e. the
-// correctly rounded quotient for normal operands with a normal quotient.
-__device__ __forceinline__ F4 f4_div(const F4 a, const F4 b, const F4 nb) {
-  const F4 one = f4_splat(1.0f);
-  const F4 r0 = F4{make_float2(rcp_approx(b.lo.x), rcp_approx(b.lo.y)),
-                   make_float2(rcp_approx(b.hi.x), rcp_approx(b.hi.y))};
-  const F4 e = f4_fma(nb, r0, one);
-  const F4 r = f4_fma(r0, e, r0);
-  const F4 q = f4_mul(a, r);
-  const F4 rem = f4_fma(nb, q, a);
-  return f4_fma(r, rem, q);
-}
-
-// o = pc / (1 - pc)
-__device__ __forceinline__ F4 f4_to_odds(const F4 pc) {
-  const F4 one = f4_splat(1.0f), mone = f4_splat(-1.0f);
-  const F4 b = f4_fma(pc, mone, one);   // 1 - pc   (single rounding, == __fsub_rn(1, pc))
-  const F4 nb = f4_fma(pc, one, mone);  // pc - 1 == -(1 - pc) exactly
-  return f4_div(pc, b, nb);
-}
-
-// p = o/(1+o) for o < 1, 1 - 1/(1+o) otherwise (symmetric form: keeps the accuracy of 1-p near p = 1)
-__device__ __forceinline__ F4 f4_from_odds(const F4 o) {
-  const F4 one = f4_splat(1.0f), mone = f4_splat(-1.0f);
-  const F4 d = f4_fma(o, one, one);     // 1 + o
-  const F4 nd = f4_fma(o, mone, mone);  // -(1 + o)
-  const F4 num = F4{make_float2(fminf(o.lo.x, 1.0f), fminf(o.lo.y, 1.0f)),
-                    make_float2(fminf(o.hi.x, 1.0f), fminf(o.hi.y, 1.0f))};
-  const F4 q = f4_div(num, d, nd);
-  const F4 alt = f4_fma(q, mone, one);  // 1 - q
-  return F4{make_float2(o.lo.x < 1.0f ? q.lo.x : alt.lo.x, o.lo.y < 1.0f ? q.lo.y : alt.lo.y),
-            make_float2(o.hi.x < 1.0f ? q.hi.x : alt.hi.x, o.hi.y < 1.0f ? q.hi.y : alt.hi.y)};
-}
-
 // ------------------------------------------------------------------------------------------------
 // measurement codes: one byte per (quad, agent), AP = 4 (A <= 4) or 8 bytes per quad
 // ------------------------------------------------------------------------------------------------
@@ -174,18 +140,19 @@ __device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMe
 }
 
 // ------------------------------------------------------------------------------------------------
-// One belief map of the quad through its chain of passes.
+// One belief map (float32 odds) of the quad through its chain of passes.
 //   en      : bit j = fuse pass j enabled for this map (warp-uniform)
 //   own     : 4-bit mask of cells inside the own new footprint, k_own their multipliers
 // Semantics per cell (oracle/kernel_model.py::_apply): every enabled fuse pass clamps the odds and
 // multiplies by k_j (k_out outside footprint j); then, inside the own footprint only, clamp and
-// multiply by k_own.  Untouched cells keep p (or clamp(p) if some fuse pass ran) bit for bit.
+// multiply by k_own.  Untouched cells keep o (or clamp(o) if some fuse pass ran) bit for bit.
 // Padding cells beyond gx*gy are never inside a footprint, hold the prior and stay unchanged.
+// oc_out = the clamped input odds (the reward's "last" map), touched = cells some pass multiplied.
 // ------------------------------------------------------------------------------------------------
 template <int A>
-__device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadCtx<A>& q, const F4 p,
+__device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadCtx<A>& q, const F4 o_in,
                                               const uint32_t en, const uint32_t en4, const uint32_t own,
-                                              const F4 k_own, F4& pc_out, uint32_t& touched) {
+                                              const F4 k_own, F4& oc_out, uint32_t& touched) {
   const bool kout_one = (cfg.k_out == 1.0f);
   const bool any_fuse = en != 0u;
   uint32_t x = q.in_prev & en4;  // footprint nibbles of the enabled passes, OR-folded into one nibble
@@ -195,17 +162,13 @@ __device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadC
   uint32_t t = (x & 0xFu) | own;
   if (any_fuse && !kout_one) t = 0xFu;
   touched = t;
-  if (t == 0u && !any_fuse) {  // nothing happens to this quad of this map
-    pc_out = p;
-    return p;
+  F4 o = o_in;
+  bool clean = false;  // o is known to lie inside [o_min, o_max] (just clamped)
+  if (any_fuse) {      // the first enabled fuse pass clamps every cell of the map
+    o = f4_clamp(o, cfg.o_min, cfg.o_max);
+    clean = true;
   }
-  const F4 pc = f4_clamp(p, cfg.p_min, cfg.p_max);
-  pc_out = pc;
-  const F4 fallback = any_fuse ? pc : p;
-  if (t == 0u) return fallback;
-
-  F4 o = f4_to_odds(pc);
-  bool clean = true;  // o is known to lie inside [o_min, o_max] (fresh from pc, or just clamped)
+  oc_out = o;
 #pragma unroll
   for (int j = 0; j < A; ++j) {
     if (!((en >> j) & 1u)) continue;  // warp-uniform
@@ -230,45 +193,51 @@ __device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadC
     const F4 oc = clean ? o : f4_clamp(o, cfg.o_min, cfg.o_max);
     o = f4_select(own, f4_mul(oc, k_own), o);
   }
-  return f4_select(t, f4_from_odds(o), fallback);
+  return o;
 }
 
-// float32 reward terms; H in bits (utils/state.py:118-121)
+// float32 reward terms; H in bits (utils/state.py:118-121) of a cell given its CLAMPED odds:
+// q = 1/(1+o), p = o*q, H = -(p lg p + q lg q)
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float entropy_bits(float pc) {  // pc already clamped to [p_min, p_max]
-  const float qc = 1.0f - pc;
+__device__ __forceinline__ float entropy_bits_odds(float oc) {
+  const float qc = rcp_approx(1.0f + oc);
+  const float pc = oc * qc;
   return -(pc * lg2_approx(pc) + qc * lg2_approx(qc));
 }
+
+// utils/state.py:67-73 thresholds p > 0.501 / p < 0.499 in odds space (oracle/kernel_model.py W_HI / W_LO)
+#define IPP_W_HI 1.0040080547332764f
+#define IPP_W_LO 0.9960079789161682f
 
 // Global map: fuse every agent's communicated measurement (coma_wrapper.py:93-95) and accumulate
 // s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last)  (utils/reward.py:68-82).  `valid`: bit c = cell exists.
 template <int A>
-__device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, const QuadCtx<A>& q, const float4 p4,
+__device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, const QuadCtx<A>& q, const float4 o4,
                                                      const uint32_t valid, double& s1, double& s2) {
-  F4 pc;
+  F4 oc;
   uint32_t touched;
-  const F4 p = f4_from(p4);
-  const F4 pn = update_map_quad<A>(cfg, q, p, (1u << A) - 1u, 0xFFFFFFFFu, 0u, f4_splat(1.0f), pc, touched);
+  const F4 on = update_map_quad<A>(cfg, q, f4_from(o4), (1u << A) - 1u, 0xFFFFFFFFu, 0u, f4_splat(1.0f), oc,
+                                   touched);
   float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     if (!((valid >> c) & 1u)) continue;
-    const float next = f4_get(pn, c);
-    const float hl = entropy_bits(f4_get(pc, c));
+    const float next = f4_get(on, c);
+    const float hl = entropy_bits_odds(f4_get(oc, c));
     float hn = hl;
     if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl
-      hn = ((touched >> c) & 1u) ? entropy_bits(fminf(fmaxf(next, cfg.p_min), cfg.p_max)) : hl;
-    const float w = next > 0.501f ? 1.0f : (next < 0.499f ? 0.0f : 0.5f);  // == the float64 compares
+      hn = ((touched >> c) & 1u) ? entropy_bits_odds(fminf(fmaxf(next, cfg.o_min), cfg.o_max)) : hl;
+    const float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
     a1 += w * (hl - hn);
     a2 += w * hl;
   }
   s1 += (double)a1;
   s2 += (double)a2;
-  return f4_to(pn);
+  return f4_to(on);
 }
 
 // Local map of agent i: fuse the received peers' measurements (agent/agent.py:62-71), then the own
@@ -276,16 +245,16 @@ __device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, cons
 template <int A, bool DO_OWN>
 __device__ __forceinline__ float4 update_local_quad(const ipp_config& cfg, const EnvMeta<A>& meta,
                                                     const QuadCtx<A>& q, int i, const uint32_t own_byte,
-                                                    const float4* lut, const float4 p4) {
+                                                    const float4* lut, const float4 o4) {
   uint32_t own = 0;
   F4 k_own = f4_splat(1.0f);
   if (DO_OWN) {
     own = own_byte & 0xFu;
     k_own = f4_from(lut[meta.lut_next[i] + own_byte]);
   }
-  F4 pc;
+  F4 oc;
   uint32_t touched;
-  return f4_to(update_map_quad<A>(cfg, q, f4_from(p4), meta.comm[i], meta.comm4[i], own, k_own, pc, touched));
+  return f4_to(update_map_quad<A>(cfg, q, f4_from(o4), meta.comm[i], meta.comm4[i], own, k_own, oc, touched));
 }
 
 __device__ __forceinline__ uint32_t valid_mask4(int32_t c0, int32_t n_cells) {

@@ -374,10 +374,9 @@ __global__ void __launch_bounds__(256)
       const uint32_t own = byte & 0xFu;
       if (own == 0u) continue;
       float* lp = st.local_maps + ((int64_t)b * A + i) * stride + ((int64_t)q << 2);
-      const F4 p = f4_from(*reinterpret_cast<const float4*>(lp));
-      const F4 pc = f4_clamp(p, cfg.p_min, cfg.p_max);
-      const F4 o = f4_mul(f4_to_odds(pc), f4_from(lut[s_row[i] + byte]));
-      *reinterpret_cast<float4*>(lp) = f4_to(f4_select(own, f4_from_odds(o), p));
+      const F4 o = f4_from(*reinterpret_cast<const float4*>(lp));
+      const F4 upd = f4_mul(f4_clamp(o, cfg.o_min, cfg.o_max), f4_from(lut[s_row[i] + byte]));
+      *reinterpret_cast<float4*>(lp) = f4_to(f4_select(own, upd, o));
     }
   }
 }
@@ -494,8 +493,8 @@ __global__ void __launch_bounds__(STEP_THREADS)
   const int32_t n_cells = cfg.gx * cfg.gy;
   const int32_t n_quads = (int32_t)(cfg.map_stride >> 2);
   const int64_t stride = cfg.map_stride;
-  const float prior = cfg.prior;
-  const F4 o_prior = f4_to_odds(f4_clamp(f4_splat(prior), cfg.p_min, cfg.p_max));
+  const float prior = to_odds(cfg.prior);  // the maps hold odds: prior/(1-prior) in float32
+  const F4 o_prior = f4_clamp(f4_splat(prior), cfg.o_min, cfg.o_max);
   constexpr int AP = A <= 4 ? 4 : 8;
   uint8_t* codes = st.meas_codes + (int64_t)b * cfg.code_stride;  // half 0
   const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
@@ -519,7 +518,7 @@ __global__ void __launch_bounds__(STEP_THREADS)
       const uint32_t byte = (c0 < n_cells) ? meas_code_byte(cfg, s_m[i], c0, g4) : 0u;
       cw[i >> 2] |= byte << (8 * (i & 3));
       F4 pv = f4_splat(prior);
-      if (byte & 0xFu) pv = f4_select(byte & 0xFu, f4_from_odds(f4_mul(o_prior, f4_from(lut[s_row[i] + byte]))), pv);
+      if (byte & 0xFu) pv = f4_select(byte & 0xFu, f4_mul(o_prior, f4_from(lut[s_row[i] + byte])), pv);
       *reinterpret_cast<float4*>(st.local_maps + ((int64_t)b * A + i) * stride + c0) = f4_to(pv);
     }
     if ((int64_t)q * AP < cfg.code_stride) {
@@ -527,6 +526,29 @@ __global__ void __launch_bounds__(STEP_THREADS)
       else reinterpret_cast<uint2*>(codes)[q] = make_uint2(cw[0], cw[1]);
     }
   }
+}
+
+// =================================================================================================
+// export: the stored odds as probabilities, p = o/(1+o) (o < 1) or 1 - 1/(1+o) — IEEE float32 divisions,
+// bit-identical to oracle/kernel_model.py::to_p.  This is what Agent.local_map / the accumulated global map
+// of the reference hold (agent/agent.py:35, missions/episode_generator.py:47).
+// =================================================================================================
+__global__ void __launch_bounds__(256) export_beliefs_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                                             const int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 o = src[i];
+    dst[i] = make_float4(from_odds(o.x), from_odds(o.y), from_odds(o.z), from_odds(o.w));
+  }
+}
+
+cudaError_t launch_export_beliefs(const float* src, float* dst, int64_t n_floats, cudaStream_t s) {
+  const int64_t n4 = n_floats >> 2;  // map_stride is a multiple of 4
+  if (n4 == 0) return cudaSuccess;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  export_beliefs_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                         reinterpret_cast<float4*>(dst), n4);
+  return cudaGetLastError();
 }
 
 // =================================================================================================

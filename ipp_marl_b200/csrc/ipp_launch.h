@@ -55,6 +55,9 @@ cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const 
 cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
                          int32_t* pos_out, int32_t* gt_params, cudaStream_t s);
 
+// stored odds -> probabilities (n_floats multiple of 4)
+cudaError_t launch_export_beliefs(const float* src, float* dst, int64_t n_floats, cudaStream_t s);
+
 // IG-greedy planner + evaluation metrics (ipp_planner.cu)
 cudaError_t launch_ig_plan(const ipp_config& cfg, const ipp_state& st, const int32_t* pos_in, int communication,
                            int32_t* actions_out, uint8_t* mask_out, double* gains_out, double* util_out,

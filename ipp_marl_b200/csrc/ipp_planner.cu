@@ -33,10 +33,10 @@ __device__ __forceinline__ float snap_weight(float p) {
   return d > 0.501 ? 1.0f : (d < 0.499 ? 0.0f : p);
 }
 
-// expected entropy reduction of one cell with belief s for a sensor with odds multipliers k_hi / k_lo
-__device__ __forceinline__ float cell_gain(const ipp_config& cfg, float s, float k_hi, float k_lo) {
-  const float sc = clamp_p(cfg, s);
-  const float o = to_odds(sc);
+// expected entropy reduction of one cell with stored odds o_in for a sensor with odds multipliers k_hi / k_lo
+__device__ __forceinline__ float cell_gain(const ipp_config& cfg, float o_in, float k_hi, float k_lo) {
+  const float o = fminf(fmaxf(o_in, cfg.o_min), cfg.o_max);
+  const float sc = clamp_p(cfg, from_odds(o));
   const float p1 = from_odds(odds_pass(o, k_hi, cfg.o_min, cfg.o_max));  // measured "occupied"
   const float p2 = from_odds(odds_pass(o, k_lo, cfg.o_min, cfg.o_max));  // measured "free"
   const float h0 = shannon(cfg, sc);
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256)
   double h = 0.0;
   int32_t ones = 0, tp = 0, fp = 0;
   for (int32_t c = threadIdx.x; c < n_cells; c += blockDim.x) {
-    const float p = g[c];
+    const float p = from_odds(g[c]);  // the map holds odds
     const bool one = t[c] != 0, pred = p > 0.5f;
     if (one) h += (double)shannon(cfg, p);
     ones += one;

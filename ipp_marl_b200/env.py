@@ -62,12 +62,32 @@ class BatchedIPPEnv:
         t = self.tables
         return flat[..., : t.n_cells].unflatten(-1, (t.gx, t.gy))
 
+    # The resident state holds ODDS (include/ipp_b200.h); the reference-facing views below are probabilities,
+    # exported by a kernel into fresh tensors on every access.
+    def _export(self, local):
+        out = torch.empty_like(self._local if local else self._glob)
+        rc = self.lib.ipp_export_beliefs(self._h, C.byref(self._state), _ptr(out) if local else C.c_void_p(0),
+                                         C.c_void_p(0) if local else _ptr(out), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_export_beliefs")
+        return self._view(out)
+
     @property
     def local_maps(self):
-        return self._view(self._local)
+        """Agent.local_map of every (env, agent): probabilities [B, A, gx, gy]."""
+        return self._export(True)
 
     @property
     def global_map(self):
+        """Accumulated global map of every env: probabilities [B, gx, gy]."""
+        return self._export(False)
+
+    @property
+    def local_odds(self):
+        """The resident state itself: odds p/(1-p) [B, A, gx, gy] (a view, no copy)."""
+        return self._view(self._local)
+
+    @property
+    def global_odds(self):
         return self._view(self._glob)
 
     @property

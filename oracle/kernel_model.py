@@ -13,10 +13,16 @@ Arithmetic (DESIGN.md "belief update in odds space"): the reference's
 is algebraically ``o' = o * k`` on the odds ``o = x/(1-x)`` with
 ``k = exp(logit(y) - logit(prior))``; ``k`` takes two values per altitude (cell seen
 as 1 / as 0) plus ``k_out`` for the 0.5 "not observed" cells of map2communicate.
-The clamp the reference applies before every pass is kept (in odds space), the
-state is rounded to float32 probability once per step exactly where the reference
-rounds (fuse entry), and the final ``o -> p`` uses the symmetric form so that
-probabilities near 1 keep their accuracy.
+The clamp the reference applies before every pass is kept (in odds space).
+
+STATE IN ODDS SPACE: the belief maps are stored as float32 odds ``o`` (``local_o`` / ``glob_o``), so a pass
+is ``o = min(max(o, o_min), o_max) * k`` — one clamp and one multiply per cell, no division and no
+transcendental anywhere on the belief path.  Probabilities exist only where somebody reads them
+(``local`` / ``glob`` properties here, ``ipp_export_beliefs`` and the feature / planner / metric kernels on
+the device): ``p = o/(1+o)`` for ``o < 1`` else ``1 - 1/(1+o)`` (symmetric form: probabilities near 1 keep
+their accuracy).  float32 odds carry at least the relative precision of float32 probabilities
+(``dp/p = (1-p) do/o``), so the once-per-step rounding of the reference's float32 state is bounded by
+this model's rounding.
 """
 import numpy as np
 
@@ -24,6 +30,9 @@ from . import noise as hn
 from . import numpy_oracle as no
 
 F32 = np.float32
+# weight thresholds of utils/state.py:67-73 (p > 0.501 / p < 0.499) in odds space
+W_HI = F32(0.501 / 0.499)
+W_LO = F32(0.499 / 0.501)
 
 
 class KernelTables:
@@ -116,8 +125,9 @@ class KernelModelEnv:
         self.noiseless = noiseless
         gx, gy = self.tab.gx, self.tab.gy
         self.gt = np.stack([no.ground_truth(geo, int(e)) for e in self.episodes]).astype(np.uint8)
-        self.local = np.full((B, A, gx, gy), F32(geo.prior), dtype=F32)
-        self.glob = np.full((B, gx, gy), F32(geo.prior), dtype=F32)
+        o_prior = F32(geo.prior) / (F32(1) - F32(geo.prior))
+        self.local_o = np.full((B, A, gx, gy), o_prior, dtype=F32)
+        self.glob_o = np.full((B, gx, gy), o_prior, dtype=F32)
         self.pos = np.stack(
             [[no.start_position(geo, a, int(e)) for a in range(A)] for e in self.episodes]
         ).astype(np.int64)
@@ -130,7 +140,24 @@ class KernelModelEnv:
         # initial measurement at the start positions (agent/agent.py:44-49): own-update pass only
         for a in range(A):
             inr, k = self._k_of(self.pos[:, a], a, 0)
-            self.local[:, a] = self._apply(self.local[:, a], [(inr, k, False)])
+            self.local_o[:, a] = self._apply(self.local_o[:, a], [(inr, k, False)])
+
+    # ---- probabilities (what ipp_export_beliefs returns) -------------------------------------
+    @staticmethod
+    def to_p(o):
+        o = np.asarray(o, dtype=F32)
+        one = F32(1)
+        with np.errstate(over="ignore", invalid="ignore"):
+            d = one + o
+            return np.where(o < one, o / d, one - one / d).astype(F32)
+
+    @property
+    def local(self):
+        return self.to_p(self.local_o)
+
+    @property
+    def glob(self):
+        return self.to_p(self.glob_o)
 
     # ---- measurement multipliers ---------------------------------------------------------
     def _k_of(self, pos, agent, index):
@@ -150,45 +177,25 @@ class KernelModelEnv:
         return inr, k
 
     # ---- one map through a list of passes ------------------------------------------------
-    def _apply(self, p, passes):
-        """passes: list of (in_rect, k, is_fuse[, enabled[B]]).  Returns the new float32 map.
+    def _apply(self, o, passes):
+        """passes: list of (in_rect, k, is_fuse[, enabled[B]]).  Odds in, odds out (float32).
 
         fuse pass : every cell is clamped, cells in the rect *= k, the others *= k_out
         own update: only cells in the rect are clamped and *= k  (mappings.py:46-61)
         """
         tab = self.tab
-        p = p.astype(F32, copy=True)
-        B = p.shape[0]
-        touched = np.zeros(p.shape, dtype=bool)  # some pass multiplied by k != 1
-        clamped = np.zeros(p.shape, dtype=bool)  # some pass clamped the cell
-        kout_is_one = bool(tab.k_out == F32(1))
+        o = o.astype(F32, copy=True)
+        B = o.shape[0]
         for ps in passes:
             inr, k, is_fuse = ps[0], ps[1], ps[2]
             en = ps[3][:, None, None] if len(ps) > 3 else np.ones((B, 1, 1), dtype=bool)
+            oc = np.minimum(np.maximum(o, tab.o_min), tab.o_max)
             if is_fuse:
-                clamped |= en
-                touched |= en & (inr | (not kout_is_one))
+                kk = np.where(inr, k, tab.k_out).astype(F32)
+                o = np.where(en, oc * kk, o).astype(F32)
             else:
-                clamped |= en & inr
-                touched |= en & inr
-        pc = np.minimum(np.maximum(p, tab.p_min), tab.p_max)
-        with np.errstate(over="ignore", invalid="ignore"):
-            o = pc / (F32(1) - pc)
-            for ps in passes:
-                inr, k, is_fuse = ps[0], ps[1], ps[2]
-                en = ps[3][:, None, None] if len(ps) > 3 else np.ones((B, 1, 1), dtype=bool)
-                oc = np.minimum(np.maximum(o, tab.o_min), tab.o_max)
-                if is_fuse:
-                    kk = np.where(inr, k, tab.k_out).astype(F32)
-                    o = np.where(en, oc * kk, o)
-                else:
-                    o = np.where(en & inr, oc * k, o)
-            one = F32(1)
-            d = one + o
-            small = o / d
-            big = one - one / d
-            pn = np.where(o < one, small, big).astype(F32)
-        return np.where(touched, pn, np.where(clamped, pc, p)).astype(F32)
+                o = np.where(en & inr, oc * k, o).astype(F32)
+        return o
 
     # ---- comm matrix ------------------------------------------------------------------------
     def comm(self):
@@ -269,15 +276,17 @@ class KernelModelEnv:
 
     # ---- reward -------------------------------------------------------------------------------
     def _reward(self, last, nxt):
-        """utils/reward.py:68-82 with float32 per-cell terms and float64 sums."""
+        """utils/reward.py:68-82 on odds maps: float32 per-cell terms and float64 sums.  H of the clamped odds
+        (p = o/(1+o), q = 1/(1+o)); the weights compare the NEXT odds with 0.501/0.499 and 0.499/0.501."""
         tab = self.tab
 
-        def H(p):
-            pc = np.minimum(np.maximum(p, tab.p_min), tab.p_max).astype(F32)
-            q = F32(1) - pc
+        def H(o):
+            oc = np.minimum(np.maximum(o, tab.o_min), tab.o_max).astype(F32)
+            q = (F32(1) / (F32(1) + oc)).astype(F32)
+            pc = (oc * q).astype(F32)
             return (-pc * np.log2(pc) - q * np.log2(q)).astype(F32)
 
-        w = np.where(nxt.astype(np.float64) > 0.501, F32(1), np.where(nxt.astype(np.float64) < 0.499, F32(0), F32(0.5)))
+        w = np.where(nxt > W_HI, F32(1), np.where(nxt < W_LO, F32(0), F32(0.5)))
         hl, hn_ = H(last), H(nxt)
         s1 = (w * (hl - hn_)).astype(np.float64).sum(axis=(1, 2))
         s2 = (w * hl).astype(np.float64).sum(axis=(1, 2))
@@ -294,31 +303,31 @@ class KernelModelEnv:
         prev = [self._k_of(self.pos[:, j], j, self.t) for j in range(A)]
         new_pos, masks, acts = self._choose_and_move(actions)
         new = [self._k_of(new_pos[:, i], i, self.t + 1) for i in range(A)]
-        last = self.glob
-        self.glob = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
-        rel, ab = self._reward(last, self.glob)
-        fused = np.empty_like(self.local)
+        last = self.glob_o
+        self.glob_o = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
+        rel, ab = self._reward(last, self.glob_o)
+        fused = np.empty_like(self.local_o)
         for i in range(A):
             passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
-            fused[:, i] = self._apply(self.local[:, i], passes)
-            self.local[:, i] = self._apply(self.local[:, i], passes + [(new[i][0], new[i][1], False)])
-        self.local_fused_model = fused  # what a separate observe kernel would have stored
+            fused[:, i] = self._apply(self.local_o[:, i], passes)
+            self.local_o[:, i] = self._apply(self.local_o[:, i], passes + [(new[i][0], new[i][1], False)])
+        self.local_fused_model = self.to_p(fused)  # what a separate observe kernel would have stored
         self.pos = new_pos
         self.t += 1
         return dict(comm=comm, mask=masks, action=acts, reward_rel=rel, reward_abs=ab)
 
     # ---- the same timestep split around a policy network (ipp_observe / ipp_act) ----------------
     def observe(self):
-        """Fuse + reward only; the fused local maps are rounded to float32 here (state in HBM)."""
+        """Fuse + reward only (same float32 odds state, so split and fused modes agree bit for bit)."""
         A = self.A
         comm = self.comm()
         prev = [self._k_of(self.pos[:, j], j, self.t) for j in range(A)]
-        last = self.glob
-        self.glob = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
-        rel, ab = self._reward(last, self.glob)
+        last = self.glob_o
+        self.glob_o = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
+        rel, ab = self._reward(last, self.glob_o)
         for i in range(A):
             passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
-            self.local[:, i] = self._apply(self.local[:, i], passes)
+            self.local_o[:, i] = self._apply(self.local_o[:, i], passes)
         return dict(comm=comm, reward_rel=rel, reward_abs=ab)
 
     def act(self, actions=None):
@@ -326,7 +335,7 @@ class KernelModelEnv:
         new_pos, masks, acts = self._choose_and_move(actions)
         for i in range(A):
             inr, k = self._k_of(new_pos[:, i], i, self.t + 1)
-            self.local[:, i] = self._apply(self.local[:, i], [(inr, k, False)])
+            self.local_o[:, i] = self._apply(self.local_o[:, i], [(inr, k, False)])
         self.pos = new_pos
         self.t += 1
         return dict(mask=masks, action=acts)

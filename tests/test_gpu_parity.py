@@ -108,6 +108,9 @@ def test_fused_step_bit_exact_vs_kernel_model(tag, n_agents, B, variant):
         assert np.array_equal(_bits(env.masks.cpu().numpy(), env.A, 6), out["mask"])
         assert np.array_equal(env.actions.cpu().numpy(), out["action"])
         assert np.array_equal(env.pos.cpu().numpy(), model.pos)
+        # resident state (float32 odds) and its probability export, both bit for bit
+        assert np.array_equal(env.global_odds.cpu().numpy(), model.glob_o), t
+        assert np.array_equal(env.local_odds.cpu().numpy(), model.local_o), t
         assert np.array_equal(env.global_map.cpu().numpy(), model.glob), t
         assert np.array_equal(env.local_maps.cpu().numpy(), model.local), t
         assert np.allclose(rel.cpu().numpy(), out["reward_rel"], rtol=RTOL, atol=ATOL)
@@ -145,6 +148,7 @@ def test_split_observe_act_bit_exact_vs_kernel_model(variant):
             ma = model.act(actions=inj)
         assert np.array_equal(env.actions.cpu().numpy(), ma["action"])
         assert np.array_equal(env.pos.cpu().numpy(), model.pos)
+        assert np.array_equal(env.local_odds.cpu().numpy(), model.local_o)
         assert np.array_equal(env.local_maps.cpu().numpy(), model.local)
 
 

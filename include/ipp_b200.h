@@ -37,6 +37,7 @@ extern "C" {
 #define IPP_MAX_ALT 8
 #define IPP_MAX_LATTICE 128
 #define IPP_N_ACTIONS 6
+#define IPP_FLAG_QUADS 640 /* cells of a map are flagged in segments of 640 quads (2560 cells): ipp_state.map_flags */
 
 typedef enum ipp_status {
   IPP_OK = 0,
@@ -58,6 +59,7 @@ typedef struct ipp_config {
   int32_t gt_stride;       /* bytes between consecutive ground-truth maps, multiple of 16, >=      */
                            /* map_stride (16-byte rows so that TMA bulk copies can stage them)     */
   int32_t code_stride;     /* bytes of measurement codes per env: roundup16(ceil(gx*gy/4) * (A<=4 ? 4 : 8)) */
+  int32_t n_seg;           /* flag segments per map: ceil(ceil(gx*gy/4) / IPP_FLAG_QUADS)                  */
   int32_t px, py, n_alt;   /* agent lattice: agent/state_space.py:16-18                            */
   int32_t n_agents;        /* 1..IPP_MAX_AGENTS                                                    */
   int32_t n_envs;          /* envs owned by this handle (this GPU's shard)                         */
@@ -90,6 +92,11 @@ typedef struct ipp_state {
                        /* (4-cell quad, agent): low nibble = cell inside the agent's latest footprint,   */
                        /* high nibble = cell measured as occupied.  Half (t & 1) holds the measurements  */
                        /* communicated at step t, the other half receives those taken after the moves.   */
+  uint8_t* map_flags;  /* [n_envs, n_agents, n_seg] bookkeeping of the reference's lazily applied clamp          */
+                       /* (mapping/mappings.py:110-111 clamps a map only when the next update reads it): != 0    */
+                       /* means "this segment of the local map may hold odds outside [o_min, o_max]", so the    */
+                       /* next fuse pass must clamp all of it; 0 lets the kernels touch only footprint cells.  */
+                       /* Conservative (a set flag is always safe); written by reset / step / act.             */
 } ipp_state;
 
 /* Per-step inputs / outputs (device pointers; any output may be NULL). */

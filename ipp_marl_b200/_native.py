@@ -8,12 +8,13 @@ MAX_AGENTS = 8
 MAX_ALT = 8
 MAX_LATTICE = 128
 N_ACTIONS = 6
+FLAG_QUADS = 640
 
 
 class IppConfig(C.Structure):
     _fields_ = [
         ("gx", C.c_int32), ("gy", C.c_int32), ("map_stride", C.c_int32), ("gt_stride", C.c_int32),
-        ("code_stride", C.c_int32),
+        ("code_stride", C.c_int32), ("n_seg", C.c_int32),
         ("px", C.c_int32), ("py", C.c_int32), ("n_alt", C.c_int32),
         ("n_agents", C.c_int32), ("n_envs", C.c_int32), ("spacing", C.c_int32),
         ("min_altitude", C.c_int32), ("max_altitude", C.c_int32),
@@ -33,6 +34,7 @@ class IppState(C.Structure):
     _fields_ = [
         ("local_maps", C.c_void_p), ("global_map", C.c_void_p),
         ("ground_truth", C.c_void_p), ("episodes", C.c_void_p), ("meas_codes", C.c_void_p),
+        ("map_flags", C.c_void_p),
     ]
 
 

@@ -63,6 +63,8 @@ int validate(const ipp_config* c) {
   {
     const int64_t need = (((int64_t)c->gx * c->gy + 3) / 4) * (c->n_agents <= 4 ? 4 : 8);
     if (c->code_stride < need || (c->code_stride & 15) != 0) return IPP_ERR_INVALID_ARG;
+    const int64_t quads = ((int64_t)c->gx * c->gy + 3) / 4;
+    if (c->n_seg != (int32_t)((quads + IPP_FLAG_QUADS - 1) / IPP_FLAG_QUADS)) return IPP_ERR_INVALID_ARG;
   }
   if (c->n_agents < 1 || c->n_agents > IPP_MAX_AGENTS) return IPP_ERR_UNSUPPORTED;
   if (c->n_alt < 1 || c->n_alt > IPP_MAX_ALT) return IPP_ERR_UNSUPPORTED;
@@ -82,7 +84,7 @@ int validate(const ipp_config* c) {
 
 int check_state(const ipp_state* st) {
   if (st == nullptr || st->local_maps == nullptr || st->global_map == nullptr || st->ground_truth == nullptr ||
-      st->episodes == nullptr || st->meas_codes == nullptr)
+      st->episodes == nullptr || st->meas_codes == nullptr || st->map_flags == nullptr)
     return IPP_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(st->local_maps) & 15) || (reinterpret_cast<uintptr_t>(st->global_map) & 15) ||
       (reinterpret_cast<uintptr_t>(st->ground_truth) & 15) || (reinterpret_cast<uintptr_t>(st->meas_codes) & 15))

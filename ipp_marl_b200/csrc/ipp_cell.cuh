@@ -81,6 +81,13 @@ __device__ __forceinline__ F4 f4_select(uint32_t mask4, const F4 a, const F4 b) 
             make_float2((mask4 & 4u) ? a.hi.x : b.hi.x, (mask4 & 8u) ? a.hi.y : b.hi.y)};
 }
 
+// some cell lies outside [lo, hi]
+__device__ __forceinline__ bool f4_out_of_range(const F4 v, float lo, float hi) {
+  const float mx = fmaxf(fmaxf(v.lo.x, v.lo.y), fmaxf(v.hi.x, v.hi.y));
+  const float mn = fminf(fminf(v.lo.x, v.lo.y), fminf(v.hi.x, v.hi.y));
+  return mx > hi || mn < lo;
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

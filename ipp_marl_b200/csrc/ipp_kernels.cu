@@ -286,6 +286,9 @@ __global__ void __launch_bounds__(STEP_THREADS)
   __shared__ double s_red[2][STEP_THREADS / 32];
 
   load_env_meta<A>(cfg, &s_meta, tid, b, pos_in, pos_out, comm, DO_OWN);
+  // this variant keeps no range bookkeeping: mark every segment "may hold out-of-range odds" (always safe)
+  if (chunk == 0)
+    for (int32_t k = tid; k < A * cfg.n_seg; k += STEP_THREADS) st.map_flags[(int64_t)b * A * cfg.n_seg + k] = 1;
   __syncthreads();
 
   const int32_t n_cells = cfg.gx * cfg.gy;
@@ -375,8 +378,10 @@ __global__ void __launch_bounds__(256)
       if (own == 0u) continue;
       float* lp = st.local_maps + ((int64_t)b * A + i) * stride + ((int64_t)q << 2);
       const F4 o = f4_from(*reinterpret_cast<const float4*>(lp));
-      const F4 upd = f4_mul(f4_clamp(o, cfg.o_min, cfg.o_max), f4_from(lut[s_row[i] + byte]));
-      *reinterpret_cast<float4*>(lp) = f4_to(f4_select(own, upd, o));
+      const F4 upd = f4_select(own, f4_mul(f4_clamp(o, cfg.o_min, cfg.o_max), f4_from(lut[s_row[i] + byte])), o);
+      *reinterpret_cast<float4*>(lp) = f4_to(upd);
+      if (f4_out_of_range(upd, cfg.o_min, cfg.o_max))  // same-value stores from several threads: benign
+        st.map_flags[((int64_t)b * A + i) * cfg.n_seg + q / IPP_FLAG_QUADS] = 1;
     }
   }
 }
@@ -434,7 +439,8 @@ struct MtStream {
 __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__ ipp_config cfg,
                                                          const uint32_t* __restrict__ episodes,
                                                          int32_t* __restrict__ pos_out,
-                                                         int32_t* __restrict__ gt_params) {
+                                                         int32_t* __restrict__ gt_params,
+                                                         uint8_t* __restrict__ flags) {
   const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t A = cfg.n_agents;
   if (idx >= cfg.n_envs * (A + 1)) return;
@@ -451,6 +457,15 @@ __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__
     p[0] = x;
     p[1] = y;
     p[2] = 15;  // state_space.py:32 hard-codes the start altitude
+    // range flags of the local map after the t = 0 measurement (prior odds times k_hi / k_lo of that altitude)
+    {
+      const int32_t iz = clampi(15 / cfg.spacing - cfg.min_altitude / cfg.spacing, 0, cfg.n_alt - 1);
+      const float o = fminf(fmaxf(to_odds(cfg.prior), cfg.o_min), cfg.o_max);
+      const bool in_range = o * cfg.k_hi[iz] <= cfg.o_max && o * cfg.k_hi[iz] >= cfg.o_min &&
+                            o * cfg.k_lo[iz] <= cfg.o_max && o * cfg.k_lo[iz] >= cfg.o_min &&
+                            to_odds(cfg.prior) == o;
+      for (int32_t sgm = 0; sgm < cfg.n_seg; ++sgm) flags[((int64_t)b * A + a) * cfg.n_seg + sgm] = in_range ? 0 : 1;
+    }
   } else {
     mt.seed(ep);  // np.random.seed(episode): ground_truths.py:43
     const int32_t split = (int32_t)mt.bounded(3u);
@@ -626,7 +641,8 @@ cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const float
                          int32_t* pos_out, int32_t* gt_params, cudaStream_t s) {
   const int threads = 128;
   const int n = cfg.n_envs * (cfg.n_agents + 1);
-  reset_prep_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(cfg, st.episodes, pos_out, gt_params);
+  reset_prep_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(cfg, st.episodes, pos_out, gt_params,
+                                                                    st.map_flags);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const dim3 grid((unsigned)plan.n_chunks * (unsigned)cfg.n_envs);

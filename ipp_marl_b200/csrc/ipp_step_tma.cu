@@ -8,10 +8,17 @@
 //   producer warp : per item, writes EnvMeta, bulk-loads the code rows (-> env_full) and then the
 //                   item's A+1 maps, each into the next free map slot (cp.async.bulk, SASS UBLKCP,
 //                   completion on map_full via expect_tx / complete_tx);
-//   consumer warps: pull (item, tile) tasks from a shared counter (dynamic load balance: footprints make
-//                   the work per tile very uneven).  A warp decodes the tile's codes once (QuadCtx in
-//                   registers), then for each of the item's maps waits map_full, updates its 32 quads
-//                   in place (ipp_cell.cuh) and arrives on map_done — it never waits for other warps;
+//   consumer warps: pull tasks from a shared counter (dynamic load balance).  An item has NT + A tasks:
+//                   * NT tile tasks on the GLOBAL map — every cell gets all A fuse passes and its reward terms
+//                     (dense: 32 quads per warp, straight-line clamp/multiply chain, multipliers from the LUT);
+//                   * one task per LOCAL map, footprint-sparse: each enabled fuse pass and the own update walk
+//                     only the quad range of their footprint (a map whose range flag is clear is known to lie
+//                     inside [o_min, o_max], so the pass-wide clamp of the reference is a no-op on every
+//                     untouched cell — they pass through shared memory without being read by any thread);
+//                   (A = 8 needs more map slots than fit for dynamic scheduling: static tiles that update all
+//                   A + 1 maps densely, the pre-sparse code path)
+//                   a warp waits map_full, updates the slot in place and arrives on map_done — it never waits
+//                   for other warps;
 //   storer warp   : waits map_done, writes the slot back with cp.async.bulk shared->global, frees the
 //                   slot (map_empty) once the bulk engine has read it, and finishes the per-env
 //                   reward from the tiles' partial sums.
@@ -27,7 +34,109 @@ template <int A>
 struct StageMeta {
   EnvMeta<A> env;
   int32_t b, chunk, nq, pad;
+  int32_t qlo_prev[A], qhi_prev[A];  // item-local quad range of agent j's communicated footprint (lo > hi: none)
+  int32_t qlo_next[A], qhi_next[A];  // same for the footprint after the move
+  uint32_t dirty[A];                 // range flag of local map i's segment (ipp_state.map_flags)
 };
+
+static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work item)");
+
+// ------------------------------------------------------------------------------------------------
+// GLOBAL map, one quad: all A fuse passes (coma_wrapper.py:93-95) + the reward terms
+// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).  Straight-line: a pass is
+// clamp + multiply, the multipliers of all four cells come from one LUT load per agent (k_out outside
+// the footprint), so no footprint logic is needed at all.
+// ------------------------------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
+                                              const float4* lut, const float4 o4, const uint32_t valid, double& s1,
+                                              double& s2) {
+  const float lo = cfg.o_min, hi = cfg.o_max;
+  const F4 oc = f4_clamp(f4_from(o4), lo, hi);
+  F4 o = oc;
+  uint32_t touched = 0;
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    const uint32_t byte = cw.byte(j);
+    touched |= byte;
+    if (j > 0) o = f4_clamp(o, lo, hi);
+    o = f4_mul(o, f4_from(lut[meta.lut_prev[j] + byte]));
+  }
+  touched = (cfg.k_out == 1.0f) ? (touched & 0xFu) : 0xFu;
+  float a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (!((valid >> c) & 1u)) continue;
+    const float next = f4_get(o, c);
+    const float hl = entropy_bits_odds(f4_get(oc, c));
+    float hn = hl;
+    if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl
+      hn = ((touched >> c) & 1u) ? entropy_bits_odds(fminf(fmaxf(next, lo), hi)) : hl;
+    const float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
+    a1 += w * (hl - hn);
+    a2 += w * hl;
+  }
+  s1 += (double)a1;
+  s2 += (double)a2;
+  return f4_to(o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LOCAL map of agent i, whole item, one warp (agent/agent.py:62-71,91-94; mapping/mappings.py:80-124,32-61).
+// Reference semantics: every enabled fuse pass clamps the WHOLE map and multiplies the cells of footprint j;
+// the own update clamps and multiplies only the cells of the new footprint.  Here a pass walks the quad range
+// of its footprint only: cells it does not visit are inside [o_min, o_max] (flag clear, or clamped by the
+// dense pre-pass below), so the whole-map clamp leaves them unchanged bit for bit.  Results of a pass that is
+// followed by another fuse pass are stored clamped (that pass would clamp them anyway); the results of the
+// last pass stay unclamped like in the reference, and the flag records whether any of them left the range.
+// ------------------------------------------------------------------------------------------------
+template <int A, bool DO_OWN>
+__device__ __forceinline__ void local_map_task(const ipp_config& cfg, const StageMeta<A>& sm, const int i,
+                                               float4* map, const unsigned char* code_prev,
+                                               const unsigned char* code_next, const float4* lut,
+                                               uint8_t* __restrict__ flag, const int lane) {
+  constexpr int AP = A <= 4 ? 4 : 8;
+  const float lo = cfg.o_min, hi = cfg.o_max;
+  const bool kout_one = (cfg.k_out == 1.0f);
+  const uint32_t en = sm.env.comm[i];
+  bool bad = false;
+  if (en != 0u) {
+    if (sm.dirty[i] != 0u) {  // the map may hold out-of-range odds: the first fuse pass clamps every cell
+      for (int32_t q = lane; q < sm.nq; q += 32) map[q] = f4_to(f4_clamp(f4_from(map[q]), lo, hi));
+      __syncwarp();
+    }
+    const int last = 31 - __clz(en);
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      if (!((en >> j) & 1u)) continue;  // warp-uniform
+      const int32_t q0 = kout_one ? sm.qlo_prev[j] : 0, q1 = kout_one ? sm.qhi_prev[j] : sm.nq - 1;
+      const uint32_t row = sm.env.lut_prev[j];
+      for (int32_t q = q0 + lane; q <= q1; q += 32) {
+        const uint32_t byte = code_prev[q * AP + j];
+        if ((byte & 0xFu) == 0u && kout_one) continue;
+        F4 o = f4_mul(f4_clamp(f4_from(map[q]), lo, hi), f4_from(lut[row + byte]));
+        if (j != last) o = f4_clamp(o, lo, hi);
+        else bad |= f4_out_of_range(o, lo, hi);
+        map[q] = f4_to(o);
+      }
+      __syncwarp();  // the next pass visits the quads in a different lane order
+    }
+  }
+  if (DO_OWN) {
+    const uint32_t row = sm.env.lut_next[i];
+    for (int32_t q = sm.qlo_next[i] + lane; q <= sm.qhi_next[i]; q += 32) {
+      const uint32_t byte = code_next[q * AP + i];
+      const uint32_t own = byte & 0xFu;
+      if (own == 0u) continue;
+      const F4 o = f4_from(map[q]);
+      const F4 upd = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[row + byte])), o);
+      bad |= f4_out_of_range(upd, lo, hi);
+      map[q] = f4_to(upd);
+    }
+  }
+  bad = __any_sync(0xFFFFFFFFu, bad);
+  if (lane == 0) *flag = (uint8_t)((bad || (en == 0u && sm.dirty[i] != 0u)) ? 1 : 0);
+}
 
 constexpr int TMA_D_MAP = 16;     // map slots (power of two: slot / phase of a counter by shift & mask)
 constexpr int TMA_D_ENV = 4;      // env slots
@@ -50,6 +159,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   constexpr int AP = A <= 4 ? 4 : 8;
   constexpr int QPC = TMA_QPC;
   constexpr int CONSUMER_THREADS = TMA_CONSUMER_WARPS * 32;
+  // Dynamic scheduling needs 2 items' maps to fit the slot ring (see the producer's comment on phase parity);
+  // it also enables the footprint-sparse local-map tasks.  A = 8 runs static dense tiles.
+  constexpr bool kSparse = (2 * A <= 14);
   unsigned char* map_slots = smem;
   unsigned char* env_slots = map_slots + (size_t)TMA_D_MAP * slot_bytes;
   float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)TMA_D_ENV * env_bytes);
@@ -78,7 +190,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     }
     for (int s = 0; s < TMA_D_ENV; ++s) {
       ptx::mbar_init(env_full + 8u * s, 1);       // producer
-      ptx::mbar_init(env_done + 8u * s, NT + 1);  // tiles + storer
+      ptx::mbar_init(env_done + 8u * s, (kSparse ? NT + A : NT) + 1);  // tasks + storer
     }
     *tile_counter = 0u;
     ptx::fence_mbar_init();
@@ -152,6 +264,25 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         meta[es].chunk = chunk;
         meta[es].nq = nq;
       }
+      if (kSparse) {
+        if (lane < 2 * A) {  // item-local quad ranges of the communicated (lane < A) / new footprints
+          const int a = lane < A ? lane : lane - A;
+          int32_t q_lo = 1, q_hi = 0;
+          if (lane < A || DO_OWN)
+            footprint_quads(cfg, (lane < A ? pos_in : pos_out) + ((int64_t)b * A + a) * 3, q_lo, q_hi);
+          q_lo = max(q_lo - chunk * QPC, 0);
+          q_hi = min(q_hi - chunk * QPC, nq - 1);
+          if (lane < A) {
+            meta[es].qlo_prev[a] = q_lo;
+            meta[es].qhi_prev[a] = q_hi;
+          } else {
+            meta[es].qlo_next[a] = q_lo;
+            meta[es].qhi_next[a] = q_hi;
+          }
+        } else if (lane < 3 * A) {
+          meta[es].dirty[lane - 2 * A] = st.map_flags[((int64_t)b * A + (lane - 2 * A)) * cfg.n_seg + chunk];
+        }
+      }
       __syncwarp();
       if (lane == 0) {
         // Consumers pick (item, tile) tasks dynamically, so a warp may skip whole items and then wait on a
@@ -194,22 +325,68 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   const uint32_t my_items = (blockIdx.x < (uint32_t)n_items)
                                 ? (uint32_t)(n_items - (int32_t)blockIdx.x + (int32_t)gridDim.x - 1) / gridDim.x
                                 : 0u;
-  const uint32_t total_tiles = my_items * NT;
-  constexpr bool kDynamic = (2 * A <= 14);  // see the producer's comment on phase parity
   const uint32_t warp = (uint32_t)tid >> 5;
-  uint32_t n_static = warp;
-  while (true) {
-    uint32_t n;
-    if (kDynamic) {
-      n = 0;
+
+  if (kSparse) {
+    constexpr uint32_t TPI = NT + A;  // tasks per item: NT global tiles, then one per local map
+    const uint32_t total_tasks = my_items * TPI;
+    while (true) {
+      uint32_t n = 0;
       if (lane == 0) n = atomicAdd(tile_counter, 1u);
       n = __shfl_sync(0xFFFFFFFFu, n, 0);
-    } else {  // warp w owns tile w of every item (warps >= NT idle): every barrier is waited in order
-      if (warp >= (uint32_t)NT) break;
-      n = n_static;
-      n_static += NT;
+      if (n >= total_tasks) break;
+      const uint32_t k = n / TPI, sub = n - k * TPI;
+      const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
+      ptx::mbar_wait(env_full + 8u * es, pe);
+      const StageMeta<A>& sm = meta[es];
+      const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
+      const unsigned char* code_next = code_prev + code_row;
+      if (sub < (uint32_t)NT) {
+        // ---- one tile of the global map ----
+        const uint32_t g = k * (A + 1);
+        const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
+        const int32_t ql = (int32_t)sub * 32 + lane;
+        ptx::mbar_wait(map_full + 8u * ms, pm);
+        double s1 = 0.0, s2 = 0.0;
+        if (ql < sm.nq) {
+          float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
+          *mp = global_quad<A>(cfg, sm.env, load_code<A>(code_prev, ql), lut, *mp,
+                               valid_mask4((sm.chunk * QPC + ql) << 2, n_cells), s1, s2);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+          double* r = red + (size_t)es * 2 * NT;
+          r[sub] = s1;
+          r[NT + sub] = s2;
+        }
+        ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
+      } else {
+        // ---- one whole local map, footprint-sparse ----
+        const int i = (int)(sub - NT);
+        const uint32_t g = k * (A + 1) + 1u + (uint32_t)i;
+        const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
+        ptx::mbar_wait(map_full + 8u * ms, pm);
+        local_map_task<A, DO_OWN>(cfg, sm, i, reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes),
+                                  code_prev, code_next, lut,
+                                  st.map_flags + ((int64_t)sm.b * A + i) * cfg.n_seg + sm.chunk, lane);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cnt(map_done + 8u * ms, NT);  // stands for the NT tiles of a dense map
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(env_done + 8u * es);
     }
-    if (n >= total_tiles) break;
+    return;
+  }
+
+  // ---- static dense tiles (A = 8): warp w owns tile w of every item (warps >= NT idle), all A + 1 maps;
+  //      every barrier is waited in order, so phase parity is never ambiguous ----
+  if (warp >= (uint32_t)NT) return;
+  const uint32_t total_tiles = my_items * NT;
+  for (uint32_t n = warp; n < total_tiles; n += NT) {
     const uint32_t k = n / NT, tile = n - k * NT;
     const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
     ptx::mbar_wait(env_full + 8u * es, pe);
@@ -226,6 +403,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       if (DO_OWN) next = load_code<A>(code_next, ql);
       valid = valid_mask4((sm.chunk * QPC + ql) << 2, n_cells);
     }
+    if (tile == 0 && lane < A)  // no range bookkeeping on this path: flags stay "unknown" (always safe)
+      st.map_flags[((int64_t)sm.b * A + lane) * cfg.n_seg + sm.chunk] = 1;
     uint32_t g = k * (A + 1);
     // ---- global map ----
     {
@@ -243,7 +422,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         r[tile] = s1;
         r[NT + tile] = s2;
       }
-      ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
+      ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
       ++g;

@@ -43,6 +43,7 @@ class BatchedIPPEnv:
         self._gt = torch.zeros((self.B, t.gt_stride), dtype=torch.uint8, device=dev)
         self.episodes = torch.zeros((self.B,), dtype=torch.int32, device=dev)  # bit pattern = uint32
         self._codes = torch.zeros((2, self.B, t.code_stride), dtype=torch.uint8, device=dev)
+        self._flags = torch.ones((self.B, self.A, int(self.cfg.n_seg)), dtype=torch.uint8, device=dev)
         self.positions = torch.zeros((self.T + 1, self.B, self.A, 3), dtype=torch.int32, device=dev)
         self.actions = torch.zeros((self.B, self.A), dtype=torch.int32, device=dev)
         self.masks = torch.zeros((self.B, self.A), dtype=torch.uint8, device=dev)
@@ -51,7 +52,7 @@ class BatchedIPPEnv:
         self.reward_abs = torch.zeros((self.B,), dtype=torch.float32, device=dev)
         self.stuck = torch.zeros((self.B,), dtype=torch.uint8, device=dev)
         self._state = N.IppState(_ptr(self._local), _ptr(self._glob), _ptr(self._gt), _ptr(self.episodes),
-                                 _ptr(self._codes))
+                                 _ptr(self._codes), _ptr(self._flags))
         self.t = 0
         self._observed = False
         self._folded = False

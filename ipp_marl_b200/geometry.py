@@ -135,12 +135,18 @@ class HostTables:
         return ((self.n_cells + 3) // 4 * per_quad + 15) // 16 * 16
 
 
+def n_flag_segments(tables):
+    """Flag segments per map (include/ipp_b200.h: IPP_FLAG_QUADS quads each)."""
+    return ((tables.n_cells + 3) // 4 + N.FLAG_QUADS - 1) // N.FLAG_QUADS
+
+
 def make_config(tables, n_envs):
     """Fill the C struct ipp_config (include/ipp_b200.h) from the host tables."""
     t = tables
     c = N.IppConfig()
     c.gx, c.gy, c.map_stride, c.gt_stride = t.gx, t.gy, t.map_stride, t.gt_stride
     c.code_stride = t.code_stride
+    c.n_seg = n_flag_segments(t)
     c.px, c.py, c.n_alt = t.px, t.py, t.n_alt
     c.n_agents, c.n_envs, c.spacing = t.n_agents, int(n_envs), t.spacing
     c.min_altitude, c.max_altitude = t.min_altitude, t.max_altitude

@@ -8,20 +8,20 @@
 //   producer warp : per item, writes EnvMeta, bulk-loads the code rows (-> env_full) and then the
 //                   item's A+1 maps, each into the next free map slot (cp.async.bulk, SASS UBLKCP,
 //                   completion on map_full via expect_tx / complete_tx);
-//   consumer warps: pull tasks from a shared counter (dynamic load balance).  An item has NT + A tasks:
-//                   * NT tile tasks on the GLOBAL map — every cell gets all A fuse passes and its reward terms
-//                     (dense: 32 quads per warp, straight-line clamp/multiply chain, multipliers from the LUT);
-//                   * one task per LOCAL map, footprint-sparse: each enabled fuse pass and the own update walk
-//                     only the quad range of their footprint (a map whose range flag is clear is known to lie
-//                     inside [o_min, o_max], so the pass-wide clamp of the reference is a no-op on every
-//                     untouched cell — they pass through shared memory without being read by any thread);
-//                   (A = 8 needs more map slots than fit for dynamic scheduling: static tiles that update all
-//                   A + 1 maps densely, the pre-sparse code path)
+//   consumer warps: pull (item, tile) tasks from a shared counter (dynamic load balance).  A warp decodes the
+//                   tile's code bytes once and takes its 32 quads through the item's maps, in registers:
+//                   * GLOBAL map: every cell gets all A fuse passes and its reward terms — a straight-line
+//                     clamp / multiply chain, the four multipliers of a quad from one LUT load per agent;
+//                   * LOCAL maps: the enabled fuse passes and the own update, but only where it matters: a map
+//                     whose range flag is clear is known to lie inside [o_min, o_max], so the whole-map clamp of
+//                     the reference is a no-op on cells outside every footprint and a (tile, map) pair that no
+//                     footprint reaches is skipped by one warp vote, without touching shared memory;
+//                   (A = 8 needs more map slots than fit for dynamic scheduling: static tiles, pre-sparse code)
 //                   a warp waits map_full, updates the slot in place and arrives on map_done — it never waits
 //                   for other warps;
 //   storer warp   : waits map_done, writes the slot back with cp.async.bulk shared->global, frees the
-//                   slot (map_empty) once the bulk engine has read it, and finishes the per-env
-//                   reward from the tiles' partial sums.
+//                   slot (map_empty) once the bulk engine has read it, finishes the per-env reward from the
+//                   tiles' partial sums and writes the local maps' new range flags.
 // HBM traffic is one read + one write of every belief map plus the code rows; all global addressing
 // is done by the TMA unit, so the SM issue slots go to the map arithmetic.
 #include "ipp_cell.cuh"
@@ -34,9 +34,8 @@ template <int A>
 struct StageMeta {
   EnvMeta<A> env;
   int32_t b, chunk, nq, pad;
-  int32_t qlo_prev[A], qhi_prev[A];  // item-local quad range of agent j's communicated footprint (lo > hi: none)
-  int32_t qlo_next[A], qhi_next[A];  // same for the footprint after the move
-  uint32_t dirty[A];                 // range flag of local map i's segment (ipp_state.map_flags)
+  uint32_t dirty[A];  // range flag of local map i's segment on entry (ipp_state.map_flags)
+  uint32_t bad[A];    // set by a tile task whose results left [o_min, o_max]
 };
 
 static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work item)");
@@ -45,12 +44,12 @@ static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work it
 // GLOBAL map, one quad: all A fuse passes (coma_wrapper.py:93-95) + the reward terms
 // s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).  Straight-line: a pass is
 // clamp + multiply, the multipliers of all four cells come from one LUT load per agent (k_out outside
-// the footprint), so no footprint logic is needed at all.
+// the footprint), so no footprint logic is needed at all.  kj[] keeps the multipliers for the local maps.
 // ------------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
-                                              const float4* lut, const float4 o4, const uint32_t valid, double& s1,
-                                              double& s2) {
+                                              const float4* lut, const float4 o4, const uint32_t valid, F4 (&kj)[A],
+                                              double& s1, double& s2) {
   const float lo = cfg.o_min, hi = cfg.o_max;
   const F4 oc = f4_clamp(f4_from(o4), lo, hi);
   F4 o = oc;
@@ -59,8 +58,9 @@ __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMe
   for (int j = 0; j < A; ++j) {
     const uint32_t byte = cw.byte(j);
     touched |= byte;
+    kj[j] = f4_from(lut[meta.lut_prev[j] + byte]);
     if (j > 0) o = f4_clamp(o, lo, hi);
-    o = f4_mul(o, f4_from(lut[meta.lut_prev[j] + byte]));
+    o = f4_mul(o, kj[j]);
   }
   touched = (cfg.k_out == 1.0f) ? (touched & 0xFu) : 0xFu;
   float a1 = 0.0f, a2 = 0.0f;
@@ -82,60 +82,26 @@ __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMe
 }
 
 // ------------------------------------------------------------------------------------------------
-// LOCAL map of agent i, whole item, one warp (agent/agent.py:62-71,91-94; mapping/mappings.py:80-124,32-61).
-// Reference semantics: every enabled fuse pass clamps the WHOLE map and multiplies the cells of footprint j;
-// the own update clamps and multiplies only the cells of the new footprint.  Here a pass walks the quad range
-// of its footprint only: cells it does not visit are inside [o_min, o_max] (flag clear, or clamped by the
-// dense pre-pass below), so the whole-map clamp leaves them unchanged bit for bit.  Results of a pass that is
-// followed by another fuse pass are stored clamped (that pass would clamp them anyway); the results of the
-// last pass stay unclamped like in the reference, and the flag records whether any of them left the range.
+// LOCAL map of agent i, one quad (agent/agent.py:62-71,91-94; mapping/mappings.py:80-124,32-61): the enabled
+// fuse passes in id order — each clamps and multiplies (by exactly 1 outside footprint j) — then, inside the new
+// own footprint only, clamp and multiply.  Straight-line; `en` is warp-uniform.  Returns true when a result left
+// [o_min, o_max] (the reference clamps lazily, at the next update that reads the cell).
 // ------------------------------------------------------------------------------------------------
 template <int A, bool DO_OWN>
-__device__ __forceinline__ void local_map_task(const ipp_config& cfg, const StageMeta<A>& sm, const int i,
-                                               float4* map, const unsigned char* code_prev,
-                                               const unsigned char* code_next, const float4* lut,
-                                               uint8_t* __restrict__ flag, const int lane) {
-  constexpr int AP = A <= 4 ? 4 : 8;
+__device__ __forceinline__ bool local_quad(const ipp_config& cfg, const uint32_t en, const F4 (&kj)[A],
+                                           const uint32_t own_byte, const uint32_t lut_next, const float4* lut,
+                                           float4* mp) {
   const float lo = cfg.o_min, hi = cfg.o_max;
-  const bool kout_one = (cfg.k_out == 1.0f);
-  const uint32_t en = sm.env.comm[i];
-  bool bad = false;
-  if (en != 0u) {
-    if (sm.dirty[i] != 0u) {  // the map may hold out-of-range odds: the first fuse pass clamps every cell
-      for (int32_t q = lane; q < sm.nq; q += 32) map[q] = f4_to(f4_clamp(f4_from(map[q]), lo, hi));
-      __syncwarp();
-    }
-    const int last = 31 - __clz(en);
+  F4 o = f4_from(*mp);
 #pragma unroll
-    for (int j = 0; j < A; ++j) {
-      if (!((en >> j) & 1u)) continue;  // warp-uniform
-      const int32_t q0 = kout_one ? sm.qlo_prev[j] : 0, q1 = kout_one ? sm.qhi_prev[j] : sm.nq - 1;
-      const uint32_t row = sm.env.lut_prev[j];
-      for (int32_t q = q0 + lane; q <= q1; q += 32) {
-        const uint32_t byte = code_prev[q * AP + j];
-        if ((byte & 0xFu) == 0u && kout_one) continue;
-        F4 o = f4_mul(f4_clamp(f4_from(map[q]), lo, hi), f4_from(lut[row + byte]));
-        if (j != last) o = f4_clamp(o, lo, hi);
-        else bad |= f4_out_of_range(o, lo, hi);
-        map[q] = f4_to(o);
-      }
-      __syncwarp();  // the next pass visits the quads in a different lane order
-    }
-  }
+  for (int j = 0; j < A; ++j)
+    if ((en >> j) & 1u) o = f4_mul(f4_clamp(o, lo, hi), kj[j]);  // warp-uniform branch
   if (DO_OWN) {
-    const uint32_t row = sm.env.lut_next[i];
-    for (int32_t q = sm.qlo_next[i] + lane; q <= sm.qhi_next[i]; q += 32) {
-      const uint32_t byte = code_next[q * AP + i];
-      const uint32_t own = byte & 0xFu;
-      if (own == 0u) continue;
-      const F4 o = f4_from(map[q]);
-      const F4 upd = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[row + byte])), o);
-      bad |= f4_out_of_range(upd, lo, hi);
-      map[q] = f4_to(upd);
-    }
+    const uint32_t own = own_byte & 0xFu;
+    if (own != 0u) o = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[lut_next + own_byte])), o);
   }
-  bad = __any_sync(0xFFFFFFFFu, bad);
-  if (lane == 0) *flag = (uint8_t)((bad || (en == 0u && sm.dirty[i] != 0u)) ? 1 : 0);
+  *mp = f4_to(o);
+  return f4_out_of_range(o, lo, hi);
 }
 
 constexpr int TMA_D_MAP = 16;     // map slots (power of two: slot / phase of a counter by shift & mask)
@@ -190,7 +156,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     }
     for (int s = 0; s < TMA_D_ENV; ++s) {
       ptx::mbar_init(env_full + 8u * s, 1);       // producer
-      ptx::mbar_init(env_done + 8u * s, (kSparse ? NT + A : NT) + 1);  // tasks + storer
+      ptx::mbar_init(env_done + 8u * s, NT + 1);  // tiles + storer
     }
     *tile_counter = 0u;
     ptx::fence_mbar_init();
@@ -231,6 +197,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           dst = st.global_map + (int64_t)b * stride + cell0;
         } else {
           dst = st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
+          if (kSparse) {  // new range flag: some result left the range, or nothing clamped an already flagged map
+            const bool keep = sm.env.comm[m - 1] == 0u && sm.dirty[m - 1] != 0u;
+            st.map_flags[((int64_t)b * A + (m - 1)) * cfg.n_seg + chunk] = (uint8_t)((sm.bad[m - 1] != 0u || keep) ? 1 : 0);
+          }
         }
         ptx::bulk_store(dst, ptx::smem_u32(map_slots + (size_t)ms * slot_bytes), map_bytes);
         ptx::bulk_commit();
@@ -264,24 +234,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         meta[es].chunk = chunk;
         meta[es].nq = nq;
       }
-      if (kSparse) {
-        if (lane < 2 * A) {  // item-local quad ranges of the communicated (lane < A) / new footprints
-          const int a = lane < A ? lane : lane - A;
-          int32_t q_lo = 1, q_hi = 0;
-          if (lane < A || DO_OWN)
-            footprint_quads(cfg, (lane < A ? pos_in : pos_out) + ((int64_t)b * A + a) * 3, q_lo, q_hi);
-          q_lo = max(q_lo - chunk * QPC, 0);
-          q_hi = min(q_hi - chunk * QPC, nq - 1);
-          if (lane < A) {
-            meta[es].qlo_prev[a] = q_lo;
-            meta[es].qhi_prev[a] = q_hi;
-          } else {
-            meta[es].qlo_next[a] = q_lo;
-            meta[es].qhi_next[a] = q_hi;
-          }
-        } else if (lane < 3 * A) {
-          meta[es].dirty[lane - 2 * A] = st.map_flags[((int64_t)b * A + (lane - 2 * A)) * cfg.n_seg + chunk];
-        }
+      if (kSparse && lane < A) {
+        meta[es].dirty[lane] = st.map_flags[((int64_t)b * A + lane) * cfg.n_seg + chunk];
+        meta[es].bad[lane] = 0u;
       }
       __syncwarp();
       if (lane == 0) {
@@ -328,53 +283,79 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   const uint32_t warp = (uint32_t)tid >> 5;
 
   if (kSparse) {
-    constexpr uint32_t TPI = NT + A;  // tasks per item: NT global tiles, then one per local map
-    const uint32_t total_tasks = my_items * TPI;
+    const uint32_t total_tiles = my_items * NT;
+    const bool kout_one = (cfg.k_out == 1.0f);
     while (true) {
       uint32_t n = 0;
       if (lane == 0) n = atomicAdd(tile_counter, 1u);
       n = __shfl_sync(0xFFFFFFFFu, n, 0);
-      if (n >= total_tasks) break;
-      const uint32_t k = n / TPI, sub = n - k * TPI;
+      if (n >= total_tiles) break;
+      const uint32_t k = n / NT, tile = n - k * NT;
       const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
       ptx::mbar_wait(env_full + 8u * es, pe);
-      const StageMeta<A>& sm = meta[es];
+      StageMeta<A>& sm = meta[es];
+      const int32_t ql = (int32_t)tile * 32 + lane;
+      const bool have = ql < sm.nq;
       const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
       const unsigned char* code_next = code_prev + code_row;
-      if (sub < (uint32_t)NT) {
-        // ---- one tile of the global map ----
-        const uint32_t g = k * (A + 1);
+      CodeWord<A> cw, nw;
+#pragma unroll
+      for (int w = 0; w < CodeWord<A>::WORDS; ++w) cw.w[w] = nw.w[w] = 0u;
+      if (have) {
+        cw = load_code<A>(code_prev, ql);
+        if (DO_OWN) nw = load_code<A>(code_next, ql);
+      }
+      F4 kj[A];
+      uint32_t g = k * (A + 1);
+      // ---- global map ----
+      {
         const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-        const int32_t ql = (int32_t)sub * 32 + lane;
         ptx::mbar_wait(map_full + 8u * ms, pm);
         double s1 = 0.0, s2 = 0.0;
-        if (ql < sm.nq) {
+        if (have) {
           float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
-          *mp = global_quad<A>(cfg, sm.env, load_code<A>(code_prev, ql), lut, *mp,
-                               valid_mask4((sm.chunk * QPC + ql) << 2, n_cells), s1, s2);
+          *mp = global_quad<A>(cfg, sm.env, cw, lut, *mp, valid_mask4((sm.chunk * QPC + ql) << 2, n_cells), kj, s1, s2);
+        } else {
+#pragma unroll
+          for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
         }
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
         if (lane == 0) {
           double* r = red + (size_t)es * 2 * NT;
-          r[sub] = s1;
-          r[NT + sub] = s2;
+          r[tile] = s1;
+          r[NT + tile] = s2;
         }
         ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
-      } else {
-        // ---- one whole local map, footprint-sparse ----
-        const int i = (int)(sub - NT);
-        const uint32_t g = k * (A + 1) + 1u + (uint32_t)i;
+        ++g;
+      }
+      // ---- local maps ----
+      uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
+#pragma unroll
+      for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
+#pragma unroll
+      for (int i = 0; i < A; ++i, ++g) {
         const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-        ptx::mbar_wait(map_full + 8u * ms, pm);
-        local_map_task<A, DO_OWN>(cfg, sm, i, reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes),
-                                  code_prev, code_next, lut,
-                                  st.map_flags + ((int64_t)sm.b * A + i) * cfg.n_seg + sm.chunk, lane);
-        ptx::fence_proxy_async();
+        const uint32_t en = sm.env.comm[i];
+        const uint32_t own_byte = DO_OWN ? nw.byte(i) : 0u;
+        // does this quad have work?  cells of an enabled fuse pass or of the own footprint; everything if the
+        // map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
+        const bool all = en != 0u && (sm.dirty[i] != 0u || !kout_one);
+        const bool mine = have && (all || ((in_prev & sm.env.comm4[i]) | (own_byte & 0xFu)) != 0u);
+        const bool any = __any_sync(0xFFFFFFFFu, mine);
+        ptx::mbar_wait(map_full + 8u * ms, pm);  // (also when skipping: the storer must not run ahead of the load)
+        if (any) {
+          bool bad = false;
+          if (mine)
+            bad = local_quad<A, DO_OWN>(cfg, en, kj, own_byte, sm.env.lut_next[i], lut,
+                                        reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql);
+          if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) sm.bad[i] = 1u;
+          ptx::fence_proxy_async();
+        }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cnt(map_done + 8u * ms, NT);  // stands for the NT tiles of a dense map
+        if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(env_done + 8u * es);

@@ -12,8 +12,9 @@
 //     code byte into the 4 odds multipliers with ONE 16-byte table load (lut[altitude][byte]);
 //   * the 4 cells of a quad are processed branch-free, the multiplies two cells per instruction with the
 //     sm_100 packed-float32 FMUL2 form (IEEE per lane => still bit-exact);
-//   * a fuse pass whose footprint touches no cell of the whole warp degenerates to a clamp, clamps
-//     are idempotent, so such passes are skipped warp-uniformly and one clamp is applied instead;
+//   * a local map whose range flag (ipp_state.map_flags) is clear lies inside [o_min, o_max], so the whole-map
+//     clamp of a fuse pass changes nothing outside the footprints: quads no footprint reaches are skipped
+//     (the TMA kernel: by one warp vote per (tile, map); the direct kernel: not even loaded from HBM);
 //   * only the reward needs more: H(p) of the global map's cells from their odds (1 MUFU.RCP + 2 MUFU.LG2).
 #pragma once
 #include "ipp_device.cuh"
@@ -117,92 +118,6 @@ __device__ __forceinline__ CodeWord<A> load_code(const void* base, int32_t quad)
   return c;
 }
 
-template <int A>
-struct QuadCtx {
-  F4 kprev[A];       // multipliers of the communicated measurements (k_out outside a footprint)
-  uint32_t in_prev;  // bits 4j..4j+3: cells inside agent j's communicated footprint
-  uint32_t wcov;     // bit j: some active lane of this warp has a cell inside footprint j
-};
-
-// Must be called with the warp's loop-active lanes converged (it votes over __activemask()).
-// `lut` is the [n_alt][256] float4 table (shared or global memory).
-template <int A>
-__device__ __forceinline__ void make_quad_ctx(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& prev,
-                                              const float4* lut, QuadCtx<A>& q) {
-  q.in_prev = 0;
-  q.wcov = 0;
-  const uint32_t active = __activemask();
-  const bool kout_one = (cfg.k_out == 1.0f);
-#pragma unroll
-  for (int j = 0; j < A; ++j) {
-    const uint32_t byte = prev.byte(j);
-    const uint32_t in = byte & 0xFu;
-    q.in_prev |= in << (4 * j);
-    q.kprev[j] = f4_splat(cfg.k_out);
-    if (__any_sync(active, in != 0u) || !kout_one) {  // warp-uniform
-      q.wcov |= 1u << j;
-      q.kprev[j] = f4_from(lut[meta.lut_prev[j] + byte]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// One belief map (float32 odds) of the quad through its chain of passes.
-//   en      : bit j = fuse pass j enabled for this map (warp-uniform)
-//   own     : 4-bit mask of cells inside the own new footprint, k_own their multipliers
-// Semantics per cell (oracle/kernel_model.py::_apply): every enabled fuse pass clamps the odds and
-// multiplies by k_j (k_out outside footprint j); then, inside the own footprint only, clamp and
-// multiply by k_own.  Untouched cells keep o (or clamp(o) if some fuse pass ran) bit for bit.
-// Padding cells beyond gx*gy are never inside a footprint, hold the prior and stay unchanged.
-// oc_out = the clamped input odds (the reward's "last" map), touched = cells some pass multiplied.
-// ------------------------------------------------------------------------------------------------
-template <int A>
-__device__ __forceinline__ F4 update_map_quad(const ipp_config& cfg, const QuadCtx<A>& q, const F4 o_in,
-                                              const uint32_t en, const uint32_t en4, const uint32_t own,
-                                              const F4 k_own, F4& oc_out, uint32_t& touched) {
-  const bool kout_one = (cfg.k_out == 1.0f);
-  const bool any_fuse = en != 0u;
-  uint32_t x = q.in_prev & en4;  // footprint nibbles of the enabled passes, OR-folded into one nibble
-  if (A > 4) x |= x >> 16;
-  if (A > 2) x |= x >> 8;
-  if (A > 1) x |= x >> 4;
-  uint32_t t = (x & 0xFu) | own;
-  if (any_fuse && !kout_one) t = 0xFu;
-  touched = t;
-  F4 o = o_in;
-  bool clean = false;  // o is known to lie inside [o_min, o_max] (just clamped)
-  if (any_fuse) {      // the first enabled fuse pass clamps every cell of the map
-    o = f4_clamp(o, cfg.o_min, cfg.o_max);
-    clean = true;
-  }
-  oc_out = o;
-#pragma unroll
-  for (int j = 0; j < A; ++j) {
-    if (!((en >> j) & 1u)) continue;  // warp-uniform
-    if ((q.wcov >> j) & 1u) {         // warp-uniform: somebody's cell is inside footprint j
-      if (!clean) o = f4_clamp(o, cfg.o_min, cfg.o_max);
-      o = f4_mul(o, q.kprev[j]);
-      clean = false;
-    }
-    // else: the pass is a pure clamp for the whole warp; clamps are idempotent, so it is absorbed by
-    // the clamp of the next executed pass or by the one below
-  }
-  // A fuse pass skipped AFTER the last executed one still owes its clamp to every cell (warp-uniform).
-  {
-    const uint32_t exec = en & q.wcov;
-    const bool pending = exec != 0u && (en >> (32 - __clz(exec))) != 0u;  // enabled pass above the last executed
-    if (pending) {
-      o = f4_clamp(o, cfg.o_min, cfg.o_max);
-      clean = true;
-    }
-  }
-  if (own != 0u) {  // own update: only the cells inside the own footprint are clamped and multiplied
-    const F4 oc = clean ? o : f4_clamp(o, cfg.o_min, cfg.o_max);
-    o = f4_select(own, f4_mul(oc, k_own), o);
-  }
-  return o;
-}
-
 // float32 reward terms; H in bits (utils/state.py:118-121) of a cell given its CLAMPED odds:
 // q = 1/(1+o), p = o*q, H = -(p lg p + q lg q)
 __device__ __forceinline__ float lg2_approx(float x) {
@@ -220,48 +135,88 @@ __device__ __forceinline__ float entropy_bits_odds(float oc) {
 #define IPP_W_HI 1.0040080547332764f
 #define IPP_W_LO 0.9960079789161682f
 
-// Global map: fuse every agent's communicated measurement (coma_wrapper.py:93-95) and accumulate
-// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last)  (utils/reward.py:68-82).  `valid`: bit c = cell exists.
+// ------------------------------------------------------------------------------------------------
+// GLOBAL map, one quad: all A fuse passes (coma_wrapper.py:93-95) + the reward terms
+// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).  Straight-line: a pass is
+// clamp + multiply, the multipliers of all four cells come from one LUT load per agent (k_out outside
+// the footprint), so no footprint logic is needed at all.  kj[] keeps the multipliers for the local maps.
+// ------------------------------------------------------------------------------------------------
 template <int A>
-__device__ __forceinline__ float4 update_global_quad(const ipp_config& cfg, const QuadCtx<A>& q, const float4 o4,
-                                                     const uint32_t valid, double& s1, double& s2) {
-  F4 oc;
-  uint32_t touched;
-  const F4 on = update_map_quad<A>(cfg, q, f4_from(o4), (1u << A) - 1u, 0xFFFFFFFFu, 0u, f4_splat(1.0f), oc,
-                                   touched);
+__device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
+                                              const float4* lut, const float4 o4, const uint32_t valid, F4 (&kj)[A],
+                                              double& s1, double& s2) {
+  const float lo = cfg.o_min, hi = cfg.o_max;
+  const F4 oc = f4_clamp(f4_from(o4), lo, hi);
+  F4 o = oc;
+  uint32_t touched = 0;
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    const uint32_t byte = cw.byte(j);
+    touched |= byte;
+    kj[j] = f4_from(lut[meta.lut_prev[j] + byte]);
+    if (j > 0) o = f4_clamp(o, lo, hi);
+    o = f4_mul(o, kj[j]);
+  }
+  touched = (cfg.k_out == 1.0f) ? (touched & 0xFu) : 0xFu;
   float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     if (!((valid >> c) & 1u)) continue;
-    const float next = f4_get(on, c);
+    const float next = f4_get(o, c);
     const float hl = entropy_bits_odds(f4_get(oc, c));
     float hn = hl;
     if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl
-      hn = ((touched >> c) & 1u) ? entropy_bits_odds(fminf(fmaxf(next, cfg.o_min), cfg.o_max)) : hl;
+      hn = ((touched >> c) & 1u) ? entropy_bits_odds(fminf(fmaxf(next, lo), hi)) : hl;
     const float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
     a1 += w * (hl - hn);
     a2 += w * hl;
   }
   s1 += (double)a1;
   s2 += (double)a2;
-  return f4_to(on);
+  return f4_to(o);
 }
 
-// Local map of agent i: fuse the received peers' measurements (agent/agent.py:62-71), then the own
-// measurement at the new position (agent/agent.py:91-94) when DO_OWN (code byte `own_byte`).
+// ------------------------------------------------------------------------------------------------
+// LOCAL map of agent i, one quad (agent/agent.py:62-71,91-94; mapping/mappings.py:80-124,32-61): the enabled
+// fuse passes in id order — each clamps and multiplies (by exactly 1 outside footprint j) — then, inside the new
+// own footprint only, clamp and multiply.  Straight-line; `en` is warp-uniform.  Returns true when a result left
+// [o_min, o_max] (the reference clamps lazily, at the next update that reads the cell).
+// ------------------------------------------------------------------------------------------------
 template <int A, bool DO_OWN>
-__device__ __forceinline__ float4 update_local_quad(const ipp_config& cfg, const EnvMeta<A>& meta,
-                                                    const QuadCtx<A>& q, int i, const uint32_t own_byte,
-                                                    const float4* lut, const float4 o4) {
-  uint32_t own = 0;
-  F4 k_own = f4_splat(1.0f);
+__device__ __forceinline__ bool local_quad(const ipp_config& cfg, const uint32_t en, const F4 (&kj)[A],
+                                           const uint32_t own_byte, const uint32_t lut_next, const float4* lut,
+                                           float4& v) {
+  const float lo = cfg.o_min, hi = cfg.o_max;
+  F4 o = f4_from(v);
+#pragma unroll
+  for (int j = 0; j < A; ++j)
+    if ((en >> j) & 1u) o = f4_mul(f4_clamp(o, lo, hi), kj[j]);  // warp-uniform branch
   if (DO_OWN) {
-    own = own_byte & 0xFu;
-    k_own = f4_from(lut[meta.lut_next[i] + own_byte]);
+    const uint32_t own = own_byte & 0xFu;
+    if (own != 0u) o = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[lut_next + own_byte])), o);
   }
-  F4 oc;
-  uint32_t touched;
-  return f4_to(update_map_quad<A>(cfg, q, f4_from(o4), meta.comm[i], meta.comm4[i], own, k_own, oc, touched));
+  v = f4_to(o);
+  return f4_out_of_range(o, lo, hi);
+}
+
+// The same with the multipliers re-read from the LUT (L1-resident) instead of held in registers: the direct-load
+// kernel keeps its registers for loads in flight.
+template <int A, bool DO_OWN>
+__device__ __forceinline__ bool local_quad_lut(const ipp_config& cfg, const EnvMeta<A>& meta, const int i,
+                                               const CodeWord<A>& cw, const uint32_t own_byte, const float4* lut,
+                                               float4& v) {
+  const float lo = cfg.o_min, hi = cfg.o_max;
+  const uint32_t en = meta.comm[i];
+  F4 o = f4_from(v);
+#pragma unroll
+  for (int j = 0; j < A; ++j)
+    if ((en >> j) & 1u) o = f4_mul(f4_clamp(o, lo, hi), f4_from(lut[meta.lut_prev[j] + cw.byte(j)]));
+  if (DO_OWN) {
+    const uint32_t own = own_byte & 0xFu;
+    if (own != 0u) o = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[meta.lut_next[i] + own_byte])), o);
+  }
+  v = f4_to(o);
+  return f4_out_of_range(o, lo, hi);
 }
 
 __device__ __forceinline__ uint32_t valid_mask4(int32_t c0, int32_t n_cells) {

@@ -2,7 +2,7 @@
 //
 //   plan_kernel          per env: comm matrix, sequential masks / action choice / moves, and the
 //                        measurement codes of the footprints at the new positions (rect-sparse)
-//   step_dense_kernel    direct-load map kernel: fuse (local + global) + own update + reward sums
+//   step_direct_kernel   direct-load map kernel: fuse (local + global) + own update + reward sums
 //   reward_finalize      per-env reward from per-chunk partial sums (only when an env spans >1 chunk)
 //   own_update_kernel    own measurement update of the local maps (split observe/act mode)
 //   reset_prep / reset_fill   episode reset (MT19937-compatible start positions + ground truth)
@@ -269,55 +269,87 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
 }
 
 // =================================================================================================
-// map kernel, direct-load variant (per-quad arithmetic: ipp_cell.cuh)
-// one block per (env, chunk); each thread owns quads tid, tid+256, ... of the chunk in all A+1 maps
+// map kernel, direct-load variant (per-quad arithmetic: ipp_cell.cuh).
+// One 640-thread block per (env, segment of IPP_FLAG_QUADS quads), one quad per thread, everything in registers:
+// the loads that depend on nothing (code words, global quad) are issued first, then — once the env's comm bits
+// and range flags are known — the local quads that some footprint reaches; (quad, local map) pairs without
+// work are neither loaded nor stored, so this variant moves fewer HBM bytes than the dense contract figure.
 // =================================================================================================
+constexpr int DIRECT_THREADS = IPP_FLAG_QUADS;
+
 template <int A, bool DO_OWN>
-__global__ void __launch_bounds__(STEP_THREADS)
-    step_dense_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut,
-                      const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
-                      const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
-                      float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks,
-                      const int32_t quads_per_chunk) {
+__global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
+    step_direct_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut,
+                       const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
+                       const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
+                       float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks) {
   const int32_t b = blockIdx.x / n_chunks;
   const int32_t chunk = blockIdx.x - b * n_chunks;
   const int32_t tid = threadIdx.x;
   __shared__ EnvMeta<A> s_meta;
-  __shared__ double s_red[2][STEP_THREADS / 32];
-
-  load_env_meta<A>(cfg, &s_meta, tid, b, pos_in, pos_out, comm, DO_OWN);
-  // this variant keeps no range bookkeeping: mark every segment "may hold out-of-range odds" (always safe)
-  if (chunk == 0)
-    for (int32_t k = tid; k < A * cfg.n_seg; k += STEP_THREADS) st.map_flags[(int64_t)b * A * cfg.n_seg + k] = 1;
-  __syncthreads();
+  __shared__ uint32_t s_dirty[A], s_bad[A];
+  __shared__ double s_red[2][DIRECT_THREADS / 32];
 
   const int32_t n_cells = cfg.gx * cfg.gy;
   const int32_t n_quads = (n_cells + 3) >> 2;
   const int64_t stride = cfg.map_stride;
-  float* glob_b = st.global_map + (int64_t)b * stride;
-  float* loc_b = st.local_maps + (int64_t)b * A * stride;
-  const uint8_t* code_prev = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
-  const uint8_t* code_next = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const int32_t q = chunk * IPP_FLAG_QUADS + tid;
+  const bool have = q < n_quads;
+  const int64_t c0 = (int64_t)q << 2;
+  float* glob = st.global_map + (int64_t)b * stride + c0;
+  float* loc = st.local_maps + (int64_t)b * A * stride + c0;
 
-  double s1 = 0.0, s2 = 0.0;
-  const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
-  for (int32_t q = chunk * quads_per_chunk + tid; q < q_end; q += STEP_THREADS) {
-    const int32_t c0 = q << 2;
-    QuadCtx<A> qc;
-    make_quad_ctx<A>(cfg, s_meta, load_code<A>(code_prev, q), lut, qc);
-    CodeWord<A> next;
-    if (DO_OWN) next = load_code<A>(code_next, q);
-    *reinterpret_cast<float4*>(glob_b + c0) = update_global_quad<A>(
-        cfg, qc, *reinterpret_cast<const float4*>(glob_b + c0), valid_mask4(c0, n_cells), s1, s2);
+  // ---- loads that depend on nothing ----
+  CodeWord<A> cw, nw;
 #pragma unroll
-    for (int i = 0; i < A; ++i) {
-      float* lp = loc_b + (int64_t)i * stride + c0;
-      *reinterpret_cast<float4*>(lp) = update_local_quad<A, DO_OWN>(
-          cfg, s_meta, qc, i, DO_OWN ? next.byte(i) : 0u, lut, *reinterpret_cast<const float4*>(lp));
+  for (int w = 0; w < CodeWord<A>::WORDS; ++w) cw.w[w] = nw.w[w] = 0u;
+  float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+  if (have) {
+    cw = load_code<A>(st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, q);
+    if (DO_OWN) nw = load_code<A>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride, q);
+    g4 = __ldcs(reinterpret_cast<const float4*>(glob));
+  }
+  load_env_meta<A>(cfg, &s_meta, tid, b, pos_in, pos_out, comm, DO_OWN);
+  if (tid >= 2 * A && tid < 3 * A) {
+    s_dirty[tid - 2 * A] = st.map_flags[((int64_t)b * A + (tid - 2 * A)) * cfg.n_seg + chunk];
+    s_bad[tid - 2 * A] = 0u;
+  }
+  __syncthreads();
+
+  // ---- local quads with work: cells of an enabled fuse pass or of the own new footprint; every quad if the
+  //      map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1 ----
+  const bool kout_one = (cfg.k_out == 1.0f);
+  uint32_t in_prev = 0;
+#pragma unroll
+  for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
+  float4 l4[A];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    const uint32_t en = s_meta.comm[i];
+    const bool all = en != 0u && (s_dirty[i] != 0u || !kout_one);
+    if (have && (all || ((in_prev & s_meta.comm4[i]) | (nw.byte(i) & 0xFu)) != 0u)) {
+      mine |= 1u << i;
+      l4[i] = __ldcs(reinterpret_cast<const float4*>(loc + (int64_t)i * stride));
     }
   }
 
-  // ---- per-env reward: warp shuffle + shared-memory reduction of the two float64 sums ----
+  // ---- global map + reward terms ----
+  double s1 = 0.0, s2 = 0.0;
+  if (have) {
+    F4 kj[A];  // (unused here: the local maps re-read their multipliers)
+    g4 = global_quad<A>(cfg, s_meta, cw, lut, g4, valid_mask4((int32_t)c0, n_cells), kj, s1, s2);
+    __stcs(reinterpret_cast<float4*>(glob), g4);
+  }
+  // ---- local maps ----
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    if (!((mine >> i) & 1u)) continue;
+    if (local_quad_lut<A, DO_OWN>(cfg, s_meta, i, cw, nw.byte(i), lut, l4[i])) s_bad[i] = 1u;
+    __stcs(reinterpret_cast<float4*>(loc + (int64_t)i * stride), l4[i]);
+  }
+
+  // ---- per-env reward: warp shuffle + shared-memory reduction of the two float64 sums (fixed order) ----
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
   if ((tid & 31) == 0) {
@@ -328,7 +360,7 @@ __global__ void __launch_bounds__(STEP_THREADS)
   if (tid == 0) {
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int w = 0; w < STEP_THREADS / 32; ++w) {
+    for (int w = 0; w < DIRECT_THREADS / 32; ++w) {
       t1 += s_red[0][w];
       t2 += s_red[1][w];
     }
@@ -338,6 +370,11 @@ __global__ void __launch_bounds__(STEP_THREADS)
       partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
       partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
     }
+  } else if (tid >= 32 && tid < 32 + A) {
+    // new range flag: some result left the range, or nothing clamped an already flagged map
+    const int i = tid - 32;
+    const bool keep = s_meta.comm[i] == 0u && s_dirty[i] != 0u;
+    st.map_flags[((int64_t)b * A + i) * cfg.n_seg + chunk] = (uint8_t)((s_bad[i] != 0u || keep) ? 1 : 0);
   }
 }
 
@@ -603,19 +640,21 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
 cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
                               const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
                               float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
-  const dim3 grid((unsigned)plan.n_chunks * (unsigned)cfg.n_envs);
+  (void)plan;
+  const int32_t n_chunks = cfg.n_seg;  // one block per (env, flag segment)
+  const dim3 grid((unsigned)n_chunks * (unsigned)cfg.n_envs);
   if (do_own) {
-    IPP_DISPATCH_A(cfg.n_agents, (step_dense_kernel<kA, true><<<grid, STEP_THREADS, 0, s>>>(
+    IPP_DISPATCH_A(cfg.n_agents, (step_direct_kernel<kA, true><<<grid, DIRECT_THREADS, 0, s>>>(
                                      cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
-                                     plan.n_chunks, plan.quads_per_chunk)));
+                                     n_chunks)));
   } else {
-    IPP_DISPATCH_A(cfg.n_agents, (step_dense_kernel<kA, false><<<grid, STEP_THREADS, 0, s>>>(
+    IPP_DISPATCH_A(cfg.n_agents, (step_direct_kernel<kA, false><<<grid, DIRECT_THREADS, 0, s>>>(
                                      cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
-                                     plan.n_chunks, plan.quads_per_chunk)));
+                                     n_chunks)));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (plan.n_chunks > 1) e = launch_reward_finalize(cfg, partials, plan.n_chunks, reward_rel, reward_abs, s);
+  if (n_chunks > 1) e = launch_reward_finalize(cfg, partials, n_chunks, reward_rel, reward_abs, s);
   return e;
 }
 

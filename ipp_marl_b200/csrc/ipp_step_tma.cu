@@ -16,7 +16,7 @@
 //                     whose range flag is clear is known to lie inside [o_min, o_max], so the whole-map clamp of
 //                     the reference is a no-op on cells outside every footprint and a (tile, map) pair that no
 //                     footprint reaches is skipped by one warp vote, without touching shared memory;
-//                   (A = 8 needs more map slots than fit for dynamic scheduling: static tiles, pre-sparse code)
+//                   (A = 8 needs more map slots than fit for dynamic scheduling: tiles are assigned statically)
 //                   a warp waits map_full, updates the slot in place and arrives on map_done — it never waits
 //                   for other warps;
 //   storer warp   : waits map_done, writes the slot back with cp.async.bulk shared->global, frees the
@@ -40,70 +40,6 @@ struct StageMeta {
 
 static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work item)");
 
-// ------------------------------------------------------------------------------------------------
-// GLOBAL map, one quad: all A fuse passes (coma_wrapper.py:93-95) + the reward terms
-// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).  Straight-line: a pass is
-// clamp + multiply, the multipliers of all four cells come from one LUT load per agent (k_out outside
-// the footprint), so no footprint logic is needed at all.  kj[] keeps the multipliers for the local maps.
-// ------------------------------------------------------------------------------------------------
-template <int A>
-__device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
-                                              const float4* lut, const float4 o4, const uint32_t valid, F4 (&kj)[A],
-                                              double& s1, double& s2) {
-  const float lo = cfg.o_min, hi = cfg.o_max;
-  const F4 oc = f4_clamp(f4_from(o4), lo, hi);
-  F4 o = oc;
-  uint32_t touched = 0;
-#pragma unroll
-  for (int j = 0; j < A; ++j) {
-    const uint32_t byte = cw.byte(j);
-    touched |= byte;
-    kj[j] = f4_from(lut[meta.lut_prev[j] + byte]);
-    if (j > 0) o = f4_clamp(o, lo, hi);
-    o = f4_mul(o, kj[j]);
-  }
-  touched = (cfg.k_out == 1.0f) ? (touched & 0xFu) : 0xFu;
-  float a1 = 0.0f, a2 = 0.0f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (!((valid >> c) & 1u)) continue;
-    const float next = f4_get(o, c);
-    const float hl = entropy_bits_odds(f4_get(oc, c));
-    float hn = hl;
-    if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl
-      hn = ((touched >> c) & 1u) ? entropy_bits_odds(fminf(fmaxf(next, lo), hi)) : hl;
-    const float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
-    a1 += w * (hl - hn);
-    a2 += w * hl;
-  }
-  s1 += (double)a1;
-  s2 += (double)a2;
-  return f4_to(o);
-}
-
-// ------------------------------------------------------------------------------------------------
-// LOCAL map of agent i, one quad (agent/agent.py:62-71,91-94; mapping/mappings.py:80-124,32-61): the enabled
-// fuse passes in id order — each clamps and multiplies (by exactly 1 outside footprint j) — then, inside the new
-// own footprint only, clamp and multiply.  Straight-line; `en` is warp-uniform.  Returns true when a result left
-// [o_min, o_max] (the reference clamps lazily, at the next update that reads the cell).
-// ------------------------------------------------------------------------------------------------
-template <int A, bool DO_OWN>
-__device__ __forceinline__ bool local_quad(const ipp_config& cfg, const uint32_t en, const F4 (&kj)[A],
-                                           const uint32_t own_byte, const uint32_t lut_next, const float4* lut,
-                                           float4* mp) {
-  const float lo = cfg.o_min, hi = cfg.o_max;
-  F4 o = f4_from(*mp);
-#pragma unroll
-  for (int j = 0; j < A; ++j)
-    if ((en >> j) & 1u) o = f4_mul(f4_clamp(o, lo, hi), kj[j]);  // warp-uniform branch
-  if (DO_OWN) {
-    const uint32_t own = own_byte & 0xFu;
-    if (own != 0u) o = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[lut_next + own_byte])), o);
-  }
-  *mp = f4_to(o);
-  return f4_out_of_range(o, lo, hi);
-}
-
 constexpr int TMA_D_MAP = 16;     // map slots (power of two: slot / phase of a counter by shift & mask)
 constexpr int TMA_D_ENV = 4;      // env slots
 constexpr int TMA_STORE_LAG = 2;  // bulk-store groups allowed in flight before a map slot is recycled
@@ -126,8 +62,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   constexpr int QPC = TMA_QPC;
   constexpr int CONSUMER_THREADS = TMA_CONSUMER_WARPS * 32;
   // Dynamic scheduling needs 2 items' maps to fit the slot ring (see the producer's comment on phase parity);
-  // it also enables the footprint-sparse local-map tasks.  A = 8 runs static dense tiles.
-  constexpr bool kSparse = (2 * A <= 14);
+  // A = 8 assigns the tiles statically.
+  constexpr bool kDynamic = (2 * A <= 14);
   unsigned char* map_slots = smem;
   unsigned char* env_slots = map_slots + (size_t)TMA_D_MAP * slot_bytes;
   float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)TMA_D_ENV * env_bytes);
@@ -197,7 +133,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           dst = st.global_map + (int64_t)b * stride + cell0;
         } else {
           dst = st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
-          if (kSparse) {  // new range flag: some result left the range, or nothing clamped an already flagged map
+          {  // new range flag: some result left the range, or nothing clamped an already flagged map
             const bool keep = sm.env.comm[m - 1] == 0u && sm.dirty[m - 1] != 0u;
             st.map_flags[((int64_t)b * A + (m - 1)) * cfg.n_seg + chunk] = (uint8_t)((sm.bad[m - 1] != 0u || keep) ? 1 : 0);
           }
@@ -234,7 +170,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         meta[es].chunk = chunk;
         meta[es].nq = nq;
       }
-      if (kSparse && lane < A) {
+      if (lane < A) {
         meta[es].dirty[lane] = st.map_flags[((int64_t)b * A + lane) * cfg.n_seg + chunk];
         meta[es].bad[lane] = 0u;
       }
@@ -282,13 +218,20 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
                                 : 0u;
   const uint32_t warp = (uint32_t)tid >> 5;
 
-  if (kSparse) {
+  {
     const uint32_t total_tiles = my_items * NT;
     const bool kout_one = (cfg.k_out == 1.0f);
+    uint32_t n_static = warp;
     while (true) {
       uint32_t n = 0;
-      if (lane == 0) n = atomicAdd(tile_counter, 1u);
-      n = __shfl_sync(0xFFFFFFFFu, n, 0);
+      if (kDynamic) {
+        if (lane == 0) n = atomicAdd(tile_counter, 1u);
+        n = __shfl_sync(0xFFFFFFFFu, n, 0);
+      } else {  // warp w owns tile w of every item (warps >= NT idle): every barrier is waited in order
+        if (warp >= (uint32_t)NT) break;
+        n = n_static;
+        n_static += NT;
+      }
       if (n >= total_tiles) break;
       const uint32_t k = n / NT, tile = n - k * NT;
       const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
@@ -350,7 +293,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           bool bad = false;
           if (mine)
             bad = local_quad<A, DO_OWN>(cfg, en, kj, own_byte, sm.env.lut_next[i], lut,
-                                        reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql);
+                                        reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes)[ql]);
           if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) sm.bad[i] = 1u;
           ptx::fence_proxy_async();
         }
@@ -360,69 +303,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(env_done + 8u * es);
     }
-    return;
-  }
-
-  // ---- static dense tiles (A = 8): warp w owns tile w of every item (warps >= NT idle), all A + 1 maps;
-  //      every barrier is waited in order, so phase parity is never ambiguous ----
-  if (warp >= (uint32_t)NT) return;
-  const uint32_t total_tiles = my_items * NT;
-  for (uint32_t n = warp; n < total_tiles; n += NT) {
-    const uint32_t k = n / NT, tile = n - k * NT;
-    const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
-    ptx::mbar_wait(env_full + 8u * es, pe);
-    const StageMeta<A>& sm = meta[es];
-    const int32_t ql = (int32_t)tile * 32 + lane;
-    const bool have = ql < sm.nq;
-    const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
-    const unsigned char* code_next = code_prev + code_row;
-    QuadCtx<A> qc;
-    CodeWord<A> next;
-    uint32_t valid = 0;
-    if (have) {
-      make_quad_ctx<A>(cfg, sm.env, load_code<A>(code_prev, ql), lut, qc);
-      if (DO_OWN) next = load_code<A>(code_next, ql);
-      valid = valid_mask4((sm.chunk * QPC + ql) << 2, n_cells);
-    }
-    if (tile == 0 && lane < A)  // no range bookkeeping on this path: flags stay "unknown" (always safe)
-      st.map_flags[((int64_t)sm.b * A + lane) * cfg.n_seg + sm.chunk] = 1;
-    uint32_t g = k * (A + 1);
-    // ---- global map ----
-    {
-      const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-      ptx::mbar_wait(map_full + 8u * ms, pm);
-      double s1 = 0.0, s2 = 0.0;
-      if (have) {
-        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
-        *mp = update_global_quad<A>(cfg, qc, *mp, valid, s1, s2);
-      }
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      if (lane == 0) {
-        double* r = red + (size_t)es * 2 * NT;
-        r[tile] = s1;
-        r[NT + tile] = s2;
-      }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
-      ++g;
-    }
-    // ---- local maps ----
-#pragma unroll
-    for (int i = 0; i < A; ++i, ++g) {
-      const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-      ptx::mbar_wait(map_full + 8u * ms, pm);
-      if (have) {
-        float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
-        *mp = update_local_quad<A, DO_OWN>(cfg, sm.env, qc, i, DO_OWN ? next.byte(i) : 0u, lut, *mp);
-      }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
-    }
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(env_done + 8u * es);
   }
 }
 

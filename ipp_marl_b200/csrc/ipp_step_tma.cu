@@ -17,13 +17,14 @@
 //                     the reference is a no-op on cells outside every footprint and a (tile, map) pair that no
 //                     footprint reaches is skipped by one warp vote, without touching shared memory;
 //                   (A = 8 needs more map slots than fit for dynamic scheduling: tiles are assigned statically)
-//                   a warp waits map_full, updates the slot in place and arrives on map_done — it never waits
-//                   for other warps;
-//   storer warp   : waits map_done, writes the slot back with cp.async.bulk shared->global, frees the
-//                   slot (map_empty) once the bulk engine has read it, finishes the per-env reward from the
-//                   tiles' partial sums and writes the local maps' new range flags.
-// HBM traffic is one read + one write of every belief map plus the code rows; all global addressing
-// is done by the TMA unit, so the SM issue slots go to the map arithmetic.
+//                   a warp waits map_full, reads the slot and arrives on map_done — it never waits for other warps;
+//                   results go from registers straight to global memory with coalesced streaming 16-byte stores
+//                   (512 contiguous bytes per warp); a slot is only ever READ by the SM, so it is free again as
+//                   soon as its last tile has been read — shared memory holds data that is loading or waiting
+//                   for a warp, never data that is draining to HBM;
+//   finisher warp : (one lane) waits map_done, finishes the per-env reward from the tiles' partial sums and
+//                   writes the local maps' new range flags.
+// HBM traffic is one read of every belief map and of the code rows plus the write of the quads that changed.
 #include "ipp_cell.cuh"
 #include "ipp_launch.h"
 #include "ipp_ptx.cuh"
@@ -42,12 +43,11 @@ static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work it
 
 constexpr int TMA_D_MAP = 16;     // map slots (power of two: slot / phase of a counter by shift & mask)
 constexpr int TMA_D_ENV = 4;      // env slots
-constexpr int TMA_STORE_LAG = 2;  // bulk-store groups allowed in flight before a map slot is recycled
 constexpr int TMA_NT = TMA_QPC / 32;  // tiles per item
 
 // Shared-memory layout:
 //   [D_MAP][slot_bytes] map slots | [D_ENV][env_bytes] code rows | lut[n_alt*256] float4 | StageMeta[D_ENV] |
-//   mbarriers: map_full[D_MAP] map_done[D_MAP] map_empty[D_MAP] env_full[D_ENV] env_done[D_ENV] |
+//   mbarriers: map_full[D_MAP] map_done[D_MAP] env_full[D_ENV] env_tiles[D_ENV] env_done[D_ENV] |
 //   reward partials [D_ENV][2][NT] double | tile counter
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
@@ -69,14 +69,14 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)TMA_D_ENV * env_bytes);
   StageMeta<A>* meta = reinterpret_cast<StageMeta<A>*>(lut + cfg.n_alt * 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta + TMA_D_ENV);
-  double* red = reinterpret_cast<double*>(bars + 3 * TMA_D_MAP + 2 * TMA_D_ENV);  // [D_ENV][2][NT]
+  double* red = reinterpret_cast<double*>(bars + 2 * TMA_D_MAP + 3 * TMA_D_ENV);  // [D_ENV][2][NT]
   uint32_t* tile_counter = reinterpret_cast<uint32_t*>(red + TMA_D_ENV * 2 * NT);
   // 32-bit shared addresses of the barrier arrays (8 bytes per barrier)
   const uint32_t map_full = ptx::smem_u32(bars);
   const uint32_t map_done = map_full + 8u * TMA_D_MAP;
-  const uint32_t map_empty = map_done + 8u * TMA_D_MAP;
-  const uint32_t env_full = map_empty + 8u * TMA_D_MAP;
-  const uint32_t env_done = env_full + 8u * TMA_D_ENV;
+  const uint32_t env_full = map_done + 8u * TMA_D_MAP;
+  const uint32_t env_tiles = env_full + 8u * TMA_D_ENV;
+  const uint32_t env_done = env_tiles + 8u * TMA_D_ENV;
 
   const int32_t tid = threadIdx.x;
   const int32_t n_cells = cfg.gx * cfg.gy;
@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
     for (int s = 0; s < TMA_D_MAP; ++s) {
       ptx::mbar_init(map_full + 8u * s, 1);    // producer's arrive.expect_tx
       ptx::mbar_init(map_done + 8u * s, NT);   // one arrival per tile
-      ptx::mbar_init(map_empty + 8u * s, 1);   // storer
     }
     for (int s = 0; s < TMA_D_ENV; ++s) {
       ptx::mbar_init(env_full + 8u * s, 1);       // producer
-      ptx::mbar_init(env_done + 8u * s, NT + 1);  // tiles + storer
+      ptx::mbar_init(env_tiles + 8u * s, NT);     // one arrival per finished tile task
+      ptx::mbar_init(env_done + 8u * s, 1);       // finisher
     }
     *tile_counter = 0u;
     ptx::fence_mbar_init();
@@ -101,56 +101,40 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   __syncthreads();
 
   if (tid >= CONSUMER_THREADS + 32) {
-    // ================================================================== storer warp (one lane)
+    // ================================================================== finisher warp (one lane)
+    // Waits on the ENV-level barrier only: an env slot is recycled after this lane's own arrival, so its phase
+    // parity can never run two phases ahead of the wait (a map slot's barrier could — slots are recycled as soon
+    // as their tiles have been read).
     if (tid != CONSUMER_THREADS + 32) return;
-    uint32_t k = 0, g = 0, n_freed = 0;  // items done, bulk-store groups committed, map slots handed back
+    uint32_t k = 0;
     for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
       const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
-      ptx::mbar_wait(env_full + 8u * es, pe);
+      ptx::mbar_wait(env_tiles + 8u * es, pe);  // every tile task of the item has finished all A + 1 maps
       const StageMeta<A>& sm = meta[es];
       const int32_t b = sm.b, chunk = sm.chunk;
-      const uint32_t map_bytes = (uint32_t)sm.nq * 16u;
-      const int64_t cell0 = (int64_t)chunk * QPC * 4;
-#pragma unroll 1
-      for (int m = 0; m <= A; ++m) {
-        const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-        ptx::mbar_wait(map_done + 8u * ms, pm);
-        float* dst;
-        if (m == 0) {
-          const double* r = red + (size_t)es * 2 * NT;
-          double t1 = 0.0, t2 = 0.0;
+      {
+        const double* r = red + (size_t)es * 2 * NT;
+        double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-          for (int w = 0; w < NT; ++w) {
-            t1 += r[w];
-            t2 += r[NT + w];
-          }
-          if (n_chunks == 1) {
-            write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
-          } else {
-            partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
-            partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
-          }
-          dst = st.global_map + (int64_t)b * stride + cell0;
+        for (int w = 0; w < NT; ++w) {
+          t1 += r[w];
+          t2 += r[NT + w];
+        }
+        if (n_chunks == 1) {
+          write_rewards(reward_rel, reward_abs, b, t1, t2, n_cells);
         } else {
-          dst = st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
-          {  // new range flag: some result left the range, or nothing clamped an already flagged map
-            const bool keep = sm.env.comm[m - 1] == 0u && sm.dirty[m - 1] != 0u;
-            st.map_flags[((int64_t)b * A + (m - 1)) * cfg.n_seg + chunk] = (uint8_t)((sm.bad[m - 1] != 0u || keep) ? 1 : 0);
-          }
+          partials[((int64_t)b * n_chunks + chunk) * 2 + 0] = t1;
+          partials[((int64_t)b * n_chunks + chunk) * 2 + 1] = t2;
         }
-        ptx::bulk_store(dst, ptx::smem_u32(map_slots + (size_t)ms * slot_bytes), map_bytes);
-        ptx::bulk_commit();
-        ++g;
-        ptx::bulk_wait_read<TMA_STORE_LAG>();  // all but the newest LAG groups have been read out of smem
-        while (n_freed + TMA_STORE_LAG < g) {
-          ptx::mbar_arrive(map_empty + 8u * (n_freed & (TMA_D_MAP - 1)));
-          ++n_freed;
-        }
+      }
+#pragma unroll 1
+      for (int i = 0; i < A; ++i) {
+        // new range flag: some result left the range, or nothing clamped an already flagged map
+        const bool keep = sm.env.comm[i] == 0u && sm.dirty[i] != 0u;
+        st.map_flags[((int64_t)b * A + i) * cfg.n_seg + chunk] = (uint8_t)((sm.bad[i] != 0u || keep) ? 1 : 0);
       }
       ptx::mbar_arrive(env_done + 8u * es);
     }
-    ptx::bulk_wait_read<0>();
-    ptx::bulk_wait<0>();  // all writes to global memory complete before the CTA retires
     return;
   }
 
@@ -200,7 +184,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
 #pragma unroll 1
         for (int m = 0; m <= A; ++m, ++g) {
           const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-          ptx::mbar_wait(map_empty + 8u * ms, pm ^ 1u);
+          ptx::mbar_wait(map_done + 8u * ms, pm ^ 1u);  // every tile of the slot's previous map has been read
           const float* src = (m == 0) ? st.global_map + (int64_t)b * stride + cell0
                                       : st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
           ptx::mbar_arrive_expect_tx(map_full + 8u * ms, map_bytes);
@@ -239,6 +223,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
       StageMeta<A>& sm = meta[es];
       const int32_t ql = (int32_t)tile * 32 + lane;
       const bool have = ql < sm.nq;
+      const int32_t cell_q = sm.chunk * QPC + ql;  // quad index inside the whole map
       const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
       const unsigned char* code_next = code_prev + code_row;
       CodeWord<A> cw, nw;
@@ -256,8 +241,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         ptx::mbar_wait(map_full + 8u * ms, pm);
         double s1 = 0.0, s2 = 0.0;
         if (have) {
-          float4* mp = reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes) + ql;
-          *mp = global_quad<A>(cfg, sm.env, cw, lut, *mp, valid_mask4((sm.chunk * QPC + ql) << 2, n_cells), kj, s1, s2);
+          const float4 o4 = reinterpret_cast<const float4*>(map_slots + (size_t)ms * slot_bytes)[ql];
+          __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
+                 global_quad<A>(cfg, sm.env, cw, lut, o4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
         } else {
 #pragma unroll
           for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
@@ -269,7 +255,6 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
           r[tile] = s1;
           r[NT + tile] = s2;
         }
-        ptx::fence_proxy_async();  // my shared-memory writes -> visible to the bulk-copy (async) proxy
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
         ++g;
@@ -291,17 +276,18 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
         ptx::mbar_wait(map_full + 8u * ms, pm);  // (also when skipping: the storer must not run ahead of the load)
         if (any) {
           bool bad = false;
-          if (mine)
-            bad = local_quad<A, DO_OWN>(cfg, en, kj, own_byte, sm.env.lut_next[i], lut,
-                                        reinterpret_cast<float4*>(map_slots + (size_t)ms * slot_bytes)[ql]);
+          if (mine) {
+            float4 v = reinterpret_cast<const float4*>(map_slots + (size_t)ms * slot_bytes)[ql];
+            bad = local_quad<A, DO_OWN>(cfg, en, kj, own_byte, sm.env.lut_next[i], lut, v);
+            __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, v);
+          }
           if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) sm.bad[i] = 1u;
-          ptx::fence_proxy_async();
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(env_done + 8u * es);
+      if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);
     }
   }
 }
@@ -332,10 +318,10 @@ TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
   p.d_env = TMA_D_ENV;
   p.d_map = TMA_D_MAP;
   p.smem_bytes = TMA_D_MAP * p.slot_bytes + TMA_D_ENV * p.env_bytes + cfg.n_alt * 256 * 16 +
-                 TMA_D_ENV * (int)stage_meta_bytes(A) + (3 * TMA_D_MAP + 2 * TMA_D_ENV) * 8 +
+                 TMA_D_ENV * (int)stage_meta_bytes(A) + (2 * TMA_D_MAP + 3 * TMA_D_ENV) * 8 +
                  TMA_D_ENV * 2 * TMA_NT * 8 + 16 + 128;
-  // one whole item + the store lag + at least one slot of prefetch must fit in the map ring
-  p.ok = TMA_D_MAP >= (A + 1) + TMA_STORE_LAG + 1 && p.smem_bytes <= max_smem_optin;
+  // one whole item + at least one slot of prefetch must fit in the map ring
+  p.ok = TMA_D_MAP >= (A + 1) + 1 && p.smem_bytes <= max_smem_optin;
   return p;
 }
 

@@ -50,7 +50,7 @@ constexpr int TMA_NT = TMA_QPC / 32;  // tiles per item
 //   mbarriers: map_full[D_MAP] map_done[D_MAP] env_full[D_ENV] env_tiles[D_ENV] env_done[D_ENV] |
 //   reward partials [D_ENV][2][NT] double | tile counter
 template <int A, bool DO_OWN>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+__global__ void __launch_bounds__(tma_threads(A), 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
                     const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
                     const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1)
   constexpr int NT = TMA_NT;
   constexpr int AP = A <= 4 ? 4 : 8;
   constexpr int QPC = TMA_QPC;
-  constexpr int CONSUMER_THREADS = TMA_CONSUMER_WARPS * 32;
+  constexpr int CONSUMER_THREADS = tma_consumer_warps(A) * 32;
+  constexpr int TMA_THREADS = tma_threads(A);
   // Dynamic scheduling needs 2 items' maps to fit the slot ring (see the producer's comment on phase parity);
   // A = 8 assigns the tiles statically.
   constexpr bool kDynamic = (2 * A <= 14);
@@ -338,7 +339,7 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
   }
   const int n_items = cfg.n_envs * plan.n_chunks;
   const int grid = n_items < n_sm ? n_items : n_sm;
-  kern<<<grid, TMA_THREADS, plan.smem_bytes, s>>>(cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs,
+  kern<<<grid, tma_threads(A), plan.smem_bytes, s>>>(cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs,
                                                    partials, plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes);
   return cudaGetLastError();
 }

@@ -9,11 +9,9 @@ namespace ipp {
 
 constexpr int STEP_THREADS = 256;   // direct-load variant: threads per (env, chunk) block
 constexpr int TMA_QPC = 640;             // TMA variant: quads per work item (20 tiles of 32 quads, 10 KB per map)
-// consumer warps pulling (item, tile) tasks: the map arithmetic is a chain of dependent clamp / multiply / MUFU
-// steps per quad, so it is warps in flight (not issue slots) that bound it — as many as the register file allows
-// (48 registers per thread at 1280 threads; the A > 4 instantiations need more registers per thread)
-__host__ __device__ constexpr int tma_consumer_warps(int n_agents) { return n_agents <= 4 ? 38 : 26; }
-__host__ __device__ constexpr int tma_threads(int n_agents) { return (tma_consumer_warps(n_agents) + 2) * 32; }  // + producer + finisher
+// consumer warps pulling (item, tile) tasks (+ 1 producer warp + 1 finisher warp; a block has at most 1024 threads)
+__host__ __device__ constexpr int tma_consumer_warps(int n_agents) { return n_agents <= 4 ? 26 : 26; }
+__host__ __device__ constexpr int tma_threads(int n_agents) { return (tma_consumer_warps(n_agents) + 2) * 32; }
 
 struct LaunchPlan {
   int32_t n_chunks;         // chunks per env map (1 => per-env reward finishes inside the block)

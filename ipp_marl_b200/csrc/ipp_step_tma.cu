@@ -234,58 +234,79 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
         cw = load_code<A>(code_prev, ql);
         if (DO_OWN) nw = load_code<A>(code_next, ql);
       }
-      F4 kj[A];
-      uint32_t g = k * (A + 1);
-      // ---- global map ----
-      {
-        const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-        ptx::mbar_wait(map_full + 8u * ms, pm);
-        double s1 = 0.0, s2 = 0.0;
-        if (have) {
-          const float4 o4 = reinterpret_cast<const float4*>(map_slots + (size_t)ms * slot_bytes)[ql];
-          __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
-                 global_quad<A>(cfg, sm.env, cw, lut, o4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
-        } else {
-#pragma unroll
-          for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
-        }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-          double* r = red + (size_t)es * 2 * NT;
-          r[tile] = s1;
-          r[NT + tile] = s2;
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
-        ++g;
-      }
-      // ---- local maps ----
+      // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint; every
+      // quad if the map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
       uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
 #pragma unroll
       for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
+      uint32_t mine = 0, any = 0;
 #pragma unroll
-      for (int i = 0; i < A; ++i, ++g) {
-        const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-        const uint32_t en = sm.env.comm[i];
-        const uint32_t own_byte = DO_OWN ? nw.byte(i) : 0u;
-        // does this quad have work?  cells of an enabled fuse pass or of the own footprint; everything if the
-        // map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
-        const bool all = en != 0u && (sm.dirty[i] != 0u || !kout_one);
-        const bool mine = have && (all || ((in_prev & sm.env.comm4[i]) | (own_byte & 0xFu)) != 0u);
-        const bool any = __any_sync(0xFFFFFFFFu, mine);
-        ptx::mbar_wait(map_full + 8u * ms, pm);  // (also when skipping: the storer must not run ahead of the load)
-        if (any) {
-          bool bad = false;
-          if (mine) {
-            float4 v = reinterpret_cast<const float4*>(map_slots + (size_t)ms * slot_bytes)[ql];
-            bad = local_quad<A, DO_OWN>(cfg, en, kj, own_byte, sm.env.lut_next[i], lut, v);
-            __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, v);
+      for (int i = 0; i < A; ++i) {
+        const bool all = sm.env.comm[i] != 0u && (sm.dirty[i] != 0u || !kout_one);
+        const bool m_i = have && (all || ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u);
+        mine |= (m_i ? 1u : 0u) << i;
+        any |= (__any_sync(0xFFFFFFFFu, m_i) ? 1u : 0u) << i;
+      }
+      // all A + 1 maps of the item must have landed (they were requested together); then every load, every
+      // clamp / multiply chain and every store of the tile is independent work the scheduler can overlap
+      const uint32_t g0 = k * (A + 1);
+#pragma unroll
+      for (int m = 0; m <= A; ++m) {
+        const uint32_t g = g0 + m;
+        ptx::mbar_wait(map_full + 8u * (g & (TMA_D_MAP - 1)), (g / TMA_D_MAP) & 1u);
+      }
+      float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+      float4 l4[A];
+      if (have) g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+      constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
+      if (kWide) {
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+          if ((mine >> i) & 1u)
+            l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+      }
+      // ---- global map + reward terms ----
+      F4 kj[A];
+      double s1 = 0.0, s2 = 0.0;
+      if (have) {
+        __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
+               global_quad<A>(cfg, sm.env, cw, lut, g4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
+      } else {
+#pragma unroll
+        for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
+      }
+      // ---- local maps ----
+      uint32_t bad = 0;
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
+        if ((mine >> i) & 1u) {
+          bool b_i;
+          if (kWide) {
+            b_i = local_quad<A, DO_OWN>(cfg, sm.env.comm[i], kj, DO_OWN ? nw.byte(i) : 0u, sm.env.lut_next[i], lut, l4[i]);
+          } else {  // A > 4: one map at a time, multipliers re-read from the LUT
+            l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+            b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
           }
-          if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) sm.bad[i] = 1u;
+          if (b_i) bad |= 1u << i;
+          __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, l4[i]);
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(map_done + 8u * ms);
+      }
+      bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        double* r = red + (size_t)es * 2 * NT;
+        r[tile] = s1;
+        r[NT + tile] = s2;
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+          if ((bad >> i) & 1u) sm.bad[i] = 1u;
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m <= A; ++m) ptx::mbar_arrive(map_done + 8u * ((g0 + m) & (TMA_D_MAP - 1)));
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);

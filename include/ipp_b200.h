@@ -92,7 +92,8 @@ typedef struct ipp_state {
                        /* (4-cell quad, agent): low nibble = cell inside the agent's latest footprint,   */
                        /* high nibble = cell measured as occupied.  Half (t & 1) holds the measurements  */
                        /* communicated at step t, the other half receives those taken after the moves.   */
-  uint8_t* map_flags;  /* [n_envs, n_agents, n_seg] bookkeeping of the reference's lazily applied clamp          */
+  uint8_t* map_flags;  /* [n_envs, n_seg, 16] (byte i of a 16-byte record = local map i; 16-byte aligned)       */
+                       /* bookkeeping of the reference's lazily applied clamp                                   */
                        /* (mapping/mappings.py:110-111 clamps a map only when the next update reads it): != 0    */
                        /* means "this segment of the local map may hold odds outside [o_min, o_max]", so the    */
                        /* next fuse pass must clamp all of it; 0 lets the kernels touch only footprint cells.  */

@@ -17,6 +17,7 @@ struct ipp_handle {
   double* partials;     // [n_envs, n_chunks, 2]
   int32_t* gt_params;   // [n_envs, 4]
   uint8_t* comm;        // [n_envs, n_agents] when the caller does not ask for comm_out
+  uint32_t* step_meta;  // [n_envs, 4 * n_agents] per-env record handed from the plan kernel to the map kernels
   float4* lut;          // [n_alt, 256] odds multipliers of a quad for every measurement code byte
   ipp::PoolTables pool; // cv2.INTER_AREA tap tables of the feature builders
   // facade scratch (grown on demand)
@@ -41,17 +42,16 @@ int fail_cuda(ipp_handle* h, cudaError_t e, const char* where) {
 
 cudaError_t launch_maps(ipp_handle* h, const ipp_state* st, const ipp_step_io& io, int32_t t, bool do_own,
                         cudaStream_t s) {
-  const int32_t* pos_out = do_own ? io.pos_out : io.pos_in;
   if (h->variant == IPP_VARIANT_TMA) {
-    cudaError_t e = ipp::launch_step_tma(h->cfg, *st, h->lut, h->tma, h->n_sm, io.pos_in, pos_out, io.comm_out, t,
-                                         io.reward_rel, io.reward_abs, h->partials, do_own, s);
+    cudaError_t e = ipp::launch_step_tma(h->cfg, *st, h->lut, h->tma, h->n_sm, h->step_meta, t, io.reward_rel,
+                                         io.reward_abs, h->partials, do_own, s);
     if (e != cudaSuccess) return e;
     if (h->tma.n_chunks > 1)
       e = ipp::launch_reward_finalize(h->cfg, h->partials, h->tma.n_chunks, io.reward_rel, io.reward_abs, s);
     return e;
   }
-  return ipp::launch_step_dense(h->cfg, *st, h->lut, h->plan, io.pos_in, pos_out, io.comm_out, t, io.reward_rel,
-                                io.reward_abs, h->partials, do_own, s);
+  return ipp::launch_step_dense(h->cfg, *st, h->lut, h->step_meta, t, io.reward_rel, io.reward_abs, h->partials,
+                                do_own, s);
 }
 
 int validate(const ipp_config* c) {
@@ -87,7 +87,8 @@ int check_state(const ipp_state* st) {
       st->episodes == nullptr || st->meas_codes == nullptr || st->map_flags == nullptr)
     return IPP_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(st->local_maps) & 15) || (reinterpret_cast<uintptr_t>(st->global_map) & 15) ||
-      (reinterpret_cast<uintptr_t>(st->ground_truth) & 15) || (reinterpret_cast<uintptr_t>(st->meas_codes) & 15))
+      (reinterpret_cast<uintptr_t>(st->ground_truth) & 15) || (reinterpret_cast<uintptr_t>(st->meas_codes) & 15) ||
+      (reinterpret_cast<uintptr_t>(st->map_flags) & 15))
     return IPP_ERR_INVALID_ARG;
   return IPP_OK;
 }
@@ -153,8 +154,9 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
   const size_t pb = sizeof(double) * 2 * (size_t)cfg->n_envs * max_chunks;
   const size_t gb = sizeof(int32_t) * 4 * (size_t)cfg->n_envs;
   const size_t cb = (size_t)cfg->n_envs * cfg->n_agents;
+  const size_t mb = sizeof(uint32_t) * 4 * (size_t)cfg->n_envs * cfg->n_agents;
   if (cudaMalloc(&h->partials, pb) != cudaSuccess || cudaMalloc(&h->gt_params, gb) != cudaSuccess ||
-      cudaMalloc(&h->comm, cb) != cudaSuccess) {
+      cudaMalloc(&h->comm, cb) != cudaSuccess || cudaMalloc(&h->step_meta, mb) != cudaSuccess) {
     ipp_destroy(h);
     return IPP_ERR_ALLOC;
   }
@@ -185,7 +187,7 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
     ipp_destroy(h);
     return IPP_ERR_ALLOC;
   }
-  h->scratch_bytes = (int64_t)(pb + gb + cb + lb);
+  h->scratch_bytes = (int64_t)(pb + gb + cb + lb + mb);
   *out = h;
   return IPP_OK;
 }
@@ -195,6 +197,7 @@ int ipp_destroy(ipp_handle* h) {
   if (h->partials) cudaFree(h->partials);
   if (h->gt_params) cudaFree(h->gt_params);
   if (h->comm) cudaFree(h->comm);
+  if (h->step_meta) cudaFree(h->step_meta);
   if (h->lut) cudaFree(h->lut);
   ipp::free_pool_tables(&h->pool);
   if (h->fbuf) cudaFree(h->fbuf);
@@ -238,7 +241,7 @@ int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_ste
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 1, s));
+  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 1, h->step_meta, s));
   if (phases & IPP_PHASE_MAPS) IPP_CUDA(h, launch_maps(h, st, io2, t, true, s));
   return IPP_OK;
 }
@@ -255,7 +258,7 @@ int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 0, s));
+  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 0, h->step_meta, s));
   IPP_CUDA(h, launch_maps(h, st, io2, t, false, s));
   return IPP_OK;
 }
@@ -267,7 +270,7 @@ int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io
   if (rc != IPP_OK) return rc;
   if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, *io, t, 0, 1, s));
+  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, *io, t, 0, 1, h->step_meta, s));
   IPP_CUDA(h, ipp::launch_own_update(h->cfg, *st, h->lut, io->pos_out, t, s));
   return IPP_OK;
 }

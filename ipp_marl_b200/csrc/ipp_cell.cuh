@@ -21,7 +21,7 @@
 
 namespace ipp {
 
-// Per-env facts the per-quad code needs (shared memory).
+// Per-env facts the per-quad code needs (shared memory; filled from the record written by plan_moves).
 template <int A>
 struct EnvMeta {
   uint32_t comm[A];      // bit j: agent i fuses agent j's measurement (own bit cleared)
@@ -35,22 +35,20 @@ __device__ __forceinline__ uint32_t lut_row(const ipp_config& c, const int32_t* 
   return (uint32_t)iz * 256u;
 }
 
-template <int A>
-__device__ __forceinline__ void load_env_meta(const ipp_config& cfg, EnvMeta<A>* m, int lane_or_tid, int32_t b,
-                                              const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm,
-                                              bool do_own) {
-  if (lane_or_tid < A) {
-    const int a = lane_or_tid;
-    m->lut_prev[a] = lut_row(cfg, pos_in + ((int64_t)b * A + a) * 3);
-    const uint32_t en = (uint32_t)comm[(int64_t)b * A + a] & ~(1u << a);  // own measurement already used
+// One env's record (4 * n_agents words, in the field order of EnvMeta): written by plan_moves once per step, read by
+// the map kernels as a plain 16A-byte copy.
+__device__ __forceinline__ void write_env_meta(const ipp_config& cfg, uint32_t* rec, const uint32_t* comm_rows,
+                                               const int32_t (*pos)[3], const int32_t (*npos)[3], bool have_next) {
+  const int A = cfg.n_agents;
+  for (int a = 0; a < A; ++a) {
+    const uint32_t en = comm_rows[a] & ~(1u << a);  // own measurement already used
     uint32_t en4 = 0;
     for (int j = 0; j < A; ++j)
       if ((en >> j) & 1u) en4 |= 0xFu << (4 * j);
-    m->comm[a] = en;
-    m->comm4[a] = en4;
-  } else if (lane_or_tid < 2 * A) {
-    const int a = lane_or_tid - A;
-    m->lut_next[a] = do_own ? lut_row(cfg, pos_out + ((int64_t)b * A + a) * 3) : 0u;
+    rec[a] = en;
+    rec[A + a] = en4;
+    rec[2 * A + a] = lut_row(cfg, pos[a]);
+    rec[3 * A + a] = have_next ? lut_row(cfg, npos[a]) : 0u;
   }
 }
 

@@ -43,7 +43,8 @@ __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
 // Sequential masks / action choice / moves of one env (one thread; agents act in id order and agent i
 // sees the NEW positions of agents < i: agent/agent.py:73-104, coma_wrapper.py:97-104).
 __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_t ep, const ipp_step_io& io,
-                           const int32_t t, const bool do_comm, const bool do_move, int32_t (*npos)[3]) {
+                           const int32_t t, const bool do_comm, const bool do_move, int32_t (*npos)[3],
+                           uint32_t* __restrict__ step_meta) {
   const int32_t A = cfg.n_agents;
   int32_t pos[IPP_MAX_AGENTS][3];
   int32_t ix[IPP_MAX_AGENTS], iy[IPP_MAX_AGENTS], nix[IPP_MAX_AGENTS], niy[IPP_MAX_AGENTS];  // lattice indices
@@ -52,6 +53,8 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
     ix[a] = pos[a][0] / cfg.spacing;
     iy[a] = pos[a][1] / cfg.spacing;
   }
+  uint32_t comm_rows[IPP_MAX_AGENTS];
+  for (int32_t a = 0; a < A; ++a) comm_rows[a] = 0u;
   if (do_comm && io.comm_out != nullptr) {
     // comm matrix: agent/communication_log.py:39-58 (one uniform draw per ordered pair, used or not, :46)
     for (int32_t i = 0; i < A; ++i) {
@@ -65,9 +68,13 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
         row |= (ok ? 1u : 0u) << j;
       }
       io.comm_out[(int64_t)b * A + i] = (uint8_t)row;
+      comm_rows[i] = row;
     }
   }
-  if (!do_move) return;
+  if (!do_move) {  // ipp_observe: the map kernel fuses only
+    if (do_comm) write_env_meta(cfg, step_meta + (int64_t)b * 4 * A, comm_rows, pos, pos, false);
+    return;
+  }
   uint32_t stuck = 0;
   for (int32_t a = 0; a < A; ++a) {
     const uint32_t bounds = bounds_mask(cfg, pos[a]);
@@ -138,6 +145,7 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
     if (io.mask_out != nullptr) io.mask_out[(int64_t)b * A + a] = (uint8_t)m;
   }
   if (io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)stuck;
+  if (do_comm) write_env_meta(cfg, step_meta + (int64_t)b * 4 * A, comm_rows, pos, npos, true);
 }
 
 // Write the code byte of quad q (cells 4q..4q+3, first cell in grid row x) for measurement m.
@@ -210,7 +218,7 @@ constexpr int PLAN_ENVS = 16;   // envs per block
 // (7.4 M per launch at 8192 envs — that, not the arithmetic, bounded earlier versions of this kernel).
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
-                const int32_t do_comm, const int32_t do_move, const int32_t stage) {
+                const int32_t do_comm, const int32_t do_move, const int32_t stage, uint32_t* __restrict__ step_meta) {
   extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride + code_stride] when stage
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t e0 = blockIdx.x * PLAN_ENVS;
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
           io.pos_out[((int64_t)(e0 + lane) * A + a) * 3 + d] = s_npos[lane][a][d];
         }
     } else {
-      plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane]);
+      plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane], step_meta);
     }
   }
   if (!do_move) return;
@@ -280,8 +288,7 @@ constexpr int DIRECT_THREADS = IPP_FLAG_QUADS;
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
     step_direct_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut,
-                       const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
-                       const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
+                       const uint32_t* __restrict__ step_meta, const int32_t t, float* __restrict__ reward_rel,
                        float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks) {
   const int32_t b = blockIdx.x / n_chunks;
   const int32_t chunk = blockIdx.x - b * n_chunks;
@@ -309,10 +316,11 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
     if (DO_OWN) nw = load_code<A>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride, q);
     g4 = __ldcs(reinterpret_cast<const float4*>(glob));
   }
-  load_env_meta<A>(cfg, &s_meta, tid, b, pos_in, pos_out, comm, DO_OWN);
-  if (tid >= 2 * A && tid < 3 * A) {
-    s_dirty[tid - 2 * A] = st.map_flags[((int64_t)b * A + (tid - 2 * A)) * cfg.n_seg + chunk];
-    s_bad[tid - 2 * A] = 0u;
+  if (tid < 4 * A) {  // the env's record from the plan kernel (comm bits, LUT rows)
+    reinterpret_cast<uint32_t*>(&s_meta)[tid] = step_meta[(int64_t)b * 4 * A + tid];
+  } else if (tid < 5 * A) {
+    s_dirty[tid - 4 * A] = st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + (tid - 4 * A)];
+    s_bad[tid - 4 * A] = 0u;
   }
   __syncthreads();
 
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
     // new range flag: some result left the range, or nothing clamped an already flagged map
     const int i = tid - 32;
     const bool keep = s_meta.comm[i] == 0u && s_dirty[i] != 0u;
-    st.map_flags[((int64_t)b * A + i) * cfg.n_seg + chunk] = (uint8_t)((s_bad[i] != 0u || keep) ? 1 : 0);
+    st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + i] = (uint8_t)((s_bad[i] != 0u || keep) ? 1 : 0);
   }
 }
 
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(256)
       const F4 upd = f4_select(own, f4_mul(f4_clamp(o, cfg.o_min, cfg.o_max), f4_from(lut[s_row[i] + byte])), o);
       *reinterpret_cast<float4*>(lp) = f4_to(upd);
       if (f4_out_of_range(upd, cfg.o_min, cfg.o_max))  // same-value stores from several threads: benign
-        st.map_flags[((int64_t)b * A + i) * cfg.n_seg + q / IPP_FLAG_QUADS] = 1;
+        st.map_flags[((int64_t)b * cfg.n_seg + q / IPP_FLAG_QUADS) * 16 + i] = 1;
     }
   }
 }
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__
       const bool in_range = o * cfg.k_hi[iz] <= cfg.o_max && o * cfg.k_hi[iz] >= cfg.o_min &&
                             o * cfg.k_lo[iz] <= cfg.o_max && o * cfg.k_lo[iz] >= cfg.o_min &&
                             to_odds(cfg.prior) == o;
-      for (int32_t sgm = 0; sgm < cfg.n_seg; ++sgm) flags[((int64_t)b * A + a) * cfg.n_seg + sgm] = in_range ? 0 : 1;
+      for (int32_t sgm = 0; sgm < cfg.n_seg; ++sgm) flags[((int64_t)b * cfg.n_seg + sgm) * 16 + a] = in_range ? 0 : 1;
     }
   } else {
     mt.seed(ep);  // np.random.seed(episode): ground_truths.py:43
@@ -620,7 +628,7 @@ cudaError_t launch_export_beliefs(const float* src, float* dst, int64_t n_floats
   }
 
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
-                        int do_move, cudaStream_t s) {
+                        int do_move, uint32_t* step_meta, cudaStream_t s) {
   // ground truth + new code row of one env per warp in shared memory (falls back to global for big grids)
   const int stage_gt = (do_move && (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) <= 96 * 1024) ? 1 : 0;
   const size_t smem = stage_gt ? (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) : 0;
@@ -633,24 +641,21 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
     attr_set = true;
   }
   plan_kernel<<<(cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
-                                                                                      do_move, stage_gt | dbg);
+                                                                                      do_move, stage_gt | dbg, step_meta);
   return cudaGetLastError();
 }
 
-cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
-                              const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
-                              float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
-  (void)plan;
+cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut,
+                              const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
+                              double* partials, bool do_own, cudaStream_t s) {
   const int32_t n_chunks = cfg.n_seg;  // one block per (env, flag segment)
   const dim3 grid((unsigned)n_chunks * (unsigned)cfg.n_envs);
   if (do_own) {
     IPP_DISPATCH_A(cfg.n_agents, (step_direct_kernel<kA, true><<<grid, DIRECT_THREADS, 0, s>>>(
-                                     cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
-                                     n_chunks)));
+                                     cfg, st, lut, step_meta, t, reward_rel, reward_abs, partials, n_chunks)));
   } else {
     IPP_DISPATCH_A(cfg.n_agents, (step_direct_kernel<kA, false><<<grid, DIRECT_THREADS, 0, s>>>(
-                                     cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs, partials,
-                                     n_chunks)));
+                                     cfg, st, lut, step_meta, t, reward_rel, reward_abs, partials, n_chunks)));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -41,14 +41,16 @@ cudaError_t launch_features_critic(const ipp_config& cfg, const ipp_state& st, c
                                    float* state_out, cudaStream_t s);
 
 // lut: device table [n_alt][256] float4 = odds multipliers of the 4 cells of a quad for a code byte
+// step_meta: device scratch [n_envs][4 * n_agents] uint32 — the EnvMeta record (ipp_cell.cuh) of every env, written
+// by the plan kernel (comm bits, LUT rows of the communicated / new measurements) and read by the map kernels
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
-                        int do_move, cudaStream_t s);
-cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
-                              const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
-                              float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s);
+                        int do_move, uint32_t* step_meta, cudaStream_t s);
+cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut,
+                              const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
+                              double* partials, bool do_own, cudaStream_t s);
 cudaError_t launch_step_tma(const ipp_config& cfg, const ipp_state& st, const float4* lut, const TmaPlan& plan,
-                            int n_sm, const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
-                            float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s);
+                            int n_sm, const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
+                            double* partials, bool do_own, cudaStream_t s);
 cudaError_t launch_reward_finalize(const ipp_config& cfg, const double* partials, int32_t n_chunks, float* reward_rel,
                                    float* reward_abs, cudaStream_t s);
 cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const float4* lut, const int32_t* pos_out,

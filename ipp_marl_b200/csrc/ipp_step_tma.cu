@@ -25,6 +25,8 @@
 //   finisher warp : (one lane) waits map_done, finishes the per-env reward from the tiles' partial sums and
 //                   writes the local maps' new range flags.
 // HBM traffic is one read of every belief map and of the code rows plus the write of the quads that changed.
+#include <cstdlib>
+
 #include "ipp_cell.cuh"
 #include "ipp_launch.h"
 #include "ipp_ptx.cuh"
@@ -32,11 +34,11 @@
 namespace ipp {
 
 template <int A>
-struct StageMeta {
-  EnvMeta<A> env;
+struct alignas(16) StageMeta {
+  alignas(16) EnvMeta<A> env;     // bulk-copied: the env's record written by the plan kernel (16 A bytes)
+  alignas(16) uint8_t dirty[16];  // bulk-copied: range flags of the local maps' segment on entry (map_flags record)
   int32_t b, chunk, nq, pad;
-  uint32_t dirty[A];  // range flag of local map i's segment on entry (ipp_state.map_flags)
-  uint32_t bad[A];    // set by a tile task whose results left [o_min, o_max]
+  uint32_t bad[A];                // set by a tile task whose results left [o_min, o_max]
 };
 
 static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work item)");
@@ -52,10 +54,9 @@ constexpr int TMA_NT = TMA_QPC / 32;  // tiles per item
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(tma_threads(A), 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
-                    const int32_t* __restrict__ pos_in, const int32_t* __restrict__ pos_out,
-                    const uint8_t* __restrict__ comm, const int32_t t, float* __restrict__ reward_rel,
+                    const uint32_t* __restrict__ step_meta, const int32_t t, float* __restrict__ reward_rel,
                     float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks,
-                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes) {
+                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes, const int32_t dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int NT = TMA_NT;
   constexpr int AP = A <= 4 ? 4 : 8;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       for (int i = 0; i < A; ++i) {
         // new range flag: some result left the range, or nothing clamped an already flagged map
         const bool keep = sm.env.comm[i] == 0u && sm.dirty[i] != 0u;
-        st.map_flags[((int64_t)b * A + i) * cfg.n_seg + chunk] = (uint8_t)((sm.bad[i] != 0u || keep) ? 1 : 0);
+        st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + i] = (uint8_t)((sm.bad[i] != 0u || keep) ? 1 : 0);
       }
       ptx::mbar_arrive(env_done + 8u * es);
     }
@@ -149,16 +150,13 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       const int32_t b = item / n_chunks;
       const int32_t chunk = item - b * n_chunks;
       const int32_t nq = min(QPC, n_quads - chunk * QPC);
-      load_env_meta<A>(cfg, &meta[es].env, lane, b, pos_in, pos_out, comm, DO_OWN);
+      // (no global loads here: everything the item needs arrives by bulk copy, so this warp never waits on memory)
       if (lane == 0) {
         meta[es].b = b;
         meta[es].chunk = chunk;
         meta[es].nq = nq;
       }
-      if (lane < A) {
-        meta[es].dirty[lane] = st.map_flags[((int64_t)b * A + lane) * cfg.n_seg + chunk];
-        meta[es].bad[lane] = 0u;
-      }
+      if (lane < A) meta[es].bad[lane] = 0u;
       __syncwarp();
       if (lane == 0) {
         // Consumers pick (item, tile) tasks dynamically, so a warp may skip whole items and then wait on a
@@ -173,7 +171,10 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
         const uint32_t code_bytes = ((uint32_t)nq * AP + 15u) & ~15u;
         const uint32_t edst = ptx::smem_u32(env_slots + (size_t)es * env_bytes);
         const int64_t code0 = (int64_t)chunk * QPC * AP;
-        ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u));
+        ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u) + 16u * A + 16u);
+        ptx::bulk_load(ptx::smem_u32(&meta[es].env), step_meta + (int64_t)b * 4 * A, 16u * A, efull);
+        ptx::bulk_load(ptx::smem_u32(&meta[es].dirty[0]), st.map_flags + ((int64_t)b * cfg.n_seg + chunk) * 16, 16u,
+                       efull);
         ptx::bulk_load(edst, st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
                        code_bytes, efull);
         if (DO_OWN)
@@ -257,6 +258,16 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       }
       float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
       float4 l4[A];
+      if (dbg & 1) {  // timing experiment (IPP_TMA_DEBUG): the load pipeline alone, results are NOT computed
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int m = 0; m <= A; ++m) ptx::mbar_arrive(map_done + 8u * ((g0 + m) & (TMA_D_MAP - 1)));
+          ptx::mbar_arrive(env_tiles + 8u * es);
+        }
+        continue;
+      }
+      if (dbg & 4) any = 0u, mine = 0u;  // timing experiment: global map only
       if (have) g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[ql];
       constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
       if (kWide) {
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       // ---- global map + reward terms ----
       F4 kj[A];
       double s1 = 0.0, s2 = 0.0;
-      if (have) {
+      if (have && !(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
         __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
                global_quad<A>(cfg, sm.env, cw, lut, g4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
       } else {
@@ -349,8 +360,8 @@ TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
 
 template <int A, bool DO_OWN>
 static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, const float4* lut, const TmaPlan& plan,
-                                int n_sm, const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm,
-                                int32_t t, float* reward_rel, float* reward_abs, double* partials, cudaStream_t s) {
+                                int n_sm, const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
+                                double* partials, cudaStream_t s) {
   auto kern = step_tma_kernel<A, DO_OWN>;
   static int configured_bytes = 0;  // per template instantiation; grows to the largest plan seen
   if (plan.smem_bytes > configured_bytes) {
@@ -360,20 +371,22 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
   }
   const int n_items = cfg.n_envs * plan.n_chunks;
   const int grid = n_items < n_sm ? n_items : n_sm;
-  kern<<<grid, tma_threads(A), plan.smem_bytes, s>>>(cfg, st, lut, pos_in, pos_out, comm, t, reward_rel, reward_abs,
-                                                   partials, plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes);
+  int dbg = 0;
+  if (const char* v = getenv("IPP_TMA_DEBUG")) dbg = atoi(v);  // timing experiments only (results are wrong)
+  kern<<<grid, tma_threads(A), plan.smem_bytes, s>>>(cfg, st, lut, step_meta, t, reward_rel, reward_abs, partials,
+                                                   plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes, dbg);
   return cudaGetLastError();
 }
 
 cudaError_t launch_step_tma(const ipp_config& cfg, const ipp_state& st, const float4* lut, const TmaPlan& plan,
-                            int n_sm, const int32_t* pos_in, const int32_t* pos_out, const uint8_t* comm, int32_t t,
-                            float* reward_rel, float* reward_abs, double* partials, bool do_own, cudaStream_t s) {
-#define IPP_TMA_CASE(A_)                                                                                       \
-  case A_:                                                                                                     \
-    return do_own ? launch_tma_t<A_, true>(cfg, st, lut, plan, n_sm, pos_in, pos_out, comm, t, reward_rel,     \
-                                           reward_abs, partials, s)                                            \
-                  : launch_tma_t<A_, false>(cfg, st, lut, plan, n_sm, pos_in, pos_out, comm, t, reward_rel,    \
-                                            reward_abs, partials, s);
+                            int n_sm, const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
+                            double* partials, bool do_own, cudaStream_t s) {
+#define IPP_TMA_CASE(A_)                                                                                          \
+  case A_:                                                                                                        \
+    return do_own ? launch_tma_t<A_, true>(cfg, st, lut, plan, n_sm, step_meta, t, reward_rel, reward_abs,        \
+                                           partials, s)                                                           \
+                  : launch_tma_t<A_, false>(cfg, st, lut, plan, n_sm, step_meta, t, reward_rel, reward_abs,       \
+                                            partials, s);
   switch (cfg.n_agents) {
     IPP_TMA_CASE(1)
     IPP_TMA_CASE(2)

@@ -1,29 +1,30 @@
 // TMA-staged, warp-specialised, persistent variant of the map kernel (sm_100a).
 //
-// One CTA per SM walks the (env, chunk) work items.  A chunk is 640 quads (2560 cells) = 20 TILES of
-// 32 quads, so the 50x50 grid is a single chunk.  Shared memory holds two rings:
-//   * 16 MAP slots of 10 KB: one belief map of one item per slot;
-//   * 4 ENV slots: the item's two measurement-code rows + its EnvMeta + the reward partial sums.
-// Roles (no block-wide barrier anywhere after start-up; everything is mbarrier based):
-//   producer warp : per item, writes EnvMeta, bulk-loads the code rows (-> env_full) and then the
-//                   item's A+1 maps, each into the next free map slot (cp.async.bulk, SASS UBLKCP,
-//                   completion on map_full via expect_tx / complete_tx);
-//   consumer warps: pull (item, tile) tasks from a shared counter (dynamic load balance).  A warp decodes the
-//                   tile's code bytes once and takes its 32 quads through the item's maps, in registers:
-//                   * GLOBAL map: every cell gets all A fuse passes and its reward terms — a straight-line
-//                     clamp / multiply chain, the four multipliers of a quad from one LUT load per agent;
+// One CTA per SM walks the (env, chunk) work items.  A chunk is 640 quads (2560 cells) = 20 TILES of 32 quads, so
+// the 50x50 grid is a single chunk.  Shared memory holds two rings:
+//   * 16 MAP slots of 10 KB: one belief map of one item per slot (an item takes A + 1 consecutive slots);
+//   * 4 ENV slots: the item's two measurement-code rows, its StageMeta record and its reward partial sums.
+// Roles (no block-wide barrier after start-up; three mbarriers per env slot do all the synchronisation):
+//   producer warp : (one lane) per item: arms env_full with the item's total byte count, then bulk-loads
+//                   (cp.async.bulk, SASS UBLKCP) the env's record from the plan kernel, its range flags, the code
+//                   rows and the A + 1 maps, each map as soon as the item that used its slot before has been
+//                   consumed.  It issues no ordinary load, so it never waits on memory itself — with the record
+//                   read by plain loads this warp's latency was the whole kernel's bottleneck (profiles/);
+//   consumer warps: pull (item, tile) tasks from a shared counter (dynamic load balance), wait ONCE for the item
+//                   (env_full), decode the tile's code bytes and take its 32 quads through the item's maps in
+//                   registers — all loads, clamp / multiply chains and stores of the tile are independent work:
+//                   * GLOBAL map: every cell gets all A fuse passes and its reward terms — straight-line, the four
+//                     multipliers of a quad from one LUT load per agent;
 //                   * LOCAL maps: the enabled fuse passes and the own update, but only where it matters: a map
-//                     whose range flag is clear is known to lie inside [o_min, o_max], so the whole-map clamp of
-//                     the reference is a no-op on cells outside every footprint and a (tile, map) pair that no
-//                     footprint reaches is skipped by one warp vote, without touching shared memory;
-//                   (A = 8 needs more map slots than fit for dynamic scheduling: tiles are assigned statically)
-//                   a warp waits map_full, reads the slot and arrives on map_done — it never waits for other warps;
+//                     whose range flag is clear lies inside [o_min, o_max], so the whole-map clamp of the
+//                     reference is a no-op outside every footprint and a (tile, map) pair that no footprint
+//                     reaches is skipped by one warp vote, without touching shared memory;
 //                   results go from registers straight to global memory with coalesced streaming 16-byte stores
-//                   (512 contiguous bytes per warp); a slot is only ever READ by the SM, so it is free again as
-//                   soon as its last tile has been read — shared memory holds data that is loading or waiting
-//                   for a warp, never data that is draining to HBM;
-//   finisher warp : (one lane) waits map_done, finishes the per-env reward from the tiles' partial sums and
-//                   writes the local maps' new range flags.
+//                   (512 contiguous bytes per warp); the slots are only ever READ by the SM, so they are free as
+//                   soon as the item's last tile has arrived on env_tiles — shared memory holds data that is
+//                   loading or waiting for a warp, never data that is draining to HBM;
+//   finisher warp : (one lane) waits env_tiles, finishes the per-env reward from the tiles' partial sums in a
+//                   fixed order, writes the local maps' new range flags and hands the env slot back (env_done).
 // HBM traffic is one read of every belief map and of the code rows plus the write of the quads that changed.
 #include <cstdlib>
 
@@ -37,20 +38,19 @@ template <int A>
 struct alignas(16) StageMeta {
   alignas(16) EnvMeta<A> env;     // bulk-copied: the env's record written by the plan kernel (16 A bytes)
   alignas(16) uint8_t dirty[16];  // bulk-copied: range flags of the local maps' segment on entry (map_flags record)
-  int32_t b, chunk, nq, pad;
-  uint32_t bad[A];                // set by a tile task whose results left [o_min, o_max]
+  int32_t b, chunk, nq;
+  uint32_t bad;                   // bit i: a tile task's results for local map i left [o_min, o_max]
 };
 
 static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work item)");
 
-constexpr int TMA_D_MAP = 16;     // map slots (power of two: slot / phase of a counter by shift & mask)
-constexpr int TMA_D_ENV = 4;      // env slots
+constexpr int TMA_D_MAP = 16;     // map slots (power of two)
+constexpr int TMA_D_ENV = 4;      // env slots (power of two)
 constexpr int TMA_NT = TMA_QPC / 32;  // tiles per item
 
 // Shared-memory layout:
 //   [D_MAP][slot_bytes] map slots | [D_ENV][env_bytes] code rows | lut[n_alt*256] float4 | StageMeta[D_ENV] |
-//   mbarriers: map_full[D_MAP] map_done[D_MAP] env_full[D_ENV] env_tiles[D_ENV] env_done[D_ENV] |
-//   reward partials [D_ENV][2][NT] double | tile counter
+//   mbarriers: env_full[D_ENV] env_tiles[D_ENV] env_done[D_ENV] | reward partials [D_ENV][2][NT] double | tile counter
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(tma_threads(A), 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
@@ -63,22 +63,17 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
   constexpr int QPC = TMA_QPC;
   constexpr int CONSUMER_THREADS = tma_consumer_warps(A) * 32;
   constexpr int TMA_THREADS = tma_threads(A);
-  // Dynamic scheduling needs 2 items' maps to fit the slot ring (see the producer's comment on phase parity);
-  // A = 8 assigns the tiles statically.
-  constexpr bool kDynamic = (2 * A <= 14);
   unsigned char* map_slots = smem;
   unsigned char* env_slots = map_slots + (size_t)TMA_D_MAP * slot_bytes;
   float4* lut = reinterpret_cast<float4*>(env_slots + (size_t)TMA_D_ENV * env_bytes);
   StageMeta<A>* meta = reinterpret_cast<StageMeta<A>*>(lut + cfg.n_alt * 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta + TMA_D_ENV);
-  double* red = reinterpret_cast<double*>(bars + 2 * TMA_D_MAP + 3 * TMA_D_ENV);  // [D_ENV][2][NT]
+  double* red = reinterpret_cast<double*>(bars + 3 * TMA_D_ENV);  // [D_ENV][2][NT]
   uint32_t* tile_counter = reinterpret_cast<uint32_t*>(red + TMA_D_ENV * 2 * NT);
   // 32-bit shared addresses of the barrier arrays (8 bytes per barrier)
-  const uint32_t map_full = ptx::smem_u32(bars);
-  const uint32_t map_done = map_full + 8u * TMA_D_MAP;
-  const uint32_t env_full = map_done + 8u * TMA_D_MAP;
-  const uint32_t env_tiles = env_full + 8u * TMA_D_ENV;
-  const uint32_t env_done = env_tiles + 8u * TMA_D_ENV;
+  const uint32_t env_full = ptx::smem_u32(bars);            // producer's arrive.expect_tx + the bulk copies' bytes
+  const uint32_t env_tiles = env_full + 8u * TMA_D_ENV;     // one arrival per finished tile task
+  const uint32_t env_done = env_tiles + 8u * TMA_D_ENV;     // finisher
 
   const int32_t tid = threadIdx.x;
   const int32_t n_cells = cfg.gx * cfg.gy;
@@ -87,14 +82,10 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
   const uint32_t code_row = (uint32_t)QPC * AP;
 
   if (tid == 0) {
-    for (int s = 0; s < TMA_D_MAP; ++s) {
-      ptx::mbar_init(map_full + 8u * s, 1);    // producer's arrive.expect_tx
-      ptx::mbar_init(map_done + 8u * s, NT);   // one arrival per tile
-    }
     for (int s = 0; s < TMA_D_ENV; ++s) {
-      ptx::mbar_init(env_full + 8u * s, 1);       // producer
-      ptx::mbar_init(env_tiles + 8u * s, NT);     // one arrival per finished tile task
-      ptx::mbar_init(env_done + 8u * s, 1);       // finisher
+      ptx::mbar_init(env_full + 8u * s, 1);
+      ptx::mbar_init(env_tiles + 8u * s, NT);
+      ptx::mbar_init(env_done + 8u * s, 1);
     }
     *tile_counter = 0u;
     ptx::fence_mbar_init();
@@ -104,9 +95,8 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
 
   if (tid >= CONSUMER_THREADS + 32) {
     // ================================================================== finisher warp (one lane)
-    // Waits on the ENV-level barrier only: an env slot is recycled after this lane's own arrival, so its phase
-    // parity can never run two phases ahead of the wait (a map slot's barrier could — slots are recycled as soon
-    // as their tiles have been read).
+    // An env slot is recycled only after this lane's own arrival on env_done, so the phase parity of env_tiles
+    // can never run two phases ahead of the wait.
     if (tid != CONSUMER_THREADS + 32) return;
     uint32_t k = 0;
     for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
@@ -133,7 +123,7 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       for (int i = 0; i < A; ++i) {
         // new range flag: some result left the range, or nothing clamped an already flagged map
         const bool keep = sm.env.comm[i] == 0u && sm.dirty[i] != 0u;
-        st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + i] = (uint8_t)((sm.bad[i] != 0u || keep) ? 1 : 0);
+        st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + i] = (uint8_t)((((sm.bad >> i) & 1u) != 0u || keep) ? 1 : 0);
       }
       ptx::mbar_arrive(env_done + 8u * es);
     }
@@ -141,57 +131,54 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
   }
 
   if (tid >= CONSUMER_THREADS) {
-    // ================================================================== producer warp
-    const int lane = tid - CONSUMER_THREADS;
-    uint32_t k = 0, g = 0;
+    // ================================================================== producer warp (one lane)
+    if (tid != CONSUMER_THREADS) return;
+    uint32_t k = 0;
+    uint32_t released = 0;  // items [0, released) are known to be fully consumed (their map slots may be reused)
     for (int32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
       const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
-      ptx::mbar_wait(env_done + 8u * es, pe ^ 1u);
+      ptx::mbar_wait(env_done + 8u * es, pe ^ 1u);  // the env slot's previous item (k - D_ENV) is finished
+      if (k >= TMA_D_ENV && released < k - TMA_D_ENV + 1) released = k - TMA_D_ENV + 1;
       const int32_t b = item / n_chunks;
       const int32_t chunk = item - b * n_chunks;
       const int32_t nq = min(QPC, n_quads - chunk * QPC);
-      // (no global loads here: everything the item needs arrives by bulk copy, so this warp never waits on memory)
-      if (lane == 0) {
-        meta[es].b = b;
-        meta[es].chunk = chunk;
-        meta[es].nq = nq;
-      }
-      if (lane < A) meta[es].bad[lane] = 0u;
-      __syncwarp();
-      if (lane == 0) {
-        // Consumers pick (item, tile) tasks dynamically, so a warp may skip whole items and then wait on a
-        // map slot by phase PARITY.  That is only sound if the slot's previous use has already been loaded:
-        // before publishing item k, make sure every map load of items <= k-2 has landed (they were issued
-        // two items ago, so this never stalls in practice).  Covers A <= 7 with 16 slots; A = 8 is static.
-        if (k >= 2) {
-          for (uint32_t gg = (k - 2) * (A + 1); gg < (k - 1) * (A + 1); ++gg)
-            ptx::mbar_wait(map_full + 8u * (gg & (TMA_D_MAP - 1)), (gg / TMA_D_MAP) & 1u);
-        }
-        const uint32_t efull = env_full + 8u * es;
-        const uint32_t code_bytes = ((uint32_t)nq * AP + 15u) & ~15u;
-        const uint32_t edst = ptx::smem_u32(env_slots + (size_t)es * env_bytes);
-        const int64_t code0 = (int64_t)chunk * QPC * AP;
-        ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u) + 16u * A + 16u);
-        ptx::bulk_load(ptx::smem_u32(&meta[es].env), step_meta + (int64_t)b * 4 * A, 16u * A, efull);
-        ptx::bulk_load(ptx::smem_u32(&meta[es].dirty[0]), st.map_flags + ((int64_t)b * cfg.n_seg + chunk) * 16, 16u,
-                       efull);
-        ptx::bulk_load(edst, st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
+      meta[es].b = b;
+      meta[es].chunk = chunk;
+      meta[es].nq = nq;
+      meta[es].bad = 0u;
+      const uint32_t efull = env_full + 8u * es;
+      const uint32_t code_bytes = ((uint32_t)nq * AP + 15u) & ~15u;
+      const uint32_t map_bytes = (uint32_t)nq * 16u;
+      const uint32_t edst = ptx::smem_u32(env_slots + (size_t)es * env_bytes);
+      const int64_t code0 = (int64_t)chunk * QPC * AP;
+      // ONE barrier phase per item: armed with the byte count of everything the item needs before the first copy
+      // is issued, so it completes exactly when the last byte has landed
+      ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u) + 16u * A + 16u + (A + 1) * map_bytes);
+      ptx::bulk_load(ptx::smem_u32(&meta[es].env), step_meta + (int64_t)b * 4 * A, 16u * A, efull);
+      ptx::bulk_load(ptx::smem_u32(&meta[es].dirty[0]), st.map_flags + ((int64_t)b * cfg.n_seg + chunk) * 16, 16u, efull);
+      ptx::bulk_load(edst, st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0, code_bytes,
+                     efull);
+      if (DO_OWN)
+        ptx::bulk_load(edst + code_row,
+                       st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
                        code_bytes, efull);
-        if (DO_OWN)
-          ptx::bulk_load(edst + code_row,
-                         st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride + code0,
-                         code_bytes, efull);
-        const uint32_t map_bytes = (uint32_t)nq * 16u;
-        const int64_t cell0 = (int64_t)chunk * QPC * 4;
+      const int64_t cell0 = (int64_t)chunk * QPC * 4;
 #pragma unroll 1
-        for (int m = 0; m <= A; ++m, ++g) {
-          const uint32_t ms = g & (TMA_D_MAP - 1), pm = (g / TMA_D_MAP) & 1u;
-          ptx::mbar_wait(map_done + 8u * ms, pm ^ 1u);  // every tile of the slot's previous map has been read
-          const float* src = (m == 0) ? st.global_map + (int64_t)b * stride + cell0
-                                      : st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
-          ptx::mbar_arrive_expect_tx(map_full + 8u * ms, map_bytes);
-          ptx::bulk_load(ptx::smem_u32(map_slots + (size_t)ms * slot_bytes), src, map_bytes, map_full + 8u * ms);
+      for (int m = 0; m <= A; ++m) {
+        const uint32_t g = k * (A + 1) + (uint32_t)m;  // running map index; slot = g mod D_MAP
+        if (g >= (uint32_t)TMA_D_MAP) {
+          // the slot's previous map belongs to item (g - D_MAP) / (A + 1): wait until that item has been consumed.
+          // Items <= k - D_ENV are covered by the env_done wait above; the others are younger than k - D_ENV, so
+          // their env slot cannot have been recycled and the phase parity of env_tiles is unambiguous.
+          const uint32_t need = (g - TMA_D_MAP) / (A + 1);
+          while (released <= need) {
+            ptx::mbar_wait(env_tiles + 8u * (released & (TMA_D_ENV - 1)), (released / TMA_D_ENV) & 1u);
+            ++released;
+          }
         }
+        const float* src = (m == 0) ? st.global_map + (int64_t)b * stride + cell0
+                                    : st.local_maps + ((int64_t)b * A + (m - 1)) * stride + cell0;
+        ptx::bulk_load(ptx::smem_u32(map_slots + (size_t)(g & (TMA_D_MAP - 1)) * slot_bytes), src, map_bytes, efull);
       }
     }
     return;
@@ -202,126 +189,104 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
   const uint32_t my_items = (blockIdx.x < (uint32_t)n_items)
                                 ? (uint32_t)(n_items - (int32_t)blockIdx.x + (int32_t)gridDim.x - 1) / gridDim.x
                                 : 0u;
-  const uint32_t warp = (uint32_t)tid >> 5;
-
-  {
-    const uint32_t total_tiles = my_items * NT;
-    const bool kout_one = (cfg.k_out == 1.0f);
-    uint32_t n_static = warp;
-    while (true) {
-      uint32_t n = 0;
-      if (kDynamic) {
-        if (lane == 0) n = atomicAdd(tile_counter, 1u);
-        n = __shfl_sync(0xFFFFFFFFu, n, 0);
-      } else {  // warp w owns tile w of every item (warps >= NT idle): every barrier is waited in order
-        if (warp >= (uint32_t)NT) break;
-        n = n_static;
-        n_static += NT;
-      }
-      if (n >= total_tiles) break;
-      const uint32_t k = n / NT, tile = n - k * NT;
-      const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
-      ptx::mbar_wait(env_full + 8u * es, pe);
-      StageMeta<A>& sm = meta[es];
-      const int32_t ql = (int32_t)tile * 32 + lane;
-      const bool have = ql < sm.nq;
-      const int32_t cell_q = sm.chunk * QPC + ql;  // quad index inside the whole map
-      const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
-      const unsigned char* code_next = code_prev + code_row;
-      CodeWord<A> cw, nw;
-#pragma unroll
-      for (int w = 0; w < CodeWord<A>::WORDS; ++w) cw.w[w] = nw.w[w] = 0u;
-      if (have) {
-        cw = load_code<A>(code_prev, ql);
-        if (DO_OWN) nw = load_code<A>(code_next, ql);
-      }
-      // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint; every
-      // quad if the map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
-      uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
-#pragma unroll
-      for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
-      uint32_t mine = 0, any = 0;
-#pragma unroll
-      for (int i = 0; i < A; ++i) {
-        const bool all = sm.env.comm[i] != 0u && (sm.dirty[i] != 0u || !kout_one);
-        const bool m_i = have && (all || ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u);
-        mine |= (m_i ? 1u : 0u) << i;
-        any |= (__any_sync(0xFFFFFFFFu, m_i) ? 1u : 0u) << i;
-      }
-      // all A + 1 maps of the item must have landed (they were requested together); then every load, every
-      // clamp / multiply chain and every store of the tile is independent work the scheduler can overlap
-      const uint32_t g0 = k * (A + 1);
-#pragma unroll
-      for (int m = 0; m <= A; ++m) {
-        const uint32_t g = g0 + m;
-        ptx::mbar_wait(map_full + 8u * (g & (TMA_D_MAP - 1)), (g / TMA_D_MAP) & 1u);
-      }
-      float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-      float4 l4[A];
-      if (dbg & 1) {  // timing experiment (IPP_TMA_DEBUG): the load pipeline alone, results are NOT computed
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int m = 0; m <= A; ++m) ptx::mbar_arrive(map_done + 8u * ((g0 + m) & (TMA_D_MAP - 1)));
-          ptx::mbar_arrive(env_tiles + 8u * es);
-        }
-        continue;
-      }
-      if (dbg & 4) any = 0u, mine = 0u;  // timing experiment: global map only
-      if (have) g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[ql];
-      constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
-      if (kWide) {
-#pragma unroll
-        for (int i = 0; i < A; ++i)
-          if ((mine >> i) & 1u)
-            l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
-      }
-      // ---- global map + reward terms ----
-      F4 kj[A];
-      double s1 = 0.0, s2 = 0.0;
-      if (have && !(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
-        __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
-               global_quad<A>(cfg, sm.env, cw, lut, g4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
-      } else {
-#pragma unroll
-        for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
-      }
-      // ---- local maps ----
-      uint32_t bad = 0;
-#pragma unroll
-      for (int i = 0; i < A; ++i) {
-        if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
-        if ((mine >> i) & 1u) {
-          bool b_i;
-          if (kWide) {
-            b_i = local_quad<A, DO_OWN>(cfg, sm.env.comm[i], kj, DO_OWN ? nw.byte(i) : 0u, sm.env.lut_next[i], lut, l4[i]);
-          } else {  // A > 4: one map at a time, multipliers re-read from the LUT
-            l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
-            b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
-          }
-          if (b_i) bad |= 1u << i;
-          __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, l4[i]);
-        }
-      }
-      bad = __reduce_or_sync(0xFFFFFFFFu, bad);
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      if (lane == 0) {
-        double* r = red + (size_t)es * 2 * NT;
-        r[tile] = s1;
-        r[NT + tile] = s2;
-#pragma unroll
-        for (int i = 0; i < A; ++i)
-          if ((bad >> i) & 1u) sm.bad[i] = 1u;
-      }
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int m = 0; m <= A; ++m) ptx::mbar_arrive(map_done + 8u * ((g0 + m) & (TMA_D_MAP - 1)));
-      }
+  const uint32_t total_tiles = my_items * NT;
+  const bool kout_one = (cfg.k_out == 1.0f);
+  while (true) {
+    uint32_t n = 0;
+    if (lane == 0) n = atomicAdd(tile_counter, 1u);
+    n = __shfl_sync(0xFFFFFFFFu, n, 0);
+    if (n >= total_tiles) break;
+    const uint32_t k = n / NT, tile = n - k * NT;
+    const uint32_t es = k & (TMA_D_ENV - 1), pe = (k / TMA_D_ENV) & 1u;
+    // Tasks are handed out in item order and an env slot is recycled only after all NT tiles of its item have
+    // arrived, so a warp can never be two phases behind on this barrier.
+    ptx::mbar_wait(env_full + 8u * es, pe);
+    StageMeta<A>& sm = meta[es];
+    const int32_t ql = (int32_t)tile * 32 + lane;
+    const bool have = ql < sm.nq;
+    if (dbg & 1) {  // timing experiment (IPP_TMA_DEBUG): the load pipeline alone, results are NOT computed
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);
+      continue;
     }
+    const int32_t cell_q = sm.chunk * QPC + ql;  // quad index inside the whole map
+    const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
+    CodeWord<A> cw, nw;
+#pragma unroll
+    for (int w = 0; w < CodeWord<A>::WORDS; ++w) cw.w[w] = nw.w[w] = 0u;
+    if (have) {
+      cw = load_code<A>(code_prev, ql);
+      if (DO_OWN) nw = load_code<A>(code_prev + code_row, ql);
+    }
+    // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint; every quad
+    // if the map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
+    uint32_t all_mask;
+    {
+      bool a_l = false;
+      if (lane < A) a_l = sm.env.comm[lane] != 0u && (sm.dirty[lane] != 0u || !kout_one);
+      all_mask = __ballot_sync(0xFFFFFFFFu, a_l);
+    }
+    uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
+#pragma unroll
+    for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
+    uint32_t mine = 0, any = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const bool m_i = have && (((all_mask >> i) & 1u) != 0u ||
+                                ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u);
+      mine |= (m_i ? 1u : 0u) << i;
+      any |= (__any_sync(0xFFFFFFFFu, m_i) ? 1u : 0u) << i;
+    }
+    if (dbg & 4) any = 0u, mine = 0u;  // timing experiment: global map only
+    const uint32_t g0 = k * (A + 1);
+    float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    float4 l4[A];
+    if (have) g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+    constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
+    if (kWide) {
+#pragma unroll
+      for (int i = 0; i < A; ++i)
+        if ((mine >> i) & 1u)
+          l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+    }
+    // ---- global map + reward terms ----
+    F4 kj[A];
+    double s1 = 0.0, s2 = 0.0;
+    if (have && !(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
+      __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
+             global_quad<A>(cfg, sm.env, cw, lut, g4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
+    } else {
+#pragma unroll
+      for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
+    }
+    // ---- local maps ----
+    uint32_t bad = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
+      if ((mine >> i) & 1u) {
+        bool b_i;
+        if (kWide) {
+          b_i = local_quad<A, DO_OWN>(cfg, sm.env.comm[i], kj, DO_OWN ? nw.byte(i) : 0u, sm.env.lut_next[i], lut, l4[i]);
+        } else {  // A > 4: one map at a time, multipliers re-read from the LUT
+          l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+          b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
+        }
+        if (b_i) bad |= 1u << i;
+        __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, l4[i]);
+      }
+    }
+    bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      double* r = red + (size_t)es * 2 * NT;
+      r[tile] = s1;
+      r[NT + tile] = s2;
+      if (bad != 0u) atomicOr(&sm.bad, bad);
+    }
+    __syncwarp();  // every lane has read its quads out of the slots
+    if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);
   }
 }
 
@@ -351,7 +316,7 @@ TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin) {
   p.d_env = TMA_D_ENV;
   p.d_map = TMA_D_MAP;
   p.smem_bytes = TMA_D_MAP * p.slot_bytes + TMA_D_ENV * p.env_bytes + cfg.n_alt * 256 * 16 +
-                 TMA_D_ENV * (int)stage_meta_bytes(A) + (2 * TMA_D_MAP + 3 * TMA_D_ENV) * 8 +
+                 TMA_D_ENV * (int)stage_meta_bytes(A) + 3 * TMA_D_ENV * 8 +
                  TMA_D_ENV * 2 * TMA_NT * 8 + 16 + 128;
   // one whole item + at least one slot of prefetch must fit in the map ring
   p.ok = TMA_D_MAP >= (A + 1) + 1 && p.smem_bytes <= max_smem_optin;

@@ -138,6 +138,7 @@ __device__ __forceinline__ float entropy_bits_odds(float oc) {
 // s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).  Straight-line: a pass is
 // clamp + multiply, the multipliers of all four cells come from one LUT load per agent (k_out outside
 // the footprint), so no footprint logic is needed at all.  kj[] keeps the multipliers for the local maps.
+// Must be called by all 32 lanes of the warp, converged (lanes without a quad pass valid = 0).
 // ------------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
@@ -156,16 +157,18 @@ __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMe
     o = f4_mul(o, kj[j]);
   }
   touched = (cfg.k_out == 1.0f) ? (touched & 0xFu) : 0xFu;
+  // H(next) only where some lane of the warp has a touched cell (warp-uniform branch: the caller runs all 32
+  // lanes converged); an untouched cell has next == clamp(last) bit for bit, so its H(next) == H(last) exactly
+  const bool any_touched = __any_sync(0xFFFFFFFFu, touched != 0u);
   float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (!((valid >> c) & 1u)) continue;
     const float next = f4_get(o, c);
     const float hl = entropy_bits_odds(f4_get(oc, c));
     float hn = hl;
-    if (touched != 0u)  // quad-level branch; untouched cells of a touched quad reuse hl
-      hn = ((touched >> c) & 1u) ? entropy_bits_odds(fminf(fmaxf(next, lo), hi)) : hl;
-    const float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
+    if (any_touched) hn = entropy_bits_odds(fminf(fmaxf(next, lo), hi));
+    float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
+    w = ((valid >> c) & 1u) ? w : 0.0f;  // cells beyond gx*gy (or of a lane without a quad) do not count
     a1 += w * (hl - hn);
     a2 += w * hl;
   }

@@ -300,22 +300,20 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   const int32_t n_cells = cfg.gx * cfg.gy;
   const int32_t n_quads = (n_cells + 3) >> 2;
   const int64_t stride = cfg.map_stride;
-  const int32_t q = chunk * IPP_FLAG_QUADS + tid;
-  const bool have = q < n_quads;
+  const bool have = chunk * IPP_FLAG_QUADS + tid < n_quads;
+  // threads beyond the map's last quad run on a copy of that quad and do not store (no divergent regions)
+  const int32_t q = min(chunk * IPP_FLAG_QUADS + tid, n_quads - 1);
   const int64_t c0 = (int64_t)q << 2;
   float* glob = st.global_map + (int64_t)b * stride + c0;
   float* loc = st.local_maps + (int64_t)b * A * stride + c0;
 
   // ---- loads that depend on nothing ----
-  CodeWord<A> cw, nw;
+  const CodeWord<A> cw = load_code<A>(st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, q);
+  CodeWord<A> nw;
 #pragma unroll
-  for (int w = 0; w < CodeWord<A>::WORDS; ++w) cw.w[w] = nw.w[w] = 0u;
-  float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-  if (have) {
-    cw = load_code<A>(st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, q);
-    if (DO_OWN) nw = load_code<A>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride, q);
-    g4 = __ldcs(reinterpret_cast<const float4*>(glob));
-  }
+  for (int w = 0; w < CodeWord<A>::WORDS; ++w) nw.w[w] = 0u;
+  if (DO_OWN) nw = load_code<A>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride, q);
+  const float4 g4 = __ldcs(reinterpret_cast<const float4*>(glob));
   if (tid < 4 * A) {  // the env's record from the plan kernel (comm bits, LUT rows)
     reinterpret_cast<uint32_t*>(&s_meta)[tid] = step_meta[(int64_t)b * 4 * A + tid];
   } else if (tid < 5 * A) {
@@ -344,10 +342,10 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
 
   // ---- global map + reward terms ----
   double s1 = 0.0, s2 = 0.0;
-  if (have) {
+  {
     F4 kj[A];  // (unused here: the local maps re-read their multipliers)
-    g4 = global_quad<A>(cfg, s_meta, cw, lut, g4, valid_mask4((int32_t)c0, n_cells), kj, s1, s2);
-    __stcs(reinterpret_cast<float4*>(glob), g4);
+    const float4 gn = global_quad<A>(cfg, s_meta, cw, lut, g4, have ? valid_mask4((int32_t)c0, n_cells) : 0u, kj, s1, s2);
+    if (have) __stcs(reinterpret_cast<float4*>(glob), gn);
   }
   // ---- local maps ----
 #pragma unroll

@@ -209,15 +209,16 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);
       continue;
     }
-    const int32_t cell_q = sm.chunk * QPC + ql;  // quad index inside the whole map
+    // Lanes beyond the item's last quad (only in its last tile) run on a copy of that quad and simply do not
+    // store: no divergent region in the whole task.
+    const int32_t qi = min(ql, sm.nq - 1);
+    const int32_t cell_q = sm.chunk * QPC + qi;  // quad index inside the whole map
     const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
-    CodeWord<A> cw, nw;
+    const CodeWord<A> cw = load_code<A>(code_prev, qi);
+    CodeWord<A> nw;
 #pragma unroll
-    for (int w = 0; w < CodeWord<A>::WORDS; ++w) cw.w[w] = nw.w[w] = 0u;
-    if (have) {
-      cw = load_code<A>(code_prev, ql);
-      if (DO_OWN) nw = load_code<A>(code_prev + code_row, ql);
-    }
+    for (int w = 0; w < CodeWord<A>::WORDS; ++w) nw.w[w] = 0u;
+    if (DO_OWN) nw = load_code<A>(code_prev + code_row, qi);
     // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint; every quad
     // if the map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
     uint32_t all_mask;
@@ -232,29 +233,30 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     uint32_t mine = 0, any = 0;
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      const bool m_i = have && (((all_mask >> i) & 1u) != 0u ||
-                                ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u);
+      const bool m_i = ((all_mask >> i) & 1u) != 0u ||
+                       ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u;
       mine |= (m_i ? 1u : 0u) << i;
       any |= (__any_sync(0xFFFFFFFFu, m_i) ? 1u : 0u) << i;
     }
     if (dbg & 4) any = 0u, mine = 0u;  // timing experiment: global map only
+    if (!have) mine = 0u;
     const uint32_t g0 = k * (A + 1);
-    float4 g4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    const float4 g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[qi];
     float4 l4[A];
-    if (have) g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[ql];
     constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
     if (kWide) {
 #pragma unroll
       for (int i = 0; i < A; ++i)
-        if ((mine >> i) & 1u)
-          l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
+        if ((any >> i) & 1u)  // warp-uniform
+          l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[qi];
     }
     // ---- global map + reward terms ----
     F4 kj[A];
     double s1 = 0.0, s2 = 0.0;
-    if (have && !(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
-      __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q,
-             global_quad<A>(cfg, sm.env, cw, lut, g4, valid_mask4(cell_q << 2, n_cells), kj, s1, s2));
+    if (!(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
+      const float4 gn = global_quad<A>(cfg, sm.env, cw, lut, g4, have ? valid_mask4(cell_q << 2, n_cells) : 0u, kj,
+                                       s1, s2);
+      if (have) __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q, gn);
     } else {
 #pragma unroll
       for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
@@ -264,14 +266,14 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
-      if ((mine >> i) & 1u) {
-        bool b_i;
-        if (kWide) {
-          b_i = local_quad<A, DO_OWN>(cfg, sm.env.comm[i], kj, DO_OWN ? nw.byte(i) : 0u, sm.env.lut_next[i], lut, l4[i]);
-        } else {  // A > 4: one map at a time, multipliers re-read from the LUT
-          l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[ql];
-          b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
-        }
+      bool b_i;
+      if (kWide) {
+        b_i = local_quad<A, DO_OWN>(cfg, sm.env.comm[i], kj, DO_OWN ? nw.byte(i) : 0u, sm.env.lut_next[i], lut, l4[i]);
+      } else {  // A > 4: one map at a time, multipliers re-read from the LUT
+        l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[qi];
+        b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
+      }
+      if ((mine >> i) & 1u) {  // lanes whose quad no footprint reaches hold an unchanged copy: nothing to store
         if (b_i) bad |= 1u << i;
         __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, l4[i]);
       }

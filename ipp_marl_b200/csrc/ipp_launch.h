@@ -10,7 +10,7 @@ namespace ipp {
 constexpr int STEP_THREADS = 256;   // direct-load variant: threads per (env, chunk) block
 constexpr int TMA_QPC = 640;             // TMA variant: quads per work item (20 tiles of 32 quads, 10 KB per map)
 // consumer warps pulling (item, tile) tasks (+ 1 producer warp + 1 finisher warp; a block has at most 1024 threads)
-__host__ __device__ constexpr int tma_consumer_warps(int n_agents) { return n_agents <= 4 ? 26 : 26; }
+__host__ __device__ constexpr int tma_consumer_warps(int n_agents) { return n_agents <= 4 ? 30 : 26; }
 __host__ __device__ constexpr int tma_threads(int n_agents) { return (tma_consumer_warps(n_agents) + 2) * 32; }
 
 struct LaunchPlan {

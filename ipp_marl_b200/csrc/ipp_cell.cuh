@@ -143,7 +143,7 @@ __device__ __forceinline__ float entropy_bits_odds(float oc) {
 template <int A>
 __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
                                               const float4* lut, const float4 o4, const uint32_t valid, F4 (&kj)[A],
-                                              double& s1, double& s2) {
+                                              float& s1, float& s2) {
   const float lo = cfg.o_min, hi = cfg.o_max;
   const F4 oc = f4_clamp(f4_from(o4), lo, hi);
   F4 o = oc;
@@ -172,8 +172,8 @@ __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMe
     a1 += w * (hl - hn);
     a2 += w * hl;
   }
-  s1 += (double)a1;
-  s2 += (double)a2;
+  s1 = a1;  // float32 per-quad terms; the callers sum 32 quads in float32, then everything in float64
+  s2 = a2;
   return f4_to(o);
 }
 
@@ -223,6 +223,12 @@ __device__ __forceinline__ bool local_quad_lut(const ipp_config& cfg, const EnvM
 __device__ __forceinline__ uint32_t valid_mask4(int32_t c0, int32_t n_cells) {
   const int32_t left = n_cells - c0;
   return left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, off);
+  return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

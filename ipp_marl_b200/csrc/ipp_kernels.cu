@@ -341,11 +341,14 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   }
 
   // ---- global map + reward terms ----
-  double s1 = 0.0, s2 = 0.0;
+  double s1, s2;
   {
     F4 kj[A];  // (unused here: the local maps re-read their multipliers)
-    const float4 gn = global_quad<A>(cfg, s_meta, cw, lut, g4, have ? valid_mask4((int32_t)c0, n_cells) : 0u, kj, s1, s2);
+    float f1 = 0.0f, f2 = 0.0f;
+    const float4 gn = global_quad<A>(cfg, s_meta, cw, lut, g4, have ? valid_mask4((int32_t)c0, n_cells) : 0u, kj, f1, f2);
     if (have) __stcs(reinterpret_cast<float4*>(glob), gn);
+    s1 = (double)warp_sum_f(f1);  // the same float32 sum over a warp's 32 quads as in the TMA kernel
+    s2 = (double)warp_sum_f(f2);
   }
   // ---- local maps ----
 #pragma unroll
@@ -356,8 +359,6 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   }
 
   // ---- per-env reward: warp shuffle + shared-memory reduction of the two float64 sums (fixed order) ----
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
   if ((tid & 31) == 0) {
     s_red[0][tid >> 5] = s1;
     s_red[1][tid >> 5] = s2;

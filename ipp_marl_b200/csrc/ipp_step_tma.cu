@@ -221,11 +221,21 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     if (DO_OWN) nw = load_code<A>(code_prev + code_row, qi);
     // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint; every quad
     // if the map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
+    // Warp-uniform facts by ballot (the compiler then knows the branches on them are uniform): bit i of all_mask
+    // = local map i needs every quad; en_bits bit (i * A + j) = local map i fuses agent j's measurement.
     uint32_t all_mask;
+    uint64_t en_bits;
     {
       bool a_l = false;
       if (lane < A) a_l = sm.env.comm[lane] != 0u && (sm.dirty[lane] != 0u || !kout_one);
       all_mask = __ballot_sync(0xFFFFFFFFu, a_l);
+      const int p0 = lane, p1 = lane + 32;
+      const bool b0 = p0 < A * A && ((sm.env.comm[p0 / A] >> (p0 % A)) & 1u) != 0u;
+      en_bits = __ballot_sync(0xFFFFFFFFu, b0);
+      if (A * A > 32) {
+        const bool b1 = p1 < A * A && ((sm.env.comm[p1 / A] >> (p1 % A)) & 1u) != 0u;
+        en_bits |= (uint64_t)__ballot_sync(0xFFFFFFFFu, b1) << 32;
+      }
     }
     uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
 #pragma unroll
@@ -252,11 +262,14 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     }
     // ---- global map + reward terms ----
     F4 kj[A];
-    double s1 = 0.0, s2 = 0.0;
+    float s1 = 0.0f, s2 = 0.0f;
+    float4* const out_g = reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q;
+    float4* const out_l = reinterpret_cast<float4*>(st.local_maps + (int64_t)sm.b * A * stride) + cell_q;
+    const int64_t stride4 = stride >> 2;
     if (!(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
       const float4 gn = global_quad<A>(cfg, sm.env, cw, lut, g4, have ? valid_mask4(cell_q << 2, n_cells) : 0u, kj,
                                        s1, s2);
-      if (have) __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q, gn);
+      if (have) __stcs(out_g, gn);
     } else {
 #pragma unroll
       for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
@@ -268,23 +281,24 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
       bool b_i;
       if (kWide) {
-        b_i = local_quad<A, DO_OWN>(cfg, sm.env.comm[i], kj, DO_OWN ? nw.byte(i) : 0u, sm.env.lut_next[i], lut, l4[i]);
+        b_i = local_quad<A, DO_OWN>(cfg, (uint32_t)(en_bits >> (i * A)), kj, DO_OWN ? nw.byte(i) : 0u,
+                                    sm.env.lut_next[i], lut, l4[i]);
       } else {  // A > 4: one map at a time, multipliers re-read from the LUT
         l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[qi];
         b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
       }
       if ((mine >> i) & 1u) {  // lanes whose quad no footprint reaches hold an unchanged copy: nothing to store
         if (b_i) bad |= 1u << i;
-        __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)sm.b * A + i) * stride) + cell_q, l4[i]);
+        __stcs(out_l + i * stride4, l4[i]);
       }
     }
     bad = __reduce_or_sync(0xFFFFFFFFu, bad);
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
+    s1 = warp_sum_f(s1);
+    s2 = warp_sum_f(s2);
     if (lane == 0) {
       double* r = red + (size_t)es * 2 * NT;
-      r[tile] = s1;
-      r[NT + tile] = s2;
+      r[tile] = (double)s1;
+      r[NT + tile] = (double)s2;
       if (bad != 0u) atomicOr(&sm.bad, bad);
     }
     __syncwarp();  // every lane has read its quads out of the slots

@@ -285,21 +285,27 @@ def run_gpu(args):
     achieved = alg / (kern_ms * 1e-3) / 1e9
 
     # ---- e2e: host policy -> device env -> host rewards, copies inside the timed region ------------
+    # BatchedIPPEnv.step_host = one C call (ipp_step_host): H2D copy of the policy probabilities from pinned host
+    # memory, the two launches, D2H copies of rewards + chosen actions; the host synchronises every step because a
+    # host policy needs the result before it can produce the next step's probabilities.
     probs_host = torch.rand((B, A, 6), dtype=torch.float32).pin_memory()
-    probs_dev = torch.empty((B, A, 6), dtype=torch.float32, device=dev)
-    rew_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
+    rel_host = torch.empty((B,), dtype=torch.float32).pin_memory()
+    abs_host = torch.empty((B,), dtype=torch.float32).pin_memory()
     act_host = torch.empty((B, A), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def e2e_step(i):
+        if i % EP_LEN == 0:
+            env.reset()
+        env.step_host(probs_host, None, rel_host, abs_host, act_host)
+        stream.synchronize()
+
     for i in range(3):
-        episode_step(i, probs=probs_dev)
+        e2e_step(i)
     barrier()
     e0.record()
     for i in range(args.steps):
-        probs_dev.copy_(probs_host, non_blocking=True)
-        episode_step(i, probs=probs_dev)
-        rew_host[0].copy_(env.reward_rel, non_blocking=True)
-        rew_host[1].copy_(env.reward_abs, non_blocking=True)
-        act_host.copy_(env.actions, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the host policy needs the result before the next step
+        e2e_step(i)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -321,8 +327,8 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * A * 6 * 4,
                     "d2h_bytes_per_step": B * 4 * 2 + B * A * 4,
-                    "what": "BatchedIPPEnv.step(probs=...) with policy probabilities copied from pinned host "
-                            "memory and rewards+actions copied back every step"},
+                    "what": "BatchedIPPEnv.step_host (C ABI ipp_step_host): policy probabilities copied from pinned "
+                            "host memory, rewards + actions copied back, host synchronises every step"},
             "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

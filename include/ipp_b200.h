@@ -159,6 +159,19 @@ int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream
  */
 int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
 
+/*
+ * ipp_step for a policy that lives on the HOST: copies the step's policy output from host memory to the device,
+ * runs the timestep and copies its results back, all asynchronously on `stream` (one call, no host work between the
+ * copies and the two launches).  probs_host [n_envs, n_agents, 6] float32 or actions_host [n_envs, n_agents] int32
+ * (exactly one non-NULL; page-locked memory keeps the copies asynchronous); io->probs_in / io->actions_in are
+ * ignored, io->reward_rel / reward_abs / actions_out must be device buffers.  reward_rel_host / reward_abs_host
+ * [n_envs] float32 and actions_out_host [n_envs, n_agents] int32 may be NULL.  The host outputs are valid once the
+ * stream has been synchronised.
+ */
+int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, const float* probs_host,
+                  const int32_t* actions_host, float* reward_rel_host, float* reward_abs_host,
+                  int32_t* actions_out_host, void* stream);
+
 /* ipp_step with its two launches selectable (profiling aid: lets bench.py bracket the map kernel
  * alone with CUDA events).  phases = IPP_PHASE_MOVE | IPP_PHASE_MAPS is exactly ipp_step; the MAPS
  * phase needs comm_out / pos_out of a preceding MOVE phase of the same timestep. */

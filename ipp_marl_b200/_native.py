@@ -50,7 +50,7 @@ class IppStepIO(C.Structure):
 EXPORTS = [
     "ipp_status_string", "ipp_last_error", "ipp_version", "ipp_create", "ipp_destroy", "ipp_scratch_bytes",
     "ipp_set_step_variant", "ipp_get_step_variant",
-    "ipp_reset", "ipp_step", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_features_actor", "ipp_features_critic",
+    "ipp_reset", "ipp_step", "ipp_step_host", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_features_actor", "ipp_features_critic",
     "ipp_export_beliefs", "ipp_ig_plan", "ipp_eval_metrics", "ipp_project_fov", "ipp_measure", "ipp_update_cells",
     "ipp_shannon_entropy", "ipp_fuse_map", "ipp_utility_reward",
 ]
@@ -92,6 +92,7 @@ def load():
         getattr(lib, name).argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp]
     lib.ipp_features_actor.argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp, vp]
     lib.ipp_features_critic.argtypes = [vp, C.POINTER(IppState), i32, vp, vp, vp, vp, vp]
+    lib.ipp_step_host.argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp, vp, vp, vp, vp, vp]
     lib.ipp_export_beliefs.argtypes = [vp, C.POINTER(IppState), vp, vp, vp]
     lib.ipp_ig_plan.argtypes = [vp, C.POINTER(IppState), vp, i32, vp, vp, vp, vp, vp]
     lib.ipp_eval_metrics.argtypes = [vp, C.POINTER(IppState), vp, vp, vp]

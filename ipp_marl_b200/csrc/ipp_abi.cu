@@ -18,6 +18,7 @@ struct ipp_handle {
   int32_t* gt_params;   // [n_envs, 4]
   uint8_t* comm;        // [n_envs, n_agents] when the caller does not ask for comm_out
   uint32_t* step_meta;  // [n_envs, 4 * n_agents] per-env record handed from the plan kernel to the map kernels
+  void* policy_in;      // [n_envs, n_agents, 6] float32 staging of ipp_step_host's policy input (lazily allocated)
   float4* lut;          // [n_alt, 256] odds multipliers of a quad for every measurement code byte
   ipp::PoolTables pool; // cv2.INTER_AREA tap tables of the feature builders
   // facade scratch (grown on demand)
@@ -198,6 +199,7 @@ int ipp_destroy(ipp_handle* h) {
   if (h->gt_params) cudaFree(h->gt_params);
   if (h->comm) cudaFree(h->comm);
   if (h->step_meta) cudaFree(h->step_meta);
+  if (h->policy_in) cudaFree(h->policy_in);
   if (h->lut) cudaFree(h->lut);
   ipp::free_pool_tables(&h->pool);
   if (h->fbuf) cudaFree(h->fbuf);
@@ -248,6 +250,39 @@ int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_ste
 
 int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
   return ipp_step_phases(h, st, t, io, IPP_PHASE_MOVE | IPP_PHASE_MAPS, stream);
+}
+
+int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, const float* probs_host,
+                  const int32_t* actions_host, float* reward_rel_host, float* reward_abs_host,
+                  int32_t* actions_out_host, void* stream) {
+  if (h == nullptr || io == nullptr || (probs_host == nullptr) == (actions_host == nullptr))
+    return IPP_ERR_INVALID_ARG;
+  if (io->reward_rel == nullptr || io->reward_abs == nullptr || io->actions_out == nullptr) return IPP_ERR_INVALID_ARG;
+  const size_t n = (size_t)h->cfg.n_envs * h->cfg.n_agents;
+  if (h->policy_in == nullptr) {
+    IPP_CUDA(h, cudaMalloc(&h->policy_in, n * IPP_N_ACTIONS * sizeof(float)));
+    h->scratch_bytes += (int64_t)(n * IPP_N_ACTIONS * sizeof(float));
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  ipp_step_io io2 = *io;
+  if (probs_host != nullptr) {
+    IPP_CUDA(h, cudaMemcpyAsync(h->policy_in, probs_host, n * IPP_N_ACTIONS * sizeof(float), cudaMemcpyHostToDevice, s));
+    io2.probs_in = static_cast<const float*>(h->policy_in);
+    io2.actions_in = nullptr;
+  } else {
+    IPP_CUDA(h, cudaMemcpyAsync(h->policy_in, actions_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    io2.actions_in = static_cast<const int32_t*>(h->policy_in);
+    io2.probs_in = nullptr;
+  }
+  int rc = ipp_step_phases(h, st, t, &io2, IPP_PHASE_MOVE | IPP_PHASE_MAPS, stream);
+  if (rc != IPP_OK) return rc;
+  if (reward_rel_host != nullptr)
+    IPP_CUDA(h, cudaMemcpyAsync(reward_rel_host, io->reward_rel, h->cfg.n_envs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (reward_abs_host != nullptr)
+    IPP_CUDA(h, cudaMemcpyAsync(reward_abs_host, io->reward_abs, h->cfg.n_envs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (actions_out_host != nullptr)
+    IPP_CUDA(h, cudaMemcpyAsync(actions_out_host, io->actions_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  return IPP_OK;
 }
 
 int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {

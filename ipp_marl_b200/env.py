@@ -57,6 +57,7 @@ class BatchedIPPEnv:
         self._observed = False
         self._folded = False
         self._ig_actions = None
+        self._ios = {}
 
     # ---- views in the reference's array convention: [.., gx, gy], first axis = world x ----------
     def _view(self, flat):
@@ -170,8 +171,11 @@ class BatchedIPPEnv:
         that the map kernel can be bracketed with CUDA events."""
         if self.t >= self.T:
             raise N.IppError("episode finished: call reset()")
-        actions, probs = self._prep(actions, probs)
-        io = self._io(actions, probs, greedy)
+        if actions is None and probs is None and not greedy:
+            io = self._io_cached(self.t)
+        else:
+            actions, probs = self._prep(actions, probs)
+            io = self._io(actions, probs, greedy)
         if _phase_hook is None:
             rc = self.lib.ipp_step(self._h, C.byref(self._state), self.t, C.byref(io), self._stream())
             N.check(self.lib, self._h, rc, "ipp_step")
@@ -184,6 +188,38 @@ class BatchedIPPEnv:
         done = self.t == self.tables.budget  # coma_wrapper.py:163-164
         self.t += 1
         return self.reward_rel, self.reward_abs, done
+
+    def step_host(self, probs_host=None, actions_host=None, reward_rel_host=None, reward_abs_host=None,
+                  actions_out_host=None):
+        """One fused timestep for a policy that lives on the host: ONE C call copies ``probs_host`` [B, A, 6]
+        float32 (or ``actions_host`` [B, A] int32) to the device, runs the step and copies rewards / chosen actions
+        into the given host tensors (pinned memory keeps everything asynchronous).  Synchronise the current stream
+        before reading the outputs.  Returns ``done``."""
+        if self.t >= self.T:
+            raise N.IppError("episode finished: call reset()")
+        for x, shape, dt in ((probs_host, (self.B, self.A, 6), torch.float32), (actions_host, (self.B, self.A), torch.int32),
+                             (reward_rel_host, (self.B,), torch.float32), (reward_abs_host, (self.B,), torch.float32),
+                             (actions_out_host, (self.B, self.A), torch.int32)):
+            if x is not None and (x.is_cuda or x.dtype != dt or tuple(x.shape) != shape or not x.is_contiguous()):
+                raise N.IppError("step_host: host tensors must be contiguous CPU tensors of shape %s, %s" % (shape, dt))
+        io = self._io_cached(self.t)
+        rc = self.lib.ipp_step_host(self._h, C.byref(self._state), self.t, C.byref(io), _ptr(probs_host),
+                                    _ptr(actions_host), _ptr(reward_rel_host), _ptr(reward_abs_host),
+                                    _ptr(actions_out_host), self._stream())
+        N.check(self.lib, self._h, rc, "ipp_step_host")
+        done = self.t == self.tables.budget
+        self.t += 1
+        return done
+
+    def _io_cached(self, t):
+        """ipp_step_io of timestep t without injected inputs (built once: the pointers never change)."""
+        io = self._ios.get(t)
+        if io is None:
+            keep, self.t = self.t, t
+            io = self._io(None, None, False)
+            self.t = keep
+            self._ios[t] = io
+        return io
 
     # ---- the same timestep split around a policy network --------------------------------------
     def observe(self, final=False):

@@ -245,3 +245,35 @@ def test_full_size_properties():
     assert np.array_equal(env.local_maps[pick].cpu().numpy(), model.local)
     # information is gained on average: the mean episode return of the relative reward is positive
     assert float(total_rel.mean()) > 0.0
+
+
+@pytest.mark.gpu
+def test_step_host_matches_device_step():
+    """ipp_step_host (host policy in pinned memory -> one C call) gives exactly what step(probs=...) gives."""
+    import torch
+    from ipp_marl_b200 import BatchedIPPEnv
+
+    params = load_kats()["synthetic50"]["params"]
+    B = 96
+    a = BatchedIPPEnv(params, B, device="cuda:0")
+    b = BatchedIPPEnv(params, B, device="cuda:0")
+    a.reset()
+    b.reset()
+    g = torch.Generator().manual_seed(1)
+    rel_h = torch.empty((B,), dtype=torch.float32).pin_memory()
+    abs_h = torch.empty((B,), dtype=torch.float32).pin_memory()
+    act_h = torch.empty((B, a.A), dtype=torch.int32).pin_memory()
+    for t in range(a.T):
+        probs = torch.rand((B, a.A, 6), generator=g, dtype=torch.float32).pin_memory()
+        rel, ab, _ = a.step(probs=probs.cuda())
+        if t % 2 == 0:
+            b.step_host(probs, None, rel_h, abs_h, act_h)
+        else:  # injected actions from the host: replay what the other env just chose
+            b.step_host(None, a.actions.cpu().contiguous(), rel_h, abs_h, act_h)
+        torch.cuda.synchronize()
+        assert torch.equal(rel.cpu(), rel_h) and torch.equal(ab.cpu(), abs_h)
+        assert torch.equal(a.actions.cpu(), act_h)
+        assert torch.equal(a.pos.cpu(), b.pos.cpu())
+    assert torch.equal(a.local_odds, b.local_odds) and torch.equal(a.global_odds, b.global_odds)
+    with pytest.raises(Exception):
+        b.step_host(probs, None, rel_h, abs_h, act_h)  # episode finished

@@ -289,9 +289,7 @@ def run_gpu(args):
     # memory, the two launches, D2H copies of rewards + chosen actions; the host synchronises every step because a
     # host policy needs the result before it can produce the next step's probabilities.
     probs_host = torch.rand((B, A, 6), dtype=torch.float32).pin_memory()
-    rel_host = torch.empty((B,), dtype=torch.float32).pin_memory()
-    abs_host = torch.empty((B,), dtype=torch.float32).pin_memory()
-    act_host = torch.empty((B, A), dtype=torch.int32).pin_memory()
+    rel_host, abs_host, act_host = env.host_results()  # one pinned block: the results come back in one copy
     stream = torch.cuda.current_stream()
 
     def e2e_step(i):

@@ -165,8 +165,9 @@ int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* i
  * copies and the two launches).  probs_host [n_envs, n_agents, 6] float32 or actions_host [n_envs, n_agents] int32
  * (exactly one non-NULL; page-locked memory keeps the copies asynchronous); io->probs_in / io->actions_in are
  * ignored, io->reward_rel / reward_abs / actions_out must be device buffers.  reward_rel_host / reward_abs_host
- * [n_envs] float32 and actions_out_host [n_envs, n_agents] int32 may be NULL.  The host outputs are valid once the
- * stream has been synchronised.
+ * [n_envs] float32 and actions_out_host [n_envs, n_agents] int32 may be NULL.  When the three device outputs and
+ * the three host buffers are each one contiguous block in the order (reward_rel, reward_abs, actions) the results
+ * travel in a single copy.  The host outputs are valid once the stream has been synchronised.
  */
 int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, const float* probs_host,
                   const int32_t* actions_host, float* reward_rel_host, float* reward_abs_host,

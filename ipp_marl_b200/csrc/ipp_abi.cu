@@ -276,10 +276,22 @@ int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_
   }
   int rc = ipp_step_phases(h, st, t, &io2, IPP_PHASE_MOVE | IPP_PHASE_MAPS, stream);
   if (rc != IPP_OK) return rc;
+  // results: one copy when the three device outputs and the three host buffers are each contiguous in the order
+  // (reward_rel, reward_abs, actions) — a device->host copy costs ~10 us of latency whatever its size
+  const size_t ne = (size_t)h->cfg.n_envs;
+  const bool dev_packed = io->reward_abs == io->reward_rel + ne &&
+                          reinterpret_cast<const char*>(io->actions_out) == reinterpret_cast<const char*>(io->reward_abs + ne);
+  const bool host_packed = reward_rel_host != nullptr && reward_abs_host == reward_rel_host + ne &&
+                           reinterpret_cast<const char*>(actions_out_host) == reinterpret_cast<const char*>(reward_abs_host + ne);
+  if (dev_packed && host_packed) {
+    IPP_CUDA(h, cudaMemcpyAsync(reward_rel_host, io->reward_rel, 2 * ne * sizeof(float) + n * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, s));
+    return IPP_OK;
+  }
   if (reward_rel_host != nullptr)
-    IPP_CUDA(h, cudaMemcpyAsync(reward_rel_host, io->reward_rel, h->cfg.n_envs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    IPP_CUDA(h, cudaMemcpyAsync(reward_rel_host, io->reward_rel, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (reward_abs_host != nullptr)
-    IPP_CUDA(h, cudaMemcpyAsync(reward_abs_host, io->reward_abs, h->cfg.n_envs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    IPP_CUDA(h, cudaMemcpyAsync(reward_abs_host, io->reward_abs, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (actions_out_host != nullptr)
     IPP_CUDA(h, cudaMemcpyAsync(actions_out_host, io->actions_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   return IPP_OK;

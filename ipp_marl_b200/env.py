@@ -45,11 +45,13 @@ class BatchedIPPEnv:
         self._codes = torch.zeros((2, self.B, t.code_stride), dtype=torch.uint8, device=dev)
         self._flags = torch.ones((self.B, int(self.cfg.n_seg), 16), dtype=torch.uint8, device=dev)
         self.positions = torch.zeros((self.T + 1, self.B, self.A, 3), dtype=torch.int32, device=dev)
-        self.actions = torch.zeros((self.B, self.A), dtype=torch.int32, device=dev)
+        # rewards + chosen actions in ONE block (ipp_step_host returns them to the host with a single copy)
+        self._results = torch.zeros((self.B * (2 + self.A),), dtype=torch.int32, device=dev)
+        self.actions = self._results[2 * self.B:].view(self.B, self.A)
         self.masks = torch.zeros((self.B, self.A), dtype=torch.uint8, device=dev)
         self.comm = torch.zeros((self.B, self.A), dtype=torch.uint8, device=dev)
-        self.reward_rel = torch.zeros((self.B,), dtype=torch.float32, device=dev)
-        self.reward_abs = torch.zeros((self.B,), dtype=torch.float32, device=dev)
+        self.reward_rel = self._results[: self.B].view(torch.float32)
+        self.reward_abs = self._results[self.B: 2 * self.B].view(torch.float32)
         self.stuck = torch.zeros((self.B,), dtype=torch.uint8, device=dev)
         self._state = N.IppState(_ptr(self._local), _ptr(self._glob), _ptr(self._gt), _ptr(self.episodes),
                                  _ptr(self._codes), _ptr(self._flags))
@@ -188,6 +190,13 @@ class BatchedIPPEnv:
         done = self.t == self.tables.budget  # coma_wrapper.py:163-164
         self.t += 1
         return self.reward_rel, self.reward_abs, done
+
+    def host_results(self):
+        """Pinned host buffers (reward_rel [B], reward_abs [B], actions [B, A]) carved out of ONE block, so that
+        step_host brings the step's results back with a single device->host copy."""
+        blk = torch.zeros((self.B * (2 + self.A),), dtype=torch.int32).pin_memory()
+        return (blk[: self.B].view(torch.float32), blk[self.B: 2 * self.B].view(torch.float32),
+                blk[2 * self.B:].view(self.B, self.A))
 
     def step_host(self, probs_host=None, actions_host=None, reward_rel_host=None, reward_abs_host=None,
                   actions_out_host=None):

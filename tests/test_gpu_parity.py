@@ -260,10 +260,11 @@ def test_step_host_matches_device_step():
     a.reset()
     b.reset()
     g = torch.Generator().manual_seed(1)
-    rel_h = torch.empty((B,), dtype=torch.float32).pin_memory()
-    abs_h = torch.empty((B,), dtype=torch.float32).pin_memory()
-    act_h = torch.empty((B, a.A), dtype=torch.int32).pin_memory()
+    packed = b.host_results()  # one pinned block -> single device->host copy
+    loose = (torch.empty((B,), dtype=torch.float32).pin_memory(), torch.empty((B,), dtype=torch.float32).pin_memory(),
+             torch.empty((B, a.A), dtype=torch.int32).pin_memory())
     for t in range(a.T):
+        rel_h, abs_h, act_h = packed if t % 3 else loose
         probs = torch.rand((B, a.A, 6), generator=g, dtype=torch.float32).pin_memory()
         rel, ab, _ = a.step(probs=probs.cuda())
         if t % 2 == 0:

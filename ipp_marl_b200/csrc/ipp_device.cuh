@@ -43,10 +43,6 @@ struct Meas {
   uint32_t key;            // noise stream of this measurement
   uint32_t thresh;         // flip threshold of its altitude
   float k_hi, k_lo;        // odds multipliers
-  // code generation (plan_kernel): qw = most quads one footprint row can overlap, qmagic = ceil(2^32 / qw) (exact
-  // floor(n / qw) == umulhi(n, qmagic) for n < 2^32 / qw^2), ntasks = rows * qw
-  uint32_t qw, qmagic;
-  int32_t ntasks;
 };
 
 __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return min(max(v, lo), hi); }
@@ -67,10 +63,6 @@ __device__ __forceinline__ Meas make_meas(const ipp_config& c, const int32_t* po
   m.thresh = c.flip_thresh[iz];
   m.k_hi = c.k_hi[iz];
   m.k_lo = c.k_lo[iz];
-  const int32_t h = m.xr - m.xl, w = m.yd - m.yu;
-  m.qw = (uint32_t)(((max(w, 0) + 3) >> 2) + 1);
-  m.qmagic = 0xFFFFFFFFu / m.qw + 1u;
-  m.ntasks = (h > 0 && w > 0) ? h * (int32_t)m.qw : 0;
   return m;
 }
 

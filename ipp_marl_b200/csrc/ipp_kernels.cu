@@ -148,39 +148,62 @@ __device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_
   if (do_comm) write_env_meta(cfg, step_meta + (int64_t)b * 4 * A, comm_rows, pos, npos, true);
 }
 
-// Write the code bytes of all A measurements into this env's zeroed code row.  The work is flattened into
-// (agent, footprint row, quad-in-row) tasks, one per lane and round: every footprint row x contributes the quads
-// qa(x)..qb(x) that overlap its cells [yu, yd), a task computes the complete byte of its quad (a quad may span two
-// grid rows: rect_mask4 covers both), one strong hash + one multiply per cell give the four Bernoulli noise bits.
-// A quad reached from two rows is written twice with the same value (plain byte stores, no atomics).
+// Write the code byte of quad q (cells 4q..4q+3, first cell in grid row x) for measurement m.
+__device__ __forceinline__ void write_code_byte(const ipp_config& cfg, const Meas& m, const int a, const int ap,
+                                                const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
+                                                const int32_t q, const int32_t x, const int32_t row0) {
+  const int32_t c0 = q << 2;
+  const int32_t y0 = c0 - row0;
+  const int32_t left = cfg.gx * cfg.gy - c0;
+  const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
+  const uint32_t in = rect_mask4(m, x, y0, min(4, cfg.gy - y0)) & valid;
+  const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
+  codes[(int64_t)q * ap + a] = (uint8_t)(in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4));
+}
+
+// Write the code bytes of all A measurements into this env's zeroed code row.  One lane per
+// (agent, grid row) pair — the rows of the footprint plus the row just above it, whose last quad may wrap
+// into the footprint.  A lane walks the quads that START in its row, left to right, so every quad of a
+// footprint is written by exactly one lane: plain byte stores, no atomics, no per-task division.
 template <int MAXA>
 __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Meas* meas, const int A, const int ap,
                                                 const uint8_t* __restrict__ gt, uint8_t* __restrict__ codes,
                                                 const int lane) {
-  const int32_t gy = cfg.gy;
-  const int32_t n_cells = cfg.gx * gy;
   int32_t total = 0;
-  for (int a = 0; a < A; ++a) total += meas[a].ntasks;
+  for (int a = 0; a < A; ++a) {
+    const int32_t h = meas[a].xr - meas[a].xl, w = meas[a].yd - meas[a].yu;
+    total += (h > 0 && w > 0) ? h + 1 : 0;
+  }
+  const int32_t gy = cfg.gy;
   for (int32_t idx = lane; idx < total; idx += 32) {
     int a = 0;
-    int32_t rem = idx;
-    for (; a < A - 1; ++a) {  // which agent does this task belong to
-      if (rem < meas[a].ntasks) break;
-      rem -= meas[a].ntasks;
+    int32_t rr = idx;
+    for (; a < A; ++a) {  // which agent does this (agent, row) pair belong to
+      const int32_t h = meas[a].xr - meas[a].xl, w = meas[a].yd - meas[a].yu;
+      const int32_t n = (h > 0 && w > 0) ? h + 1 : 0;
+      if (rr < n) break;
+      rr -= n;
     }
     const Meas m = meas[a];
-    const int32_t r = (int32_t)__umulhi((uint32_t)rem, m.qmagic), k = rem - r * (int32_t)m.qw;
-    const int32_t x = m.xl + r, row0 = x * gy;
-    const int32_t q = ((row0 + m.yu) >> 2) + k;
-    if (q > ((row0 + m.yd - 1) >> 2)) continue;  // this row's run is one quad shorter than the maximum
-    const int32_t c0 = q << 2;
-    const int32_t x0 = c0 >= row0 ? x : x - 1;  // grid row of the quad's first cell
-    const int32_t y0 = c0 - x0 * gy;
-    const int32_t left = n_cells - c0;
-    const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
-    const uint32_t in = rect_mask4(m, x0, y0, min(4, gy - y0)) & valid;
-    const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + c0);
-    codes[(int64_t)q * ap + a] = (uint8_t)(in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4));
+    const int32_t h = m.xr - m.xl;
+    const int32_t x = m.xl - 1 + rr;  // this lane owns the quads whose first cell lies in grid row x
+    if (x < 0) continue;
+    const int32_t row0 = x * gy, row1 = row0 + gy;
+    const int32_t q_first = (row0 + 3) >> 2, q_last = (row1 - 1) >> 2;
+    int32_t qa = q_last + 1, qb = q_last - 1;  // run of quads overlapping the footprint cells of row x (empty if rr == 0)
+    if (rr >= 1) {
+      qa = max(q_first, (row0 + m.yu) >> 2);
+      qb = min(q_last, (row0 + m.yd - 1) >> 2);
+    }
+    if (qa <= qb) write_code_byte(cfg, m, a, ap, gt, codes, qa, x, row0);
+    for (int32_t q = qa + 1; q < qb; ++q) {  // strictly inside the run: all 4 cells are footprint cells of row x
+      const uint32_t g4 = *reinterpret_cast<const uint32_t*>(gt + (q << 2));
+      codes[(int64_t)q * ap + a] = (uint8_t)(0xFu | (seen_mask4(m.key, m.thresh, q << 2, g4) << 4));
+    }
+    if (qb > qa) write_code_byte(cfg, m, a, ap, gt, codes, qb, x, row0);
+    // the last quad of the row may wrap into row x+1: footprint cells there have y < n1
+    const int32_t n1 = (q_last << 2) + 4 - row1;
+    if (rr < h && n1 > 0 && m.yu < n1 && qb < q_last) write_code_byte(cfg, m, a, ap, gt, codes, q_last, x, row0);
   }
 }
 

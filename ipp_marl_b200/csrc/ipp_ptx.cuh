@@ -30,23 +30,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0u;
 }
-// try_wait with a suspend-time hint (ns): the hardware may park the warp for up to that long before it reports
-// "not yet", so a waiting warp polls rarely instead of competing for issue slots with the warps that compute
-__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0u;
-}
+// A waiting warp must not compete for issue slots with the warps that compute (the map kernel is issue-bound):
+// poll once, then back off with nanosleep between polls (try_wait alone re-polls every few dozen cycles).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-  }
+  while (!mbar_try_wait(bar, parity)) __nanosleep(96);
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

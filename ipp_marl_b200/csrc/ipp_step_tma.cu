@@ -56,8 +56,14 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
                     const uint32_t* __restrict__ step_meta, const int32_t t, float* __restrict__ reward_rel,
                     float* __restrict__ reward_abs, double* __restrict__ partials, const int32_t n_chunks,
-                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes, const int32_t dbg) {
+                    const int32_t n_items, const int32_t slot_bytes, const int32_t env_bytes, const int32_t dbg_arg) {
   extern __shared__ __align__(128) unsigned char smem[];
+#ifdef IPP_TMA_TIMING_KNOBS  // scripts/dbg_bench.py: IPP_TMA_DEBUG bit 0 = load pipeline only, 1 = no global map, 2 = no
+  const int32_t dbg = dbg_arg;  // local maps (results are then wrong); compiled out of the product build
+#else
+  constexpr int32_t dbg = 0;
+  (void)dbg_arg;
+#endif
   constexpr int NT = TMA_NT;
   constexpr int AP = A <= 4 ? 4 : 8;
   constexpr int QPC = TMA_QPC;

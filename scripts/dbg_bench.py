@@ -1,4 +1,6 @@
-"""Timing experiments on the TMA map kernel (IPP_TMA_DEBUG knobs; results of those runs are not valid maps)."""
+"""Timing experiments on the TMA map kernel (IPP_TMA_DEBUG knobs; results of those runs are not valid maps).
+Needs a library built with -DIPP_TMA_TIMING_KNOBS (add it to NVCC_FLAGS in ipp_marl_b200/build.py); the product
+build compiles the knobs out."""
 import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

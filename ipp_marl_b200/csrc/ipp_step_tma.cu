@@ -46,12 +46,11 @@ static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work it
 
 constexpr int TMA_D_MAP = 16;     // map slots (power of two)
 constexpr int TMA_D_ENV = 4;      // env slots (power of two)
-constexpr int TMA_TPT = 2;                        // tiles (of 32 quads) per task
-constexpr int TMA_NT = TMA_QPC / (32 * TMA_TPT);  // tasks per item
+constexpr int TMA_NT = TMA_QPC / 32;  // tiles per item
 
 // Shared-memory layout:
 //   [D_MAP][slot_bytes] map slots | [D_ENV][env_bytes] code rows | lut[n_alt*256] float4 | StageMeta[D_ENV] |
-//   mbarriers: env_full[D_ENV] env_tiles[D_ENV] env_done[D_ENV] | reward partials [D_ENV][2][NT] double | task counter
+//   mbarriers: env_full[D_ENV] env_tiles[D_ENV] env_done[D_ENV] | reward partials [D_ENV][2][NT] double | tile counter
 template <int A, bool DO_OWN>
 __global__ void __launch_bounds__(tma_threads(A), 1)
     step_tma_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const float4* __restrict__ lut_g,
@@ -209,15 +208,27 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     // arrived, so a warp can never be two phases behind on this barrier.
     ptx::mbar_wait(env_full + 8u * es, pe);
     StageMeta<A>& sm = meta[es];
+    const int32_t ql = (int32_t)tile * 32 + lane;
+    const bool have = ql < sm.nq;
     if (dbg & 1) {  // timing experiment (IPP_TMA_DEBUG): the load pipeline alone, results are NOT computed
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);
       continue;
     }
+    // Lanes beyond the item's last quad (only in its last tile) run on a copy of that quad and simply do not
+    // store: no divergent region in the whole task.
+    const int32_t qi = min(ql, sm.nq - 1);
+    const int32_t cell_q = sm.chunk * QPC + qi;  // quad index inside the whole map
     const unsigned char* code_prev = env_slots + (size_t)es * env_bytes;
+    const CodeWord<A> cw = load_code<A>(code_prev, qi);
+    CodeWord<A> nw;
+#pragma unroll
+    for (int w = 0; w < CodeWord<A>::WORDS; ++w) nw.w[w] = 0u;
+    if (DO_OWN) nw = load_code<A>(code_prev + code_row, qi);
+    // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint; every quad
+    // if the map may hold out-of-range odds and a fuse pass (= whole-map clamp) runs, or if k_out != 1
     // Warp-uniform facts by ballot (the compiler then knows the branches on them are uniform): bit i of all_mask
-    // = local map i needs every quad (it may hold out-of-range odds and a fuse pass = whole-map clamp runs, or
-    // k_out != 1); en_bits bit (i * A + j) = local map i fuses agent j's measurement.
+    // = local map i needs every quad; en_bits bit (i * A + j) = local map i fuses agent j's measurement.
     uint32_t all_mask;
     uint64_t en_bits;
     {
@@ -232,78 +243,59 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
         en_bits |= (uint64_t)__ballot_sync(0xFFFFFFFFu, b1) << 32;
       }
     }
+    uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
+#pragma unroll
+    for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
+    uint32_t mine = 0, any = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const bool m_i = ((all_mask >> i) & 1u) != 0u ||
+                       ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u;
+      mine |= (m_i ? 1u : 0u) << i;
+      any |= (__any_sync(0xFFFFFFFFu, m_i) ? 1u : 0u) << i;
+    }
+    if (dbg & 4) any = 0u, mine = 0u;  // timing experiment: global map only
+    if (!have) mine = 0u;
     const uint32_t g0 = k * (A + 1);
-    const int64_t stride4 = stride >> 2;
-    float s1 = 0.0f, s2 = 0.0f;
-    uint32_t bad = 0;
-    // A task = TPT consecutive tiles of 32 quads: the task fetch, the barrier wait, the ballots above and the
-    // reductions below are paid once per task.
-#pragma unroll 1
-    for (int u = 0; u < TMA_TPT; ++u) {
-      const int32_t ql = ((int32_t)tile * TMA_TPT + u) * 32 + lane;
-      const bool have = ql < sm.nq;
-      // Lanes beyond the item's last quad run on a copy of that quad and simply do not store: no divergent region.
-      const int32_t qi = min(ql, sm.nq - 1);
-      const int32_t cell_q = sm.chunk * QPC + qi;  // quad index inside the whole map
-      const CodeWord<A> cw = load_code<A>(code_prev, qi);
-      CodeWord<A> nw;
+    const float4 g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[qi];
+    float4 l4[A];
+    constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
+    if (kWide) {
 #pragma unroll
-      for (int w = 0; w < CodeWord<A>::WORDS; ++w) nw.w[w] = 0u;
-      if (DO_OWN) nw = load_code<A>(code_prev + code_row, qi);
-      // which local maps have work in this tile?  cells of an enabled fuse pass or of the own footprint
-      uint32_t in_prev = 0;  // bits 4j..4j+3: cells of this quad inside agent j's communicated footprint
-#pragma unroll
-      for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
-      uint32_t mine = 0, any = 0;
-#pragma unroll
-      for (int i = 0; i < A; ++i) {
-        const bool m_i = ((all_mask >> i) & 1u) != 0u ||
-                         ((in_prev & sm.env.comm4[i]) | (DO_OWN ? (nw.byte(i) & 0xFu) : 0u)) != 0u;
-        mine |= (m_i ? 1u : 0u) << i;
-        any |= (__any_sync(0xFFFFFFFFu, m_i) ? 1u : 0u) << i;
-      }
-      if (dbg & 4) any = 0u, mine = 0u;  // timing experiment: global map only
-      if (!have) mine = 0u;
-      const float4 g4 = reinterpret_cast<const float4*>(map_slots + (size_t)(g0 & (TMA_D_MAP - 1)) * slot_bytes)[qi];
-      float4 l4[A];
-      constexpr bool kWide = (A <= 4);  // registers for all of the item's quads + multipliers at once
-      if (kWide) {
-#pragma unroll
-        for (int i = 0; i < A; ++i)
-          if ((any >> i) & 1u)  // warp-uniform
-            l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[qi];
-      }
-      // ---- global map + reward terms ----
-      F4 kj[A];
-      float4* const out_g = reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q;
-      float4* const out_l = reinterpret_cast<float4*>(st.local_maps + (int64_t)sm.b * A * stride) + cell_q;
-      if (!(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
-        float q1, q2;
-        const float4 gn = global_quad<A>(cfg, sm.env, cw, lut, g4, have ? valid_mask4(cell_q << 2, n_cells) : 0u, kj,
-                                         q1, q2);
-        s1 += q1;
-        s2 += q2;
-        if (have) __stcs(out_g, gn);
-      } else {
-#pragma unroll
-        for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
-      }
-      // ---- local maps ----
-#pragma unroll
-      for (int i = 0; i < A; ++i) {
-        if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
-        bool b_i;
-        if (kWide) {
-          b_i = local_quad<A, DO_OWN>(cfg, (uint32_t)(en_bits >> (i * A)), kj, DO_OWN ? nw.byte(i) : 0u,
-                                      sm.env.lut_next[i], lut, l4[i]);
-        } else {  // A > 4: one map at a time, multipliers re-read from the LUT
+      for (int i = 0; i < A; ++i)
+        if ((any >> i) & 1u)  // warp-uniform
           l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[qi];
-          b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
-        }
-        if ((mine >> i) & 1u) {  // lanes whose quad no footprint reaches hold an unchanged copy: nothing to store
-          if (b_i) bad |= 1u << i;
-          __stcs(out_l + i * stride4, l4[i]);
-        }
+    }
+    // ---- global map + reward terms ----
+    F4 kj[A];
+    float s1 = 0.0f, s2 = 0.0f;
+    float4* const out_g = reinterpret_cast<float4*>(st.global_map + (int64_t)sm.b * stride) + cell_q;
+    float4* const out_l = reinterpret_cast<float4*>(st.local_maps + (int64_t)sm.b * A * stride) + cell_q;
+    const int64_t stride4 = stride >> 2;
+    if (!(dbg & 2)) {  // (dbg & 2: timing experiment, local maps only)
+      const float4 gn = global_quad<A>(cfg, sm.env, cw, lut, g4, have ? valid_mask4(cell_q << 2, n_cells) : 0u, kj,
+                                       s1, s2);
+      if (have) __stcs(out_g, gn);
+    } else {
+#pragma unroll
+      for (int j = 0; j < A; ++j) kj[j] = f4_splat(1.0f);
+    }
+    // ---- local maps ----
+    uint32_t bad = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      if (!((any >> i) & 1u)) continue;  // warp-uniform: no footprint reaches this (tile, map)
+      bool b_i;
+      if (kWide) {
+        b_i = local_quad<A, DO_OWN>(cfg, (uint32_t)(en_bits >> (i * A)), kj, DO_OWN ? nw.byte(i) : 0u,
+                                    sm.env.lut_next[i], lut, l4[i]);
+      } else {  // A > 4: one map at a time, multipliers re-read from the LUT
+        l4[i] = reinterpret_cast<const float4*>(map_slots + (size_t)((g0 + 1 + i) & (TMA_D_MAP - 1)) * slot_bytes)[qi];
+        b_i = local_quad_lut<A, DO_OWN>(cfg, sm.env, i, cw, DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);
+      }
+      if ((mine >> i) & 1u) {  // lanes whose quad no footprint reaches hold an unchanged copy: nothing to store
+        if (b_i) bad |= 1u << i;
+        __stcs(out_l + i * stride4, l4[i]);
       }
     }
     bad = __reduce_or_sync(0xFFFFFFFFu, bad);

@@ -6,6 +6,7 @@ TAG=${1:-r1}
 SEC=${2:-tblnp}
 OUT=gpurun_out
 mkdir -p $OUT
+if [[ $SEC == *s* ]]; then echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -3 | tee $OUT/smoke_$TAG.log; fi
 if [[ $SEC == *t* ]]; then echo "== tests"; timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_$TAG.log; fi
 if [[ $SEC == *q* ]]; then echo "== quick"; timeout 400 python scripts/quick_bench.py 2>&1 | tail -12 | tee $OUT/quick_$TAG.log; fi
 if [[ $SEC == *b* ]]; then echo "== bench.py"; timeout 600 python bench.py 2>$OUT/bench_$TAG.err | tail -1 | tee $OUT/bench_$TAG.json; fi

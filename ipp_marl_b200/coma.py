@@ -193,6 +193,7 @@ class COMATrainer:
         self.buf_act = torch.empty((T, B, A), dtype=torch.int32, device=dev)
         self.buf_mask = torch.empty((T, B, A), dtype=torch.uint8, device=dev)
         self.buf_rew = torch.empty((T, B), dtype=torch.float32, device=dev)
+        self.buf_abs = torch.empty((T, B), dtype=torch.float32, device=dev)  # absolute rewards (logged only)
 
     def _autocast(self):
         return torch.autocast("cuda", dtype=self.compute_dtype, enabled=self.compute_dtype != torch.float32)
@@ -205,7 +206,7 @@ class COMATrainer:
         eps = epsilon(self.episodes_done, *self.eps_cfg)
         B, A = env.B, env.A
         for t in range(env.T):
-            rel, _ = env.observe()
+            rel, ab = env.observe()
             env.features_actor(out=self.buf_obs[t])
             with self._autocast():
                 probs = self.actor(self.buf_obs[t].flatten(0, 1), eps)
@@ -214,6 +215,7 @@ class COMATrainer:
             self.buf_act[t].copy_(env.actions)
             self.buf_mask[t].copy_(env.masks)
             self.buf_rew[t].copy_(rel)
+            self.buf_abs[t].copy_(ab)
         self.episodes_done += 1
         return self.buf_rew.sum(0).mean()
 

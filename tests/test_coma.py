@@ -115,3 +115,48 @@ def test_trainer_runs_and_learns_signal():
         assert torch.allclose(rel, rew[t], rtol=1e-5, atol=1e-5), t
     r1 = tr.rollout(episodes=torch.arange(64) + 100)
     assert torch.isfinite(r1)
+
+
+def test_best_model_rule_and_scalar_log(tmp_path):
+    """missions/coma_mission.py:425-435: running mean over ALL returns so far, compared once `patience` exist."""
+    import json
+
+    from ipp_marl_b200 import mission
+
+    best = mission.BestModel(patience=3, path=None)
+    took = [best.offer(r, None) for r in (1.0, 5.0, 0.0, 6.0, -10.0, 20.0)]
+    # running means: 1, 3, 2, 3, 0.4, 3.67 -> first comparison at the 3rd return
+    assert took == [False, False, True, True, False, True]
+    assert abs(best.best - 22.0 / 6.0) < 1e-12
+    log = mission.ScalarLog(str(tmp_path))
+    log.add_scalar("trainReturn/Episode/mean", 1.5, 7)
+    log.close()
+    rows = [json.loads(x) for x in open(tmp_path / "scalars.jsonl")]
+    assert rows == [{"tag": "trainReturn/Episode/mean", "value": 1.5, "step": 7}]
+
+
+@pytest.mark.gpu
+def test_mission_loop_runs_logs_and_checkpoints(tmp_path):
+    """The batched training mission: updates, the reference's scalar tags, greedy evaluation with the entropy / F1
+    metrics, best-model checkpoint that loads back into an ActorNet."""
+    import json
+
+    from ipp_marl_b200 import BatchedIPPEnv, mission
+    from tests.helpers import load_kats
+
+    params = load_kats()["synthetic50"]["params"]
+    params["experiment"]["missions"]["patience"] = 2
+    env = BatchedIPPEnv(params, 16, device="cuda:0")
+    tr = coma.COMATrainer(env, params, minibatch=512, data_passes=1, compute_dtype=torch.float32)
+    m = mission.COMAMission(tr, str(tmp_path), eval_every=2)
+    best = m.execute(3)
+    assert np.isfinite(best) and m.training_step_idx == 3 and m.environment_step_idx == 3 * 15 * 4 * 16
+    tags = {json.loads(x)["tag"] for x in open(tmp_path / "scalars.jsonl")}
+    for t in ("trainReturn/Episode/mean", "trainRewards/Episode/std", "trainReturn/Relative(used)/Episode/max",
+              "evalReturn/Episode/mean", "evalMetrics/entropy_final", "evalMetrics/f1_final", "Training/critic_loss",
+              "trainActions/0", "trainAltitudes/15"):
+        assert t in tags, t
+    actor = coma.ActorNet()
+    actor.load_state_dict(torch.load(tmp_path / "best_model.pth", map_location="cpu"))
+    ent = [json.loads(x) for x in open(tmp_path / "scalars.jsonl") if "entropy_final" in x][0]["value"]
+    assert 0.0 < ent <= 1.0

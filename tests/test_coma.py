@@ -160,3 +160,51 @@ def test_mission_loop_runs_logs_and_checkpoints(tmp_path):
     actor.load_state_dict(torch.load(tmp_path / "best_model.pth", map_location="cpu"))
     ent = [json.loads(x) for x in open(tmp_path / "scalars.jsonl") if "entropy_final" in x][0]["value"]
     assert 0.0 < ent <= 1.0
+
+
+def test_flat_grad_allreduce_gloo(tmp_path):
+    """The only collective of the path: ONE flattened all-reduce (mean) of a network's
+    gradients per optimizer step.  world_size-2 gloo run on CPU: both ranks end with the mean of the two ranks'
+    gradients, parameter by parameter, and identical weights after the optimizer step."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(r"""
+import json, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from ipp_marl_b200 import coma
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)                      # identical initial weights on every rank (COMATrainer does the same)
+net = coma.CriticNet()
+sync = coma.FlatGradAllReduce(net)
+opt = torch.optim.SGD(net.parameters(), lr=0.1)
+torch.manual_seed(100 + rank)             # different data per rank
+x = torch.rand(4, 11, 11, 12)
+loss = net(x).square().mean()
+loss.backward()
+local = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in net.parameters()]  # fc2 is unused
+sync()
+ok = True
+for p, g in zip(net.parameters(), local):
+    both = [torch.zeros_like(g) for _ in range(world)]
+    dist.all_gather(both, g)
+    ok = ok and torch.allclose(p.grad, sum(both) / world, rtol=1e-6, atol=1e-8)
+opt.step()
+w = torch.cat([p.detach().flatten() for p in net.parameters()])
+ws = [torch.zeros_like(w) for _ in range(world)]
+dist.all_gather(ws, w)
+if rank == 0:
+    print(json.dumps({"ok": bool(ok), "same_weights": bool(torch.equal(ws[0], ws[1])), "n": int(sync.flat.numel())}))
+dist.destroy_process_group()
+""" % root)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29641", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out == {"ok": True, "same_weights": True, "n": 2307846}

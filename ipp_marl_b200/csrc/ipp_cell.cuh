@@ -65,9 +65,6 @@ __device__ __forceinline__ float f4_get(const F4& v, int c) {
   return c == 0 ? v.lo.x : (c == 1 ? v.lo.y : (c == 2 ? v.hi.x : v.hi.y));
 }
 __device__ __forceinline__ F4 f4_splat(float s) { return F4{make_float2(s, s), make_float2(s, s)}; }
-__device__ __forceinline__ F4 f4_fma(const F4 a, const F4 b, const F4 c) {
-  return F4{__ffma2_rn(a.lo, b.lo, c.lo), __ffma2_rn(a.hi, b.hi, c.hi)};
-}
 __device__ __forceinline__ F4 f4_mul(const F4 a, const F4 b) {
   return F4{__fmul2_rn(a.lo, b.lo), __fmul2_rn(a.hi, b.hi)};
 }

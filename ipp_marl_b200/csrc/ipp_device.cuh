@@ -66,26 +66,6 @@ __device__ __forceinline__ Meas make_meas(const ipp_config& c, const int32_t* po
   return m;
 }
 
-// Flat quad range [q_lo, q_hi] spanned by the clipped footprint of an agent at `pos` (q_lo > q_hi: empty).
-__device__ __forceinline__ void footprint_quads(const ipp_config& c, const int32_t* pos, int32_t& q_lo,
-                                                int32_t& q_hi) {
-  const int32_t ix = clampi(pos[0] / c.spacing, 0, c.px - 1), iy = clampi(pos[1] / c.spacing, 0, c.py - 1);
-  const int32_t iz = clampi(pos[2] / c.spacing - c.min_altitude / c.spacing, 0, c.n_alt - 1);
-  const int32_t cx = c.cell_x[ix], cy = c.cell_y[iy], rx = c.radius_x[iz], ry = c.radius_y[iz];
-  const int32_t xl = clampi(cx - rx, 0, c.gx - 1), xr = clampi(cx + rx, 0, c.gx - 1);
-  const int32_t yu = clampi(cy - ry, 0, c.gy - 1), yd = clampi(cy + ry, 0, c.gy - 1);
-  q_lo = 1;
-  q_hi = 0;
-  if (xr > xl && yd > yu) {
-    q_lo = (xl * c.gy + yu) >> 2;
-    q_hi = ((xr - 1) * c.gy + yd - 1) >> 2;
-  }
-}
-
-__device__ __forceinline__ bool in_rect(const Meas& m, int32_t x, int32_t y) {
-  return (uint32_t)(x - m.xl) < (uint32_t)(m.xr - m.xl) && (uint32_t)(y - m.yu) < (uint32_t)(m.yd - m.yu);
-}
-
 // 4-bit footprint mask of a quad.  Cells c0..c0+3 lie in row x0 from column y0 (n0 = cells before
 // the row wraps, 1..4) and, when n0 < 4, continue in row x0+1 from column 0 (requires gy >= 4).
 __device__ __forceinline__ uint32_t rect_mask4(const Meas& m, int32_t x0, int32_t y0, int32_t n0) {

@@ -37,7 +37,7 @@ extern "C" {
 #define IPP_MAX_ALT 8
 #define IPP_MAX_LATTICE 128
 #define IPP_N_ACTIONS 6
-#define IPP_FLAG_QUADS 640 /* cells of a map are flagged in segments of 640 quads (2560 cells): ipp_state.map_flags */
+#define IPP_FLAG_QUADS 640 /* ipp_state.map_flags: one 32-bit word per (local map, segment of 640 quads), one bit per 32-quad tile */
 
 typedef enum ipp_status {
   IPP_OK = 0,
@@ -92,12 +92,13 @@ typedef struct ipp_state {
                        /* (4-cell quad, agent): low nibble = cell inside the agent's latest footprint,   */
                        /* high nibble = cell measured as occupied.  Half (t & 1) holds the measurements  */
                        /* communicated at step t, the other half receives those taken after the moves.   */
-  uint8_t* map_flags;  /* [n_envs, n_seg, 16] (byte i of a 16-byte record = local map i; 16-byte aligned)       */
-                       /* bookkeeping of the reference's lazily applied clamp                                   */
-                       /* (mapping/mappings.py:110-111 clamps a map only when the next update reads it): != 0    */
-                       /* means "this segment of the local map may hold odds outside [o_min, o_max]", so the    */
-                       /* next fuse pass must clamp all of it; 0 lets the kernels touch only footprint cells.  */
-                       /* Conservative (a set flag is always safe); written by reset / step / act.             */
+  uint32_t* map_flags; /* [n_envs, n_seg, 8] (word i of a 32-byte record = local map i; 16-byte aligned):           */
+                       /* bookkeeping of the reference's lazily applied clamp (mapping/mappings.py:110-111 clamps a */
+                       /* map only when the next update reads it).  Bit t of a word: tile t (32 quads = 128 cells)  */
+                       /* of this 640-quad segment of the local map may hold odds outside [o_min, o_max], so the    */
+                       /* next fuse pass must clamp all of that tile; a clear bit lets the kernels touch only the   */
+                       /* footprint cells of the tile.  Conservative (a set bit is always safe); written by reset / */
+                       /* step / act.                                                                               */
 } ipp_state;
 
 /* Per-step inputs / outputs (device pointers; any output may be NULL). */

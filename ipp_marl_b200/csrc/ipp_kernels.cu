@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   if (tid < 4 * A) {  // the env's record from the plan kernel (comm bits, LUT rows)
     reinterpret_cast<uint32_t*>(&s_meta)[tid] = step_meta[(int64_t)b * 4 * A + tid];
   } else if (tid < 5 * A) {
-    s_dirty[tid - 4 * A] = st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + (tid - 4 * A)];
+    s_dirty[tid - 4 * A] = st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 8 + (tid - 4 * A)];
     s_bad[tid - 4 * A] = 0u;
   }
   __syncthreads();
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
 #pragma unroll
   for (int i = 0; i < A; ++i) {
     const uint32_t en = s_meta.comm[i];
-    const bool all = en != 0u && (s_dirty[i] != 0u || !kout_one);
+    const bool all = en != 0u && (((s_dirty[i] >> (tid >> 5)) & 1u) != 0u || !kout_one);  // warp = tile
     if (have && (all || ((in_prev & s_meta.comm4[i]) | (nw.byte(i) & 0xFu)) != 0u)) {
       mine |= 1u << i;
       l4[i] = __ldcs(reinterpret_cast<const float4*>(loc + (int64_t)i * stride));
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
 #pragma unroll
   for (int i = 0; i < A; ++i) {
     if (!((mine >> i) & 1u)) continue;
-    if (local_quad_lut<A, DO_OWN>(cfg, s_meta, i, cw, nw.byte(i), lut, l4[i])) s_bad[i] = 1u;
+    if (local_quad_lut<A, DO_OWN>(cfg, s_meta, i, cw, nw.byte(i), lut, l4[i])) atomicOr(&s_bad[i], 1u << (tid >> 5));
     __stcs(reinterpret_cast<float4*>(loc + (int64_t)i * stride), l4[i]);
   }
 
@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   } else if (tid >= 32 && tid < 32 + A) {
     // new range flag: some result left the range, or nothing clamped an already flagged map
     const int i = tid - 32;
-    const bool keep = s_meta.comm[i] == 0u && s_dirty[i] != 0u;
-    st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + i] = (uint8_t)((s_bad[i] != 0u || keep) ? 1 : 0);
+    // a fuse pass clamped every tile it had to (flagged tiles are processed densely): only this step's results can
+    // be out of range; without a fuse pass the old bits stay
+    st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 8 + i] = s_bad[i] | (s_meta.comm[i] == 0u ? s_dirty[i] : 0u);
   }
 }
 
@@ -424,8 +425,8 @@ __global__ void __launch_bounds__(256)
       const F4 o = f4_from(*reinterpret_cast<const float4*>(lp));
       const F4 upd = f4_select(own, f4_mul(f4_clamp(o, cfg.o_min, cfg.o_max), f4_from(lut[s_row[i] + byte])), o);
       *reinterpret_cast<float4*>(lp) = f4_to(upd);
-      if (f4_out_of_range(upd, cfg.o_min, cfg.o_max))  // same-value stores from several threads: benign
-        st.map_flags[((int64_t)b * cfg.n_seg + q / IPP_FLAG_QUADS) * 16 + i] = 1;
+      if (f4_out_of_range(upd, cfg.o_min, cfg.o_max))
+        atomicOr(&st.map_flags[((int64_t)b * cfg.n_seg + q / IPP_FLAG_QUADS) * 8 + i], 1u << ((q % IPP_FLAG_QUADS) >> 5));
     }
   }
 }
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__
                                                          const uint32_t* __restrict__ episodes,
                                                          int32_t* __restrict__ pos_out,
                                                          int32_t* __restrict__ gt_params,
-                                                         uint8_t* __restrict__ flags) {
+                                                         uint32_t* __restrict__ flags) {
   const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t A = cfg.n_agents;
   if (idx >= cfg.n_envs * (A + 1)) return;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__
       const bool in_range = o * cfg.k_hi[iz] <= cfg.o_max && o * cfg.k_hi[iz] >= cfg.o_min &&
                             o * cfg.k_lo[iz] <= cfg.o_max && o * cfg.k_lo[iz] >= cfg.o_min &&
                             to_odds(cfg.prior) == o;
-      for (int32_t sgm = 0; sgm < cfg.n_seg; ++sgm) flags[((int64_t)b * cfg.n_seg + sgm) * 16 + a] = in_range ? 0 : 1;
+      for (int32_t sgm = 0; sgm < cfg.n_seg; ++sgm) flags[((int64_t)b * cfg.n_seg + sgm) * 8 + a] = in_range ? 0u : 0xFFFFFFFFu;
     }
   } else {
     mt.seed(ep);  // np.random.seed(episode): ground_truths.py:43

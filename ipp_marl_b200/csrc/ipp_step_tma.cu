@@ -37,9 +37,9 @@ namespace ipp {
 template <int A>
 struct alignas(16) StageMeta {
   alignas(16) EnvMeta<A> env;     // bulk-copied: the env's record written by the plan kernel (16 A bytes)
-  alignas(16) uint8_t dirty[16];  // bulk-copied: range flags of the local maps' segment on entry (map_flags record)
-  int32_t b, chunk, nq;
-  uint32_t bad;                   // bit i: a tile task's results for local map i left [o_min, o_max]
+  alignas(16) uint32_t dirty[8];  // bulk-copied: per local map, the tiles flagged "may be out of range" (map_flags)
+  int32_t b, chunk, nq, pad;
+  uint32_t bad[8];                // per local map, the tiles whose results left [o_min, o_max] in this step
 };
 
 static_assert(TMA_QPC == IPP_FLAG_QUADS, "one range flag per (local map, work item)");
@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       }
 #pragma unroll 1
       for (int i = 0; i < A; ++i) {
-        // new range flag: some result left the range, or nothing clamped an already flagged map
-        const bool keep = sm.env.comm[i] == 0u && sm.dirty[i] != 0u;
-        st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 16 + i] = (uint8_t)((((sm.bad >> i) & 1u) != 0u || keep) ? 1 : 0);
+        // new tile flags: a fuse pass clamped every tile it had to (flagged tiles are processed densely), so only
+        // this step's results can be out of range; without a fuse pass the old bits stay
+        st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 8 + i] = sm.bad[i] | (sm.env.comm[i] == 0u ? sm.dirty[i] : 0u);
       }
       ptx::mbar_arrive(env_done + 8u * es);
     }
@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       meta[es].b = b;
       meta[es].chunk = chunk;
       meta[es].nq = nq;
-      meta[es].bad = 0u;
+#pragma unroll
+      for (int i = 0; i < A; ++i) meta[es].bad[i] = 0u;
       const uint32_t efull = env_full + 8u * es;
       const uint32_t code_bytes = ((uint32_t)nq * AP + 15u) & ~15u;
       const uint32_t map_bytes = (uint32_t)nq * 16u;
@@ -159,9 +160,9 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       const int64_t code0 = (int64_t)chunk * QPC * AP;
       // ONE barrier phase per item: armed with the byte count of everything the item needs before the first copy
       // is issued, so it completes exactly when the last byte has landed
-      ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u) + 16u * A + 16u + (A + 1) * map_bytes);
+      ptx::mbar_arrive_expect_tx(efull, code_bytes * (DO_OWN ? 2u : 1u) + 16u * A + 32u + (A + 1) * map_bytes);
       ptx::bulk_load(ptx::smem_u32(&meta[es].env), step_meta + (int64_t)b * 4 * A, 16u * A, efull);
-      ptx::bulk_load(ptx::smem_u32(&meta[es].dirty[0]), st.map_flags + ((int64_t)b * cfg.n_seg + chunk) * 16, 16u, efull);
+      ptx::bulk_load(ptx::smem_u32(&meta[es].dirty[0]), st.map_flags + ((int64_t)b * cfg.n_seg + chunk) * 8, 32u, efull);
       ptx::bulk_load(edst, st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride + code0, code_bytes,
                      efull);
       if (DO_OWN)
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     uint64_t en_bits;
     {
       bool a_l = false;
-      if (lane < A) a_l = sm.env.comm[lane] != 0u && (sm.dirty[lane] != 0u || !kout_one);
+      if (lane < A) a_l = sm.env.comm[lane] != 0u && (((sm.dirty[lane] >> tile) & 1u) != 0u || !kout_one);
       all_mask = __ballot_sync(0xFFFFFFFFu, a_l);
       const int p0 = lane, p1 = lane + 32;
       const bool b0 = p0 < A * A && ((sm.env.comm[p0 / A] >> (p0 % A)) & 1u) != 0u;
@@ -305,7 +306,9 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
       double* r = red + (size_t)es * 2 * NT;
       r[tile] = (double)s1;
       r[NT + tile] = (double)s2;
-      if (bad != 0u) atomicOr(&sm.bad, bad);
+#pragma unroll
+      for (int i = 0; i < A; ++i)
+        if ((bad >> i) & 1u) atomicOr(&sm.bad[i], 1u << tile);
     }
     __syncwarp();  // every lane has read its quads out of the slots
     if (lane == 0) ptx::mbar_arrive(env_tiles + 8u * es);

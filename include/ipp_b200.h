@@ -98,7 +98,8 @@ typedef struct ipp_state {
                        /* of this 640-quad segment of the local map may hold odds outside [o_min, o_max], so the    */
                        /* next fuse pass must clamp all of that tile; a clear bit lets the kernels touch only the   */
                        /* footprint cells of the tile.  Conservative (a set bit is always safe); written by reset / */
-                       /* step / act.                                                                               */
+                       /* step / act.  A caller that writes odds into local_maps itself must set the words of the  */
+                       /* maps it touched to 0xFFFFFFFF.                                                            */
 } ipp_state;
 
 /* Per-step inputs / outputs (device pointers; any output may be NULL). */

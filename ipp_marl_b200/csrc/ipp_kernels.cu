@@ -40,112 +40,157 @@ __device__ __forceinline__ int32_t kth_set_bit(uint32_t m, int32_t k) {
   return -1;
 }
 
-// Sequential masks / action choice / moves of one env (one thread; agents act in id order and agent i
-// sees the NEW positions of agents < i: agent/agent.py:73-104, coma_wrapper.py:97-104).
-__device__ void plan_moves(const ipp_config& cfg, const int32_t b, const uint32_t ep, const ipp_step_io& io,
-                           const int32_t t, const bool do_comm, const bool do_move, int32_t (*npos)[3],
-                           uint32_t* __restrict__ step_meta) {
+// Masks / action choice / moves of one env by a GROUP of lanes, lane `a` of the group = agent a (lanes a >= A and the
+// lanes of envs beyond the batch only keep the warp converged).  Everything that does not depend on the other
+// agents' moves runs in parallel — comm-matrix row (agent/communication_log.py:39-58: one uniform draw per ordered
+// pair, used or not), bounds mask, the agent's random number, its policy probabilities — then the agents take their
+// turns in id order, because agent i sees the NEW positions of agents < i (agent/agent.py:73-104,
+// coma_wrapper.py:97-104) and the collision rules are order dependent (action_space.py:328-344).
+struct PlanShared {
+  int32_t pos[IPP_MAX_AGENTS][3];   // positions at the start of the step
+  int32_t nidx[IPP_MAX_AGENTS][2];  // lattice indices after the move
+  uint32_t stuck;
+};
+
+__device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const bool env_ok, const int a,
+                                 const ipp_step_io& io, const ipp_state& st, const int32_t t, const bool do_comm,
+                                 const bool do_move, PlanShared& sh, int32_t (*npos)[3],
+                                 uint32_t* __restrict__ step_meta) {
   const int32_t A = cfg.n_agents;
-  int32_t pos[IPP_MAX_AGENTS][3];
-  int32_t ix[IPP_MAX_AGENTS], iy[IPP_MAX_AGENTS], nix[IPP_MAX_AGENTS], niy[IPP_MAX_AGENTS];  // lattice indices
-  for (int32_t a = 0; a < A; ++a) {
-    for (int32_t d = 0; d < 3; ++d) pos[a][d] = io.pos_in[((int64_t)b * A + a) * 3 + d];
-    ix[a] = pos[a][0] / cfg.spacing;
-    iy[a] = pos[a][1] / cfg.spacing;
-  }
-  uint32_t comm_rows[IPP_MAX_AGENTS];
-  for (int32_t a = 0; a < A; ++a) comm_rows[a] = 0u;
-  if (do_comm && io.comm_out != nullptr) {
-    // comm matrix: agent/communication_log.py:39-58 (one uniform draw per ordered pair, used or not, :46)
-    for (int32_t i = 0; i < A; ++i) {
-      const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)i, (uint32_t)t, PURPOSE_COMM);
-      uint32_t row = 0;
-      for (int32_t j = 0; j < A; ++j) {
-        const int32_t dx = pos[i][0] - pos[j][0], dy = pos[i][1] - pos[j][1], dz = pos[i][2] - pos[j][2];
-        const int32_t d2 = dx * dx + dy * dy + dz * dz;
-        const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;
-        const bool ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
-        row |= (ok ? 1u : 0u) << j;
-      }
-      io.comm_out[(int64_t)b * A + i] = (uint8_t)row;
-      comm_rows[i] = row;
+  const bool live = env_ok && a < A;
+  int32_t p[3] = {0, 0, 0};
+  uint32_t ep = 0;
+  if (live) {
+    ep = st.episodes[b];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      p[d] = io.pos_in[((int64_t)b * A + a) * 3 + d];
+      sh.pos[a][d] = p[d];
     }
+    if (a == 0) sh.stuck = 0u;
   }
-  if (!do_move) {  // ipp_observe: the map kernel fuses only
-    if (do_comm) write_env_meta(cfg, step_meta + (int64_t)b * 4 * A, comm_rows, pos, pos, false);
-    return;
-  }
-  uint32_t stuck = 0;
-  for (int32_t a = 0; a < A; ++a) {
-    const uint32_t bounds = bounds_mask(cfg, pos[a]);
-    uint32_t m = bounds;
-    // One already-moved lower-id agent j against a: every rule is guarded by "more than one action still
-    // allowed", evaluated before the zeroing (action_space.py:328-344) => order dependent.
-    for (int32_t j = 0; j < a; ++j) {
-      const int32_t dx = nix[j] - ix[a], dy = niy[j] - iy[a];
-      if (dx == 0 && dy == 0 && __popc(m) > 1) m &= ~((1u << 0) | (1u << 5));
-      if (dx == -1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 1);
-      if (dx == 0 && dy == -1 && __popc(m) > 1) m &= ~(1u << 2);
-      if (dx == 0 && dy == 1 && __popc(m) > 1) m &= ~(1u << 3);
-      if (dx == 1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 4);
+  __syncwarp();
+  uint32_t* rec = step_meta + (int64_t)b * 4 * A;  // this env's record for the map kernels (EnvMeta field order)
+  if (live && do_comm && io.comm_out != nullptr) {
+    const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)a, (uint32_t)t, PURPOSE_COMM);
+    uint32_t row = 0;
+    for (int32_t j = 0; j < A; ++j) {
+      const int32_t dx = p[0] - sh.pos[j][0], dy = p[1] - sh.pos[j][1], dz = p[2] - sh.pos[j][2];
+      const int32_t d2 = dx * dx + dy * dy + dz * dz;
+      const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;
+      const bool ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
+      row |= (ok ? 1u : 0u) << j;
     }
-    const int32_t cnt = __popc(m);
-    int32_t act = -1;
+    io.comm_out[(int64_t)b * A + a] = (uint8_t)row;
+    const uint32_t en = row & ~(1u << a);  // own measurement already used
+    uint32_t en4 = 0;
+    for (int j = 0; j < A; ++j)
+      if ((en >> j) & 1u) en4 |= 0xFu << (4 * j);
+    rec[a] = en;
+    rec[A + a] = en4;
+    rec[2 * A + a] = lut_row(cfg, p);
+    if (!do_move) rec[3 * A + a] = 0u;  // ipp_observe: the map kernel fuses only
+  }
+  if (!do_move) return;
+
+  // ---- per-agent preparation (independent of the other agents' moves) ----
+  const uint32_t bounds = bounds_mask(cfg, p);
+  const int32_t ix = p[0] / cfg.spacing, iy = p[1] / cfg.spacing;
+  int32_t injected = -1;
+  float u = 0.0f;
+  float pk[IPP_N_ACTIONS];
+#pragma unroll
+  for (int k = 0; k < IPP_N_ACTIONS; ++k) pk[k] = 0.0f;
+  if (live) {
     if (io.actions_in != nullptr) {
-      // injected action (the reference's policy never emits a masked one): an action that would
-      // leave the lattice is turned into "stay" and flagged, so positions always index the tables
-      act = io.actions_in[(int64_t)b * A + a];
-      if (act < -1 || act >= IPP_N_ACTIONS) act = -1;
-      if (act >= 0 && !((bounds >> act) & 1u)) {
-        act = -1;
-        stuck |= 2u;
-      }
-    } else if (cnt > 0) {
-      const uint32_t key = stream_key(cfg.seed, ep, a, (uint32_t)t, PURPOSE_ACTION);
-      const float u = (float)(cell_hash(key, 0u) >> 8) * (1.0f / 16777216.0f);
+      injected = io.actions_in[(int64_t)b * A + a];
+    } else {
+      const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)a, (uint32_t)t, PURPOSE_ACTION);
+      u = (float)(cell_hash(key, 0u) >> 8) * (1.0f / 16777216.0f);
       if (io.probs_in != nullptr) {
-        // actor/network.py:63-66,90-96: probs * mask, then multinomial (train) or argmax (eval)
-        float w[IPP_N_ACTIONS];
-        float total = 0.0f;
-        for (int32_t k = 0; k < IPP_N_ACTIONS; ++k) {
-          const float pk = io.probs_in[((int64_t)b * A + a) * IPP_N_ACTIONS + k];
-          w[k] = ((m >> k) & 1u) ? fmaxf(pk, 0.0f) : 0.0f;
-          total += w[k];
+#pragma unroll
+        for (int k = 0; k < IPP_N_ACTIONS; ++k) pk[k] = io.probs_in[((int64_t)b * A + a) * IPP_N_ACTIONS + k];
+      }
+    }
+  }
+  // ---- the agents' turns, in id order ----
+  for (int32_t turn = 0; turn < A; ++turn) {
+    if (live && a == turn) {
+      uint32_t m = bounds;
+      // One already-moved lower-id agent j against a: every rule is guarded by "more than one action still
+      // allowed", evaluated before the zeroing (action_space.py:328-344) => order dependent.
+      for (int32_t j = 0; j < a; ++j) {
+        const int32_t dx = sh.nidx[j][0] - ix, dy = sh.nidx[j][1] - iy;
+        if (dx == 0 && dy == 0 && __popc(m) > 1) m &= ~((1u << 0) | (1u << 5));
+        if (dx == -1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 1);
+        if (dx == 0 && dy == -1 && __popc(m) > 1) m &= ~(1u << 2);
+        if (dx == 0 && dy == 1 && __popc(m) > 1) m &= ~(1u << 3);
+        if (dx == 1 && dy == 0 && __popc(m) > 1) m &= ~(1u << 4);
+      }
+      const int32_t cnt = __popc(m);
+      int32_t act = -1;
+      uint32_t stuck = 0;
+      if (io.actions_in != nullptr) {
+        // injected action (the reference's policy never emits a masked one): an action that would
+        // leave the lattice is turned into "stay" and flagged, so positions always index the tables
+        act = injected;
+        if (act < -1 || act >= IPP_N_ACTIONS) act = -1;
+        if (act >= 0 && !((bounds >> act) & 1u)) {
+          act = -1;
+          stuck |= 2u;
         }
-        if (!(total > 0.0f)) {
-          act = kth_set_bit(m, min((int32_t)(u * (float)cnt), cnt - 1));
-        } else if (io.greedy) {
-          float best = -1.0f;
-          for (int32_t k = 0; k < IPP_N_ACTIONS; ++k)
-            if (((m >> k) & 1u) && w[k] > best) { best = w[k]; act = k; }
-        } else {
-          const float target = u * total;
-          float acc = 0.0f;
+      } else if (cnt > 0) {
+        if (io.probs_in != nullptr) {
+          // actor/network.py:63-66,90-96: probs * mask, then multinomial (train) or argmax (eval)
+          float w[IPP_N_ACTIONS];
+          float total = 0.0f;
+#pragma unroll
           for (int32_t k = 0; k < IPP_N_ACTIONS; ++k) {
-            if (w[k] > 0.0f) {
-              act = k;  // last positive weight wins if rounding leaves target >= acc at the end
-              acc += w[k];
-              if (target < acc) break;
+            w[k] = ((m >> k) & 1u) ? fmaxf(pk[k], 0.0f) : 0.0f;
+            total += w[k];
+          }
+          if (!(total > 0.0f)) {
+            act = kth_set_bit(m, min((int32_t)(u * (float)cnt), cnt - 1));
+          } else if (io.greedy) {
+            float best = -1.0f;
+#pragma unroll
+            for (int32_t k = 0; k < IPP_N_ACTIONS; ++k)
+              if (((m >> k) & 1u) && w[k] > best) { best = w[k]; act = k; }
+          } else {
+            const float target = u * total;
+            float acc = 0.0f;
+            bool done = false;
+#pragma unroll
+            for (int32_t k = 0; k < IPP_N_ACTIONS; ++k) {
+              if (!done && w[k] > 0.0f) {
+                act = k;  // last positive weight wins if rounding leaves target >= acc at the end
+                acc += w[k];
+                if (target < acc) done = true;
+              }
             }
           }
+        } else {
+          act = kth_set_bit(m, min((int32_t)(u * (float)cnt), cnt - 1));
         }
-      } else {
-        act = kth_set_bit(m, min((int32_t)(u * (float)cnt), cnt - 1));
       }
+      if (cnt == 0) stuck |= 1u;  // the reference raises here; we stay in place and flag
+      const int32_t ox = (act == 4) - (act == 1), oy = (act == 3) - (act == 2), oz = (act == 0) - (act == 5);
+      sh.nidx[a][0] = ix + ox;
+      sh.nidx[a][1] = iy + oy;
+      int32_t np[3] = {p[0] + ox * cfg.spacing, p[1] + oy * cfg.spacing, p[2] + oz * cfg.spacing};
+#pragma unroll
+      for (int32_t d = 0; d < 3; ++d) {
+        npos[a][d] = np[d];
+        io.pos_out[((int64_t)b * A + a) * 3 + d] = np[d];
+      }
+      if (io.actions_out != nullptr) io.actions_out[(int64_t)b * A + a] = act;
+      if (io.mask_out != nullptr) io.mask_out[(int64_t)b * A + a] = (uint8_t)m;
+      if (stuck != 0u) sh.stuck |= stuck;  // only this lane of the env is active in this turn
+      if (do_comm) rec[3 * A + a] = lut_row(cfg, np);
     }
-    if (cnt == 0) stuck |= 1u;  // the reference raises here; we stay in place and flag
-    const int32_t ox = (act == 4) - (act == 1), oy = (act == 3) - (act == 2), oz = (act == 0) - (act == 5);
-    nix[a] = ix[a] + ox;
-    niy[a] = iy[a] + oy;
-    npos[a][0] = pos[a][0] + ox * cfg.spacing;
-    npos[a][1] = pos[a][1] + oy * cfg.spacing;
-    npos[a][2] = pos[a][2] + oz * cfg.spacing;
-    for (int32_t d = 0; d < 3; ++d) io.pos_out[((int64_t)b * A + a) * 3 + d] = npos[a][d];
-    if (io.actions_out != nullptr) io.actions_out[(int64_t)b * A + a] = act;
-    if (io.mask_out != nullptr) io.mask_out[(int64_t)b * A + a] = (uint8_t)m;
+    __syncwarp();
   }
-  if (io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)stuck;
-  if (do_comm) write_env_meta(cfg, step_meta + (int64_t)b * 4 * A, comm_rows, pos, npos, true);
+  if (live && a == 0 && io.stuck_out != nullptr) io.stuck_out[b] = (uint8_t)sh.stuck;
 }
 
 // Write the code byte of quad q (cells 4q..4q+3, first cell in grid row x) for measurement m.
@@ -210,8 +255,8 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
 constexpr int PLAN_WARPS = 16;  // warps per block: one env per warp in phase 2
 constexpr int PLAN_ENVS = 16;   // envs per block
 
-// Phase 1: warp 0 plans the moves of the block's 16 envs, one LANE per env (the sequential-in-agent logic is
-// scalar work: a whole warp per env would idle 31 lanes).
+// Phase 1: the first warp(s) plan the moves of the block's 16 envs, one lane per (env, agent): the parts that do not
+// depend on the other agents' moves in parallel, then the agents' turns in id order (plan_moves_group).
 // Phase 2: one warp per env builds the env's new code row.  When it fits (stage != 0) the row is assembled in
 // SHARED memory next to a staged copy of the ground truth and written out with coalesced 16-byte stores:
 // scattering one byte per (quad, agent) straight to global memory costs one L2 write transaction per byte
@@ -226,15 +271,23 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
   const int32_t A = cfg.n_agents;
   __shared__ int32_t s_npos[PLAN_ENVS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
-  if (warp == 0 && lane < n_here) {
+  __shared__ PlanShared s_plan[PLAN_ENVS];
+  // Phase 1: groups of W lanes (W = power of two >= A), one lane per agent, W / 2 warps for the block's 16 envs
+  int W = 1;
+  while (W < A) W <<= 1;
+  if (warp < max(1, W >> 1)) {
+    const int e = (warp * 32 + lane) / W, a = lane & (W - 1);
+    const bool env_ok = e < n_here;
+    const int es = min(e, PLAN_ENVS - 1);
     if (stage & 2) {  // debug: no planning, agents stay
-      for (int a = 0; a < A; ++a)
+      if (env_ok && a < A)
         for (int d = 0; d < 3; ++d) {
-          s_npos[lane][a][d] = io.pos_in[((int64_t)(e0 + lane) * A + a) * 3 + d];
-          io.pos_out[((int64_t)(e0 + lane) * A + a) * 3 + d] = s_npos[lane][a][d];
+          s_npos[es][a][d] = io.pos_in[((int64_t)(e0 + es) * A + a) * 3 + d];
+          io.pos_out[((int64_t)(e0 + es) * A + a) * 3 + d] = s_npos[es][a][d];
         }
     } else {
-      plan_moves(cfg, e0 + lane, st.episodes[e0 + lane], io, t, do_comm != 0, do_move != 0, s_npos[lane], step_meta);
+      plan_moves_group(cfg, e0 + es, env_ok, a, io, st, t, do_comm != 0, do_move != 0, s_plan[es], s_npos[es],
+                       step_meta);
     }
   }
   if (!do_move) return;

@@ -252,8 +252,9 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
   }
 }
 
-constexpr int PLAN_WARPS = 16;  // warps per block: one env per warp in phase 2
-constexpr int PLAN_ENVS = 16;   // envs per block
+constexpr int PLAN_WARPS = 16;     // warps per block: one env per warp and round in phase 2
+constexpr int PLAN_ENVS = 16;      // envs per block (default)
+constexpr int PLAN_MAX_ENVS = 32;  // most envs per block (the launcher picks: see launch_plan)
 
 // Phase 1: the first warp(s) plan the moves of the block's 16 envs, one lane per (env, agent): the parts that do not
 // depend on the other agents' moves in parallel, then the agents' turns in id order (plan_moves_group).
@@ -263,22 +264,23 @@ constexpr int PLAN_ENVS = 16;   // envs per block
 // (7.4 M per launch at 8192 envs — that, not the arithmetic, bounded earlier versions of this kernel).
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
-                const int32_t do_comm, const int32_t do_move, const int32_t stage, uint32_t* __restrict__ step_meta) {
+                const int32_t do_comm, const int32_t do_move, const int32_t stage, uint32_t* __restrict__ step_meta,
+                const int32_t epb) {
   extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride + code_stride] when stage
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int32_t e0 = blockIdx.x * PLAN_ENVS;
-  const int32_t n_here = min(PLAN_ENVS, cfg.n_envs - e0);
+  const int32_t e0 = blockIdx.x * epb;  // epb envs per block, 16 <= epb <= PLAN_MAX_ENVS
+  const int32_t n_here = min(epb, cfg.n_envs - e0);
   const int32_t A = cfg.n_agents;
-  __shared__ int32_t s_npos[PLAN_ENVS][IPP_MAX_AGENTS][3];
+  __shared__ int32_t s_npos[PLAN_MAX_ENVS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
-  __shared__ PlanShared s_plan[PLAN_ENVS];
-  // Phase 1: groups of W lanes (W = power of two >= A), one lane per agent, W / 2 warps for the block's 16 envs
+  __shared__ PlanShared s_plan[PLAN_MAX_ENVS];
+  // Phase 1: groups of W lanes (W = power of two >= A), one lane per agent, in the block's first warps
   int W = 1;
   while (W < A) W <<= 1;
-  if (warp < max(1, W >> 1)) {
+  if (warp < (epb * W + 31) / 32) {
     const int e = (warp * 32 + lane) / W, a = lane & (W - 1);
     const bool env_ok = e < n_here;
-    const int es = min(e, PLAN_ENVS - 1);
+    const int es = min(e, PLAN_MAX_ENVS - 1);
     if (stage & 2) {  // debug: no planning, agents stay
       if (env_ok && a < A)
         for (int d = 0; d < 3; ++d) {
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
     const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
     uint8_t* row = reinterpret_cast<uint8_t*>(grow);
     if (stage & 1) {
-      if (e != warp) {  // later rounds (PLAN_ENVS > PLAN_WARPS): stage this env's ground truth now
+      if (e != warp) {  // later rounds (more envs than warps): stage this env's ground truth now
         const uint4* src = reinterpret_cast<const uint4*>(gt);
         uint4* dst = reinterpret_cast<uint4*>(my_smem);
         for (int32_t i = lane; i < (cfg.gt_stride >> 4); i += 32) dst[i] = src[i];
@@ -693,8 +695,25 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  plan_kernel<<<(cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm,
-                                                                                      do_move, stage_gt | dbg, step_meta);
+  // Envs per block: two 80 KB blocks fit an SM, so the GPU runs 2 * n_sm blocks at a time.  When the batch needs
+  // more than one such wave of 16-env blocks but fits ONE wave of <= 32-env blocks, use the larger blocks: the
+  // sequential phase 1 is then paid once instead of once per wave and no SM idles in a partial second wave.
+  static int n_slots = 0;
+  if (n_slots == 0) {
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    n_slots = 2 * (n_sm > 0 ? n_sm : 1);
+  }
+  int epb = PLAN_ENVS;
+  if ((cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS > n_slots && (cfg.n_envs + n_slots - 1) / n_slots <= PLAN_MAX_ENVS)
+    epb = (cfg.n_envs + n_slots - 1) / n_slots;
+  if (const char* v = getenv("IPP_PLAN_EPB")) {  // A/B aid
+    const int e = atoi(v);
+    if (e >= 1 && e <= PLAN_MAX_ENVS) epb = e;
+  }
+  plan_kernel<<<(cfg.n_envs + epb - 1) / epb, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm, do_move,
+                                                                         stage_gt | dbg, step_meta, epb);
   return cudaGetLastError();
 }
 

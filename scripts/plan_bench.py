@@ -7,6 +7,9 @@ params = json.load(open(os.path.join(sys.path[0], "tests/golden/kats.json")))["s
 params["experiment"]["missions"]["n_agents"] = 4
 env = BatchedIPPEnv(params, 8192, device="cuda:0")
 for dbg in sys.argv[1:] or ["0", "4", "2"]:
+    if dbg.startswith("e"):  # e16 / e28: envs per block override
+        os.environ["IPP_PLAN_EPB"] = dbg[1:]
+        dbg = "0"
     os.environ["IPP_PLAN_DEBUG"] = dbg
     evs = []
     def hook(phase, before):
@@ -17,4 +20,4 @@ for dbg in sys.argv[1:] or ["0", "4", "2"]:
         for _ in range(15): env.step(_phase_hook=hook)
     torch.cuda.synchronize()
     ms = [evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(30, len(evs) // 2)]
-    print("IPP_PLAN_DEBUG=%s plan kernel mean %.1f us" % (dbg, sum(ms) / len(ms) * 1e3))
+    print("IPP_PLAN_DEBUG=%s EPB=%s plan kernel mean %.1f us" % (dbg, os.environ.get("IPP_PLAN_EPB", "auto"), sum(ms) / len(ms) * 1e3))

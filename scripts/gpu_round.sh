@@ -15,6 +15,6 @@ echo "== ncu full (tma)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_tma -s 20 -c 2 -f -o $OUT/prof_tma_$TAG \
   python bench.py --steps 45 --warmup 15 --no-cpu-baseline > $OUT/ncu_tma_$TAG.log 2>&1
 echo "== ncu full (direct)"
-IPP_STEP_VARIANT=direct timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_dense -s 20 -c 2 -f -o $OUT/prof_direct_$TAG \
+IPP_STEP_VARIANT=direct timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_direct -s 20 -c 2 -f -o $OUT/prof_direct_$TAG \
   python bench.py --steps 45 --warmup 15 --no-cpu-baseline > $OUT/ncu_direct_$TAG.log 2>&1
 ls -la $OUT | tail -20

@@ -339,3 +339,89 @@ class KernelModelEnv:
         self.pos = new_pos
         self.t += 1
         return dict(mask=masks, action=acts)
+
+
+class SparseKernelModelEnv(KernelModelEnv):
+    """The kernels' footprint-sparse processing rule on top of the dense model ("Sparsity
+    without changing results"): a quad (4 cells) of a local map is PROCESSED — taken through the map's whole pass
+    chain — only if some enabled fuse pass or the own update has a cell in it, or if its tile (32 quads) is flagged
+    "may hold odds outside [o_min, o_max]" while a fuse pass (= whole-map clamp) runs; every other quad keeps its
+    bits.  ``flags[b, i, tile]`` is maintained exactly like ``ipp_state.map_flags``.  tests/test_kernel_model.py steps
+    this class next to the dense model and requires bit-identical maps: the CPU-side proof that skipping is exact."""
+
+    TILE_CELLS = 128
+
+    def __init__(self, params, episodes, noiseless=False):
+        super().__init__(params, episodes, noiseless)
+        n_cells = self.tab.gx * self.tab.gy
+        self.n_tiles = (n_cells + self.TILE_CELLS - 1) // self.TILE_CELLS
+        self.flags = self._tile_any(self._out_of_range(self.local_o))  # reset: the t = 0 measurement is one own pass
+        self.processed_pairs = 0
+        self.touched_pairs = 0
+        self.total_pairs = 0
+
+    def _out_of_range(self, o):
+        return (o > self.tab.o_max) | (o < self.tab.o_min)
+
+    def _quads(self, mask):
+        """[..., gx, gy] cell mask -> [..., n_quads] 'some cell of the quad'."""
+        flat = mask.reshape(mask.shape[:-2] + (-1,))
+        pad = (-flat.shape[-1]) % 4
+        if pad:
+            flat = np.concatenate([flat, np.zeros(flat.shape[:-1] + (pad,), bool)], -1)
+        return flat.reshape(flat.shape[:-1] + (-1, 4)).any(-1)
+
+    def _tile_any(self, mask):
+        """[..., gx, gy] cell mask -> [..., n_tiles]."""
+        flat = mask.reshape(mask.shape[:-2] + (-1,))
+        pad = self.n_tiles * self.TILE_CELLS - flat.shape[-1]
+        if pad:
+            flat = np.concatenate([flat, np.zeros(flat.shape[:-1] + (pad,), bool)], -1)
+        return flat.reshape(flat.shape[:-1] + (self.n_tiles, self.TILE_CELLS)).any(-1)
+
+    def _cells_of_quads(self, qmask):
+        """[..., n_quads] -> [..., gx, gy] (every cell of a selected quad)."""
+        n_cells = self.tab.gx * self.tab.gy
+        cells = np.repeat(qmask, 4, axis=-1)[..., :n_cells]
+        return cells.reshape(cells.shape[:-1] + (self.tab.gx, self.tab.gy))
+
+    def step(self, actions=None):
+        A = self.A
+        comm = self.comm()
+        prev = [self._k_of(self.pos[:, j], j, self.t) for j in range(A)]
+        new_pos, masks, acts = self._choose_and_move(actions)
+        new = [self._k_of(new_pos[:, i], i, self.t + 1) for i in range(A)]
+        last = self.glob_o
+        self.glob_o = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])  # global map: dense
+        rel, ab = self._reward(last, self.glob_o)
+        kout_one = bool(self.tab.k_out == F32(1))
+        quads_per_tile = self.TILE_CELLS // 4
+        for i in range(A):
+            passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
+            dense = self._apply(self.local_o[:, i], passes + [(new[i][0], new[i][1], False)])
+            en = np.zeros(self.B, bool)
+            touched = new[i][0].copy()
+            for j in range(A):
+                if j != i:
+                    en |= comm[:, i, j]
+                    touched |= prev[j][0] & comm[:, i, j][:, None, None]
+            tq = self._quads(touched)                                            # [B, n_quads]
+            all_tile = en[:, None] & (self.flags[:, i] | (not kout_one))         # [B, n_tiles]
+            all_q = np.repeat(all_tile, quads_per_tile, axis=1)[:, : tq.shape[1]]
+            proc_q = tq | all_q
+            proc = self._cells_of_quads(proc_q)
+            self.local_o[:, i] = np.where(proc, dense, self.local_o[:, i])
+            bad = self._tile_any(self._out_of_range(self.local_o[:, i]) & proc)
+            self.flags[:, i] = bad | (self.flags[:, i] & ~en[:, None])
+            tile_proc = np.zeros((self.B, self.n_tiles), bool)
+            tile_touch = np.zeros((self.B, self.n_tiles), bool)
+            for tl in range(self.n_tiles):
+                sl = slice(tl * quads_per_tile, (tl + 1) * quads_per_tile)
+                tile_proc[:, tl] = proc_q[:, sl].any(1)
+                tile_touch[:, tl] = tq[:, sl].any(1)
+            self.processed_pairs += int(tile_proc.sum())
+            self.touched_pairs += int(tile_touch.sum())
+            self.total_pairs += tile_proc.size
+        self.pos = new_pos
+        self.t += 1
+        return dict(comm=comm, mask=masks, action=acts, reward_rel=rel, reward_abs=ab)

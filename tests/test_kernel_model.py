@@ -50,3 +50,32 @@ def test_tables_match_reference_geometry():
         for pos, raw, clipped in k["fov"]:
             rect, _ = km._rects(tab, np.array(pos))
             assert rect.tolist() == clipped, pos
+
+
+@pytest.mark.parametrize("tag,n_agents,prior", [("synthetic50", 4, 0.5), ("synthetic50", 3, 0.5), ("synthetic100", 8, 0.5),
+                                                ("synthetic50", 4, 0.4)])
+def test_sparse_processing_rule_is_exact(tag, n_agents, prior):
+    """The kernels process a quad of a local map only if a footprint reaches it or its tile is flagged 'may be out of
+    range' (DESIGN.md section 3).  CPU proof that this never changes a bit: the sparse model equals the dense model at
+    every step, while the flags keep the processed share close to the touched share."""
+    from tests.helpers import load_kats
+
+    params = load_kats()[tag]["params"]
+    params["experiment"]["missions"]["n_agents"] = n_agents
+    params["mapping"]["prior"] = prior
+    params["experiment"]["uav"]["communication_range"] = 20
+    episodes = np.arange(11, 11 + (24 if tag == "synthetic50" else 4))
+    dense = km.KernelModelEnv(params, episodes)
+    sparse = km.SparseKernelModelEnv(params, episodes)
+    for t in range(dense.geo.budget + 1):
+        a = dense.step()
+        b = sparse.step()
+        assert np.array_equal(a["action"], b["action"])
+        assert np.array_equal(dense.local_o, sparse.local_o), t
+        assert np.array_equal(dense.glob_o, sparse.glob_o), t
+    share = sparse.processed_pairs / sparse.total_pairs
+    touched = sparse.touched_pairs / sparse.total_pairs
+    if prior == 0.5:
+        assert share < 0.95 and share - touched < 0.05, (share, touched)  # the flags cost almost nothing
+    else:
+        assert share >= touched  # k_out != 1: every pass multiplies every cell -> dense by construction

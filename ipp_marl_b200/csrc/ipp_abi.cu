@@ -55,6 +55,21 @@ cudaError_t launch_maps(ipp_handle* h, const ipp_state* st, const ipp_step_io& i
                                 do_own, s);
 }
 
+// Every entry point works on the device its handle was created on, whatever the caller's current device is.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const ipp_handle* h) {
+    int cur = -1;
+    if (h != nullptr && cudaGetDevice(&cur) == cudaSuccess && cur != h->device) {
+      prev = cur;
+      cudaSetDevice(h->device);
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 int validate(const ipp_config* c) {
   if (c == nullptr) return IPP_ERR_INVALID_ARG;
   if (c->gx <= 0 || c->gy < 4 || c->n_envs <= 0) return IPP_ERR_INVALID_ARG;  // a quad spans <= 2 rows
@@ -226,6 +241,7 @@ int ipp_get_step_variant(const ipp_handle* h) { return h != nullptr ? h->variant
 int64_t ipp_scratch_bytes(const ipp_handle* h) { return h != nullptr ? h->scratch_bytes + (int64_t)h->fbuf_bytes : 0; }
 
 int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || pos_out == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
@@ -235,6 +251,7 @@ int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream
 
 int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, int32_t phases,
                     void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || io == nullptr || io->pos_in == nullptr || io->pos_out == nullptr || io->pos_in == io->pos_out)
     return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
@@ -255,6 +272,7 @@ int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* i
 int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, const float* probs_host,
                   const int32_t* actions_host, float* reward_rel_host, float* reward_abs_host,
                   int32_t* actions_out_host, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || io == nullptr || (probs_host == nullptr) == (actions_host == nullptr))
     return IPP_ERR_INVALID_ARG;
   if (io->reward_rel == nullptr || io->reward_abs == nullptr || io->actions_out == nullptr) return IPP_ERR_INVALID_ARG;
@@ -298,6 +316,7 @@ int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_
 }
 
 int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || io == nullptr || io->pos_in == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
@@ -311,6 +330,7 @@ int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io
 }
 
 int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || io == nullptr || io->pos_in == nullptr || io->pos_out == nullptr || io->pos_in == io->pos_out)
     return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
@@ -324,6 +344,7 @@ int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io
 
 int ipp_features_actor(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, float* obs_out,
                        void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || io == nullptr || io->pos_in == nullptr || obs_out == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
@@ -335,6 +356,7 @@ int ipp_features_actor(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_
 
 int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int32_t* pos_in, const int32_t* actions,
                         const float* obs_in, float* state_out, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || pos_in == nullptr || actions == nullptr || obs_in == nullptr || state_out == nullptr)
     return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
@@ -346,6 +368,7 @@ int ipp_features_critic(ipp_handle* h, const ipp_state* st, int32_t t, const int
 }
 
 int ipp_export_beliefs(ipp_handle* h, const ipp_state* st, float* local_out, float* global_out, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
@@ -363,6 +386,7 @@ int ipp_export_beliefs(ipp_handle* h, const ipp_state* st, float* local_out, flo
 
 int ipp_ig_plan(ipp_handle* h, const ipp_state* st, const int32_t* pos_in, int32_t communication,
                 int32_t* actions_out, uint8_t* mask_out, double* gains_out, double* util_out, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || pos_in == nullptr || actions_out == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
@@ -372,6 +396,7 @@ int ipp_ig_plan(ipp_handle* h, const ipp_state* st, const int32_t* pos_in, int32
 }
 
 int ipp_eval_metrics(ipp_handle* h, const ipp_state* st, double* entropy_out, double* f1_out, void* stream) {
+  DeviceGuard on_device(h);
   if (h == nullptr || entropy_out == nullptr || f1_out == nullptr) return IPP_ERR_INVALID_ARG;
   int rc = check_state(st);
   if (rc != IPP_OK) return rc;
@@ -403,6 +428,7 @@ int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, 
 
 int ipp_measure(ipp_handle* h, const uint8_t* gt_host, const int32_t* rect, int32_t altitude_m, uint32_t episode,
                 uint32_t agent, uint32_t index, float y_hi, float y_lo, float* out_host) {
+  DeviceGuard on_device(h);
   if (h == nullptr || gt_host == nullptr || rect == nullptr || out_host == nullptr) return IPP_ERR_INVALID_ARG;
   const ipp_config& c = h->cfg;
   if (rect[0] < 0 || rect[1] > c.gy || rect[2] < 0 || rect[3] > c.gx) return IPP_ERR_INVALID_ARG;
@@ -426,6 +452,7 @@ int ipp_measure(ipp_handle* h, const uint8_t* gt_host, const int32_t* rect, int3
 
 int ipp_update_cells(ipp_handle* h, float* x_host, const float* y_host, int32_t y_is_scalar, int64_t n,
                      float* out_host) {
+  DeviceGuard on_device(h);
   if (h == nullptr || x_host == nullptr || y_host == nullptr || out_host == nullptr || n < 0)
     return IPP_ERR_INVALID_ARG;
   if (n == 0) return IPP_OK;
@@ -444,6 +471,7 @@ int ipp_update_cells(ipp_handle* h, float* x_host, const float* y_host, int32_t 
 }
 
 int ipp_shannon_entropy(ipp_handle* h, float* p_host, int64_t n, float* out_host) {
+  DeviceGuard on_device(h);
   if (h == nullptr || p_host == nullptr || out_host == nullptr || n < 0) return IPP_ERR_INVALID_ARG;
   if (n == 0) return IPP_OK;
   const size_t nb = sizeof(float) * (size_t)n;
@@ -460,6 +488,7 @@ int ipp_shannon_entropy(ipp_handle* h, float* p_host, int64_t n, float* out_host
 
 int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host, int32_t n_others, int64_t cells,
                  float* out_host) {
+  DeviceGuard on_device(h);
   if (h == nullptr || own_host == nullptr || out_host == nullptr || cells < 0 || n_others < 0 ||
       (n_others > 0 && others_host == nullptr))
     return IPP_ERR_INVALID_ARG;
@@ -484,6 +513,7 @@ int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host,
 
 int ipp_utility_reward(ipp_handle* h, const float* last_host, const float* next_host, int64_t cells,
                        double* out2_host) {
+  DeviceGuard on_device(h);
   if (h == nullptr || last_host == nullptr || next_host == nullptr || out2_host == nullptr || cells <= 0)
     return IPP_ERR_INVALID_ARG;
   const size_t nb = sizeof(float) * (size_t)cells;

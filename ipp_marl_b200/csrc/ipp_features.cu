@@ -634,11 +634,11 @@ static cudaError_t actor_staged_mt(const ipp_config& cfg, const ipp_state& st, c
                                    const int32_t* pos_in, const uint8_t* comm, int32_t t, float* obs_out, size_t smem,
                                    cudaStream_t s) {
   auto kern = features_actor_staged_kernel<A, MT>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDevice attr;
+  if (!attr.cur()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.cur() = 1;
   }
   kern<<<(unsigned)cfg.n_envs * A, 128, smem, s>>>(cfg, st, pt, pos_in, comm, t, obs_out);
   return cudaGetLastError();
@@ -657,11 +657,11 @@ static cudaError_t critic_staged_mt(const ipp_config& cfg, const ipp_state& st, 
                                     const int32_t* pos_in, const int32_t* actions, int32_t t, const float* obs_in,
                                     float* state_out, size_t smem, cudaStream_t s) {
   auto kern = features_critic_staged_kernel<A, MT>;
-  static bool attr = false;
-  if (!attr) {
+  static PerDevice attr;
+  if (!attr.cur()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FEAT_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr.cur() = 1;
   }
   kern<<<(unsigned)cfg.n_envs, 128, smem, s>>>(cfg, st, pt, pos_in, actions, t, obs_in, state_out);
   return cudaGetLastError();

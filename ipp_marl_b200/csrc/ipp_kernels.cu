@@ -689,16 +689,17 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
   const size_t smem = stage_gt ? (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) : 0;
   int dbg = 0;
   if (const char* v = getenv("IPP_PLAN_DEBUG")) dbg = atoi(v) & 6;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
     cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.cur() = 1;
   }
   // Envs per block: two 80 KB blocks fit an SM, so the GPU runs 2 * n_sm blocks at a time.  When the batch needs
   // more than one such wave of 16-env blocks but fits ONE wave of <= 32-env blocks, use the larger blocks: the
   // sequential phase 1 is then paid once instead of once per wave and no SM idles in a partial second wave.
-  static int n_slots = 0;
+  static PerDevice slots;
+  int& n_slots = slots.cur();
   if (n_slots == 0) {
     int dev = 0, n_sm = 0;
     cudaGetDevice(&dev);

@@ -13,6 +13,17 @@ constexpr int TMA_QPC = 640;             // TMA variant: quads per work item (20
 __host__ __device__ constexpr int tma_consumer_warps(int n_agents) { return n_agents <= 4 ? 30 : 26; }
 __host__ __device__ constexpr int tma_threads(int n_agents) { return (tma_consumer_warps(n_agents) + 2) * 32; }
 
+// Launch-time state that is per DEVICE (function attributes such as the dynamic shared-memory limit belong to the
+// device a kernel is launched on): one slot per device ordinal, so that handles on several GPUs can live in one process.
+struct PerDevice {
+  int v[64] = {};
+  int& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[d & 63];
+  }
+};
+
 struct LaunchPlan {
   int32_t n_chunks;         // chunks per env map (1 => per-env reward finishes inside the block)
   int32_t quads_per_chunk;  // float4 groups of cells per chunk

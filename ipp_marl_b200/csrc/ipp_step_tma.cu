@@ -353,7 +353,8 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
                                 int n_sm, const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
                                 double* partials, cudaStream_t s) {
   auto kern = step_tma_kernel<A, DO_OWN>;
-  static int configured_bytes = 0;  // per template instantiation; grows to the largest plan seen
+  static PerDevice configured;  // per template instantiation and device; grows to the largest plan seen
+  int& configured_bytes = configured.cur();
   if (plan.smem_bytes > configured_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
     if (e != cudaSuccess) return e;

@@ -41,17 +41,33 @@ def _compile_one(args):
     return src, res.returncode, res.stdout, res.stderr
 
 
+def _up_to_date(digest):
+    if os.path.exists(LIB) and os.path.exists(STAMP):
+        with open(STAMP) as f:
+            return f.read().strip() == digest
+    return False
+
+
 def build(force=False, verbose=False):
     """Compile if sources changed; returns the library path.  Raises if nvcc fails.
 
     Each .cu is compiled to its own object (in parallel, cached by content digest under _lib/obj/) and the
-    objects are linked into one shared library."""
+    objects are linked into one shared library.  Concurrent callers (one process per GPU under torchrun) are
+    serialised by a file lock: the first one builds, the others find the library up to date."""
     os.makedirs(LIBDIR, exist_ok=True)
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
-        with open(STAMP) as f:
-            if f.read().strip() == digest:
-                return LIB
+    if not force and _up_to_date(digest):
+        return LIB
+    import fcntl
+
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _up_to_date(digest):  # another process built it while we waited
+            return LIB
+        return _build_locked(force, verbose, digest)
+
+
+def _build_locked(force, verbose, digest):
     nvcc = nvcc_path()
     if nvcc is None:
         if os.path.exists(LIB):

@@ -425,3 +425,44 @@ class SparseKernelModelEnv(KernelModelEnv):
         self.pos = new_pos
         self.t += 1
         return dict(comm=comm, mask=masks, action=acts, reward_rel=rel, reward_abs=ab)
+
+    # ---- the same rule in split mode (ipp_observe / ipp_act) -----------------------------------------------------
+    def observe(self):
+        A = self.A
+        comm = self.comm()
+        prev = [self._k_of(self.pos[:, j], j, self.t) for j in range(A)]
+        last = self.glob_o
+        self.glob_o = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])
+        rel, ab = self._reward(last, self.glob_o)
+        kout_one = bool(self.tab.k_out == F32(1))
+        quads_per_tile = self.TILE_CELLS // 4
+        for i in range(A):
+            passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
+            dense = self._apply(self.local_o[:, i], passes)
+            en = np.zeros(self.B, bool)
+            touched = np.zeros_like(prev[0][0])
+            for j in range(A):
+                if j != i:
+                    en |= comm[:, i, j]
+                    touched |= prev[j][0] & comm[:, i, j][:, None, None]
+            tq = self._quads(touched)
+            all_tile = en[:, None] & (self.flags[:, i] | (not kout_one))
+            proc = self._cells_of_quads(tq | np.repeat(all_tile, quads_per_tile, axis=1)[:, : tq.shape[1]])
+            self.local_o[:, i] = np.where(proc, dense, self.local_o[:, i])
+            bad = self._tile_any(self._out_of_range(self.local_o[:, i]) & proc)
+            self.flags[:, i] = bad | (self.flags[:, i] & ~en[:, None])
+        return dict(comm=comm, reward_rel=rel, reward_abs=ab)
+
+    def act(self, actions=None):
+        A = self.A
+        new_pos, masks, acts = self._choose_and_move(actions)
+        for i in range(A):
+            inr, k = self._k_of(new_pos[:, i], i, self.t + 1)
+            dense = self._apply(self.local_o[:, i], [(inr, k, False)])
+            proc = self._cells_of_quads(self._quads(inr))  # own_update_kernel: the quads of the new footprint
+            self.local_o[:, i] = np.where(proc, dense, self.local_o[:, i])
+            self.flags[:, i] |= self._tile_any(self._out_of_range(self.local_o[:, i]) & proc)
+        self.pos = new_pos
+        self.t += 1
+        return dict(mask=masks, action=acts)
+

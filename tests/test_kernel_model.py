@@ -79,3 +79,27 @@ def test_sparse_processing_rule_is_exact(tag, n_agents, prior):
         assert share < 0.95 and share - touched < 0.05, (share, touched)  # the flags cost almost nothing
     else:
         assert share >= touched  # k_out != 1: every pass multiplies every cell -> dense by construction
+
+
+def test_sparse_processing_rule_is_exact_in_split_mode():
+    """The same proof for ipp_observe / ipp_act (the flags are written by the fuse kernel and OR-ed by the own-update
+    kernel), and split mode == fused mode bit for bit (one float32 odds state, no rounding in between)."""
+    from tests.helpers import load_kats
+
+    params = load_kats()["synthetic50"]["params"]
+    params["experiment"]["uav"]["communication_range"] = 15
+    params["experiment"]["uav"]["failure_rate"] = 0.25
+    episodes = np.arange(3, 27)
+    fused = km.KernelModelEnv(params, episodes)
+    dense = km.KernelModelEnv(params, episodes)
+    sparse = km.SparseKernelModelEnv(params, episodes)
+    for t in range(dense.geo.budget + 1):
+        fused.step()
+        dense.observe()
+        sparse.observe()
+        assert np.array_equal(dense.local_o, sparse.local_o), t
+        dense.act()
+        sparse.act()
+        assert np.array_equal(dense.local_o, sparse.local_o) and np.array_equal(dense.glob_o, sparse.glob_o), t
+        assert np.array_equal(fused.local_o, dense.local_o) and np.array_equal(fused.glob_o, dense.glob_o), t
+

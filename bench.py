@@ -331,7 +331,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "%s<%d,true>" % ("step_tma_kernel" if env.step_variant == "tma" else
-                                                    "step_dense_kernel", A), "kernel_ms": kern_ms,
+                                                    "step_direct_kernel", A), "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg,
                          "note": "dense contract bytes G^2*(8(A+1)+1) per env-step (SURVEY.md 8d)"},
         }

@@ -25,7 +25,7 @@ namespace ipp {
 template <int A>
 struct EnvMeta {
   uint32_t comm[A];      // bit j: agent i fuses agent j's measurement (own bit cleared)
-  uint32_t comm4[A];     // the same, one nibble (0xF) per enabled peer: mask for QuadCtx::in_prev
+  uint32_t comm4[A];     // the same, one nibble (0xF) per enabled peer: mask for the in-footprint nibbles of a quad (in_prev)
   uint32_t lut_prev[A];  // float4 index of the LUT row (altitude) of agent j's communicated measurement
   uint32_t lut_next[A];  // same for the measurement after the move
 };

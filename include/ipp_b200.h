@@ -79,6 +79,10 @@ typedef struct ipp_config {
                                               /* float32(round(1-noise, 3)) and float32(round(noise, 3)) */
   uint32_t flip_thresh[IPP_MAX_ALT];          /* cell measured wrongly iff hash < flip_thresh      */
   int32_t cell_x[IPP_MAX_LATTICE], cell_y[IPP_MAX_LATTICE]; /* floor(pos/res_x): cameras.py:66     */
+  int32_t fix_range;       /* experiment.uav.fix_range; 0 = per-episode random range (communication_log.py:22-31): */
+  int32_t comm_d2_table[4];/* comm_d2_max of the ranges {0, 15, 25, 100} m, indexed by the episode's first         */
+                           /* randint(4) after np.random.seed(episode) (drawn by ipp_reset: call it on this handle) */
+  double l_prior;          /* np.log(prior / (1 - prior)) in float64: mapping/mappings.py:116 (single-map entry points) */
 } ipp_config;
 
 /* Device-resident state of the batch (struct-of-arrays form of agent/agent.py:13-38 per UAV and of
@@ -247,23 +251,31 @@ int ipp_project_fov(const ipp_handle* h, const int32_t* position, int32_t* raw, 
 int ipp_measure(ipp_handle* h, const uint8_t* gt_host, const int32_t* rect, int32_t altitude_m, uint32_t episode,
                 uint32_t agent, uint32_t index, float y_hi, float y_lo, float* out_host);
 
-/* Mapping.update_cells / apply_update (mapping/mappings.py:106-124) on n cells:
- * x is clamped IN PLACE like the reference; y is per cell (y_is_scalar == 0) or one value
- * (IG_baseline.py:240-245 passes a Python float); out = updated probabilities. */
-int ipp_update_cells(ipp_handle* h, float* x_host, const float* y_host, int32_t y_is_scalar, int64_t n,
-                     float* out_host);
+/*
+ * The four entry points below reproduce the reference's dtype flow under numpy >= 2: the
+ * `*_f64` flags say whether a host array holds float32 (0) or float64 (1) values, exactly as the numpy arrays the
+ * reference would pass; results have the dtype the reference returns.
+ *
+ * Mapping.update_cells / apply_update (mapping/mappings.py:106-124) on n cells: x is clamped IN PLACE (in its own
+ * dtype) like the reference; y is per cell (y_is_scalar == 0) or one value (IG_baseline.py:240-245 passes a Python
+ * float = float64 scalar); logit(x) and logit(y) are taken in their own dtypes, the sigmoid in float64;
+ * out_host [n] float64 = updated probabilities.
+ */
+int ipp_update_cells(ipp_handle* h, void* x_host, int32_t x_f64, const void* y_host, int32_t y_f64,
+                     int32_t y_is_scalar, int64_t n, double* out_host);
 
-/* get_shannon_entropy (utils/state.py:118-121): p clamped IN PLACE, H written to out. */
-int ipp_shannon_entropy(ipp_handle* h, float* p_host, int64_t n, float* out_host);
+/* get_shannon_entropy (utils/state.py:118-121): p clamped IN PLACE, H (same dtype as p) written to out. */
+int ipp_shannon_entropy(ipp_handle* h, void* p_host, int32_t is_f64, int64_t n, void* out_host);
 
-/* Mapping.fuse_map (mapping/mappings.py:80-104): own [cells] fused with n_others dense maps
- * (map2communicate arrays, [n_others, cells]) in order; result in out (own is not modified). */
-int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host, int32_t n_others,
-                 int64_t cells, float* out_host);
+/* Mapping.fuse_map (mapping/mappings.py:80-104): own [cells] (float32: the reference casts it with np.float32(...)
+ * on entry) fused with n_others dense float32 maps (map2communicate arrays, [n_others, cells]) in order; the first
+ * pass takes its logits in float32, every later pass runs in float64; result float64 in out (own is not modified). */
+int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host, int32_t n_others, int64_t cells,
+                 double* out_host);
 
 /* get_utility_reward (utils/reward.py:68-82) on two dense maps: out[0] = absolute, out[1] = relative. */
-int ipp_utility_reward(ipp_handle* h, const float* last_host, const float* next_host, int64_t cells,
-                       double* out2_host);
+int ipp_utility_reward(ipp_handle* h, const void* last_host, int32_t last_f64, const void* next_host,
+                       int32_t next_f64, int64_t cells, double* out2_host);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,8 @@ class IppConfig(C.Structure):
         ("y_hi", C.c_float * MAX_ALT), ("y_lo", C.c_float * MAX_ALT),
         ("flip_thresh", C.c_uint32 * MAX_ALT),
         ("cell_x", C.c_int32 * MAX_LATTICE), ("cell_y", C.c_int32 * MAX_LATTICE),
+        ("fix_range", C.c_int32), ("comm_d2_table", C.c_int32 * 4),
+        ("l_prior", C.c_double),
     ]
 
 
@@ -100,10 +102,10 @@ def load():
     lib.ipp_project_fov.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.ipp_measure.argtypes = [vp, vp, C.POINTER(i32), i32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
                                 C.c_float, vp]
-    lib.ipp_update_cells.argtypes = [vp, vp, vp, i32, i64, vp]
-    lib.ipp_shannon_entropy.argtypes = [vp, vp, i64, vp]
+    lib.ipp_update_cells.argtypes = [vp, vp, i32, vp, i32, i32, i64, vp]
+    lib.ipp_shannon_entropy.argtypes = [vp, vp, i32, i64, vp]
     lib.ipp_fuse_map.argtypes = [vp, vp, vp, i32, i64, vp]
-    lib.ipp_utility_reward.argtypes = [vp, vp, vp, i64, vp]
+    lib.ipp_utility_reward.argtypes = [vp, vp, i32, vp, i32, i64, vp]
     _lib = lib
     return lib
 

@@ -13,7 +13,9 @@ LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libipp_b200.so")
 STAMP = os.path.join(LIBDIR, "libipp_b200.stamp")
 SOURCES = ["ipp_kernels.cu", "ipp_step_tma.cu", "ipp_features.cu", "ipp_planner.cu", "ipp_facade_kernels.cu", "ipp_abi.cu"]
-HEADERS = ["ipp_device.cuh", "ipp_cell.cuh", "ipp_launch.h", os.path.join("..", "..", "include", "ipp_b200.h")]
+# every header a source may include: all of csrc/*.cuh, csrc/*.h and the public ABI header
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join("..", "..", "include", "ipp_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
@@ -71,7 +73,9 @@ def _build_locked(force, verbose, digest):
     nvcc = nvcc_path()
     if nvcc is None:
         if os.path.exists(LIB):
-            return LIB  # box without a toolkit: use the prebuilt library shipped with the snapshot
+            # box without a toolkit: the prebuilt library shipped with the snapshot must match these sources
+            raise RuntimeError("prebuilt %s does not match the sources (stamp mismatch) and nvcc is not available "
+                               "to rebuild it" % LIB)
         raise RuntimeError("nvcc not found and no prebuilt %s" % LIB)
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)

@@ -137,7 +137,7 @@ const char* ipp_status_string(int status) {
 
 const char* ipp_last_error(const ipp_handle* h) { return h != nullptr ? h->err : ""; }
 
-int ipp_version(void) { return 100; }
+int ipp_version(void) { return 200; }
 
 int ipp_create(const ipp_config* cfg, ipp_handle** out) {
   if (out == nullptr) return IPP_ERR_INVALID_ARG;
@@ -176,6 +176,7 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
     ipp_destroy(h);
     return IPP_ERR_ALLOC;
   }
+  cudaMemset(h->gt_params, 0, gb);  // split 0 until the first ipp_reset (read by the plan kernel when fix_range == 0)
   // lut[alt][byte][c]: cell c of a quad with code `byte` (low nibble: inside the footprint, high nibble:
   // seen as 1) is multiplied by k_hi / k_lo of the altitude, cells outside the footprint by k_out
   const size_t lb = sizeof(float) * 4 * 256 * (size_t)cfg->n_alt;
@@ -260,7 +261,7 @@ int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_ste
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 1, h->step_meta, s));
+  if (phases & IPP_PHASE_MOVE) IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 1, h->step_meta, h->gt_params, s));
   if (phases & IPP_PHASE_MAPS) IPP_CUDA(h, launch_maps(h, st, io2, t, true, s));
   return IPP_OK;
 }
@@ -324,7 +325,7 @@ int ipp_observe(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io
   ipp_step_io io2 = *io;
   if (io2.comm_out == nullptr) io2.comm_out = h->comm;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 0, h->step_meta, s));
+  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, io2, t, 1, 0, h->step_meta, h->gt_params, s));
   IPP_CUDA(h, launch_maps(h, st, io2, t, false, s));
   return IPP_OK;
 }
@@ -337,7 +338,7 @@ int ipp_act(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io
   if (rc != IPP_OK) return rc;
   if (t < 0 || t > 0xFFFE) return IPP_ERR_INVALID_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, *io, t, 0, 1, h->step_meta, s));
+  IPP_CUDA(h, ipp::launch_plan(h->cfg, *st, *io, t, 0, 1, h->step_meta, h->gt_params, s));
   IPP_CUDA(h, ipp::launch_own_update(h->cfg, *st, h->lut, io->pos_out, t, s));
   return IPP_OK;
 }
@@ -450,83 +451,84 @@ int ipp_measure(ipp_handle* h, const uint8_t* gt_host, const int32_t* rect, int3
   return IPP_OK;
 }
 
-int ipp_update_cells(ipp_handle* h, float* x_host, const float* y_host, int32_t y_is_scalar, int64_t n,
-                     float* out_host) {
+int ipp_update_cells(ipp_handle* h, void* x_host, int32_t x_f64, const void* y_host, int32_t y_f64,
+                     int32_t y_is_scalar, int64_t n, double* out_host) {
   DeviceGuard on_device(h);
   if (h == nullptr || x_host == nullptr || y_host == nullptr || out_host == nullptr || n < 0)
     return IPP_ERR_INVALID_ARG;
   if (n == 0) return IPP_OK;
-  const size_t nb = sizeof(float) * (size_t)n;
-  int rc = ensure_fbuf(h, 3 * nb);
+  const size_t xb = (x_f64 ? 8 : 4) * (size_t)n, yb = (y_f64 ? 8 : 4) * (size_t)(y_is_scalar ? 1 : n);
+  const size_t xb_al = (xb + 15) & ~(size_t)15, yb_al = (yb + 15) & ~(size_t)15;
+  int rc = ensure_fbuf(h, xb_al + yb_al + 8 * (size_t)n);
   if (rc != IPP_OK) return rc;
-  float* dx = static_cast<float*>(h->fbuf);
-  float* dy = dx + n;
-  float* dout = dy + n;
-  IPP_CUDA(h, cudaMemcpy(dx, x_host, nb, cudaMemcpyHostToDevice));
-  if (!y_is_scalar) IPP_CUDA(h, cudaMemcpy(dy, y_host, nb, cudaMemcpyHostToDevice));
-  IPP_CUDA(h, ipp::launch_update_cells(h->cfg, dx, dy, y_is_scalar, y_is_scalar ? y_host[0] : 0.0f, n, dout, 0));
-  IPP_CUDA(h, cudaMemcpy(x_host, dx, nb, cudaMemcpyDeviceToHost));
-  IPP_CUDA(h, cudaMemcpy(out_host, dout, nb, cudaMemcpyDeviceToHost));
+  char* base = static_cast<char*>(h->fbuf);
+  void* dx = base;
+  void* dy = base + xb_al;
+  double* dout = reinterpret_cast<double*>(base + xb_al + yb_al);
+  IPP_CUDA(h, cudaMemcpy(dx, x_host, xb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, cudaMemcpy(dy, y_host, yb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, ipp::launch_update_cells(dx, x_f64, dy, y_f64, y_is_scalar, h->cfg.l_prior, n, dout, 0));
+  IPP_CUDA(h, cudaMemcpy(x_host, dx, xb, cudaMemcpyDeviceToHost));
+  IPP_CUDA(h, cudaMemcpy(out_host, dout, 8 * (size_t)n, cudaMemcpyDeviceToHost));
   return IPP_OK;
 }
 
-int ipp_shannon_entropy(ipp_handle* h, float* p_host, int64_t n, float* out_host) {
+int ipp_shannon_entropy(ipp_handle* h, void* p_host, int32_t is_f64, int64_t n, void* out_host) {
   DeviceGuard on_device(h);
   if (h == nullptr || p_host == nullptr || out_host == nullptr || n < 0) return IPP_ERR_INVALID_ARG;
   if (n == 0) return IPP_OK;
-  const size_t nb = sizeof(float) * (size_t)n;
-  int rc = ensure_fbuf(h, 2 * nb);
+  const size_t nb = (is_f64 ? 8 : 4) * (size_t)n;
+  const size_t nb_al = (nb + 15) & ~(size_t)15;
+  int rc = ensure_fbuf(h, 2 * nb_al);
   if (rc != IPP_OK) return rc;
-  float* dp = static_cast<float*>(h->fbuf);
-  float* dout = dp + n;
+  char* dp = static_cast<char*>(h->fbuf);
+  char* dout = dp + nb_al;
   IPP_CUDA(h, cudaMemcpy(dp, p_host, nb, cudaMemcpyHostToDevice));
-  IPP_CUDA(h, ipp::launch_entropy(h->cfg, dp, n, dout, 0));
+  IPP_CUDA(h, ipp::launch_entropy(dp, is_f64, n, dout, 0));
   IPP_CUDA(h, cudaMemcpy(p_host, dp, nb, cudaMemcpyDeviceToHost));
   IPP_CUDA(h, cudaMemcpy(out_host, dout, nb, cudaMemcpyDeviceToHost));
   return IPP_OK;
 }
 
 int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host, int32_t n_others, int64_t cells,
-                 float* out_host) {
+                 double* out_host) {
   DeviceGuard on_device(h);
   if (h == nullptr || own_host == nullptr || out_host == nullptr || cells < 0 || n_others < 0 ||
       (n_others > 0 && others_host == nullptr))
     return IPP_ERR_INVALID_ARG;
   if (cells == 0) return IPP_OK;
   const size_t nb = sizeof(float) * (size_t)cells;
-  int rc = ensure_fbuf(h, 3 * nb);
+  const size_t nb_al = (nb + 15) & ~(size_t)15;
+  const size_t ob = nb * (size_t)n_others;
+  const size_t ob_al = (ob + 15) & ~(size_t)15;
+  int rc = ensure_fbuf(h, nb_al + ob_al + 8 * (size_t)cells);
   if (rc != IPP_OK) return rc;
-  float* cur = static_cast<float*>(h->fbuf);
-  float* dy = cur + cells;
-  float* nxt = dy + cells;
-  IPP_CUDA(h, cudaMemcpy(cur, own_host, nb, cudaMemcpyHostToDevice));
-  for (int32_t k = 0; k < n_others; ++k) {
-    IPP_CUDA(h, cudaMemcpy(dy, others_host + (size_t)k * cells, nb, cudaMemcpyHostToDevice));
-    IPP_CUDA(h, ipp::launch_update_cells(h->cfg, cur, dy, 0, 0.0f, cells, nxt, 0));
-    float* tmp = cur;
-    cur = nxt;
-    nxt = tmp;
-  }
-  IPP_CUDA(h, cudaMemcpy(out_host, cur, nb, cudaMemcpyDeviceToHost));
+  char* base = static_cast<char*>(h->fbuf);
+  float* down = reinterpret_cast<float*>(base);
+  float* doth = reinterpret_cast<float*>(base + nb_al);
+  double* dout = reinterpret_cast<double*>(base + nb_al + ob_al);
+  IPP_CUDA(h, cudaMemcpy(down, own_host, nb, cudaMemcpyHostToDevice));
+  if (n_others > 0) IPP_CUDA(h, cudaMemcpy(doth, others_host, ob, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, ipp::launch_fuse_map(down, doth, n_others, h->cfg.l_prior, cells, dout, 0));
+  IPP_CUDA(h, cudaMemcpy(out_host, dout, 8 * (size_t)cells, cudaMemcpyDeviceToHost));
   return IPP_OK;
 }
 
-int ipp_utility_reward(ipp_handle* h, const float* last_host, const float* next_host, int64_t cells,
-                       double* out2_host) {
+int ipp_utility_reward(ipp_handle* h, const void* last_host, int32_t last_f64, const void* next_host,
+                       int32_t next_f64, int64_t cells, double* out2_host) {
   DeviceGuard on_device(h);
   if (h == nullptr || last_host == nullptr || next_host == nullptr || out2_host == nullptr || cells <= 0)
     return IPP_ERR_INVALID_ARG;
-  const size_t nb = sizeof(float) * (size_t)cells;
+  const size_t lb = (last_f64 ? 8 : 4) * (size_t)cells, nb = (next_f64 ? 8 : 4) * (size_t)cells;
+  const size_t lb_al = (lb + 15) & ~(size_t)15, nb_al = (nb + 15) & ~(size_t)15;
   const size_t rb = sizeof(double) * (2 + 2 * 296);
-  const size_t nb_al = (2 * nb + 15) & ~(size_t)15;
-  int rc = ensure_fbuf(h, nb_al + rb);
+  int rc = ensure_fbuf(h, lb_al + nb_al + rb);
   if (rc != IPP_OK) return rc;
-  float* dl = static_cast<float*>(h->fbuf);
-  float* dn = dl + cells;
-  double* dres = reinterpret_cast<double*>(static_cast<char*>(h->fbuf) + nb_al);
-  IPP_CUDA(h, cudaMemcpy(dl, last_host, nb, cudaMemcpyHostToDevice));
-  IPP_CUDA(h, cudaMemcpy(dn, next_host, nb, cudaMemcpyHostToDevice));
-  IPP_CUDA(h, ipp::launch_utility_reward(h->cfg, dl, dn, cells, dres, 0));
+  char* base = static_cast<char*>(h->fbuf);
+  double* dres = reinterpret_cast<double*>(base + lb_al + nb_al);
+  IPP_CUDA(h, cudaMemcpy(base, last_host, lb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, cudaMemcpy(base + lb_al, next_host, nb, cudaMemcpyHostToDevice));
+  IPP_CUDA(h, ipp::launch_utility_reward(base, last_f64, base + lb_al, next_f64, cells, dres, 0));
   IPP_CUDA(h, cudaMemcpy(out2_host, dres, 2 * sizeof(double), cudaMemcpyDeviceToHost));
   return IPP_OK;
 }

@@ -1,48 +1,118 @@
 // Single-map kernels behind the drop-in facade entry points (ipp_update_cells, ipp_fuse_map,
-// ipp_shannon_entropy, ipp_utility_reward).  Same odds-space arithmetic as the batched kernels, with
-// the multiplier derived from an arbitrary measurement value y: k = odds(y) / odds(prior)
-// (= exp(logit y - logit prior), mapping/mappings.py:112-117).
+// ipp_shannon_entropy, ipp_utility_reward, ipp_measure).
 #include "ipp_device.cuh"
 #include "ipp_launch.h"
 
 namespace ipp {
 
-__device__ __forceinline__ float k_of_y(float y, float o_prior) { return __fdiv_rn(to_odds(y), o_prior); }
+// ------------------------------------------------------------------------------------------------------------------
+// The single-map entry points reproduce the reference's DTYPE FLOW under numpy >= 2 (SURVEY.md section 7 "dtype
+// drift"), not only its formula: mapping/mappings.py:109-124 clamps x in x's own dtype, takes logit(x) in x's dtype
+// and logit(y) in y's dtype (float32 for measurement arrays, float64 for the Python float IG_baseline.py:240-245
+// passes), adds them in the promoted dtype, and — because l_p = np.log(prior / (1 - prior)) is an np.float64 scalar —
+// evaluates `1 - 1/(1 + exp(l))` in float64 and RETURNS float64.  Mapping.fuse_map therefore returns float64 whenever
+// it fused at least one peer, every pass after the first runs entirely in float64, and Agent.local_map stays float64
+// until update_grid_map writes into a float32 map again.  The batched kernels keep one float32 odds state instead
+// (DESIGN.md section 3); these kernels exist so that the UNCHANGED reference callers see the same numbers through the
+// facade as through the reference's own modules.  float32 logs are computed in float64 and rounded (correctly rounded
+// float32 log; numpy's SIMD logf may differ from it in the last bit).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Flow;
+template <>
+struct Flow<float> {
+  static __device__ __forceinline__ float clamp(float x) {  // x[0.9999 < x] = 0.9999: the Python float is cast to float32
+    return fminf(fmaxf(x, 0.0001f), 0.9999f);
+  }
+  static __device__ __forceinline__ float logit(float x) {
+    return (float)log((double)__fdiv_rn(x, __fsub_rn(1.0f, x)));
+  }
+  static __device__ __forceinline__ float entropy(float p) {  // utils/state.py:121 in float32
+    const float q = __fsub_rn(1.0f, p);
+    const float lp = (float)log2((double)p), lq = (float)log2((double)q);
+    return __fsub_rn(__fmul_rn(-p, lp), __fmul_rn(q, lq));
+  }
+  static __device__ __forceinline__ bool gt(float v, double c) { return v > (float)c; }
+  static __device__ __forceinline__ bool lt(float v, double c) { return v < (float)c; }
+};
+template <>
+struct Flow<double> {
+  static __device__ __forceinline__ double clamp(double x) { return fmin(fmax(x, 0.0001), 0.9999); }
+  static __device__ __forceinline__ double logit(double x) { return log(x / (1.0 - x)); }
+  static __device__ __forceinline__ double entropy(double p) { return -p * log2(p) - (1.0 - p) * log2(1.0 - p); }
+  static __device__ __forceinline__ bool gt(double v, double c) { return v > c; }
+  static __device__ __forceinline__ bool lt(double v, double c) { return v < c; }
+};
 
-// mode 0: out = update(x, y) with x clamped in place (Mapping.apply_update)
-__global__ void update_cells_kernel(const __grid_constant__ ipp_config cfg, float* __restrict__ x,
-                                    const float* __restrict__ y, const int y_is_scalar, const float y_scalar,
-                                    const int64_t n, float* __restrict__ out) {
-  const float o_prior = to_odds(cfg.prior);
+template <typename XT, typename YT>
+__device__ __forceinline__ double flow_update(XT& x, const YT y, const double l_prior) {
+  x = Flow<XT>::clamp(x);
+  const XT lx = Flow<XT>::logit(x);
+  const YT ly = Flow<YT>::logit(y);
+  double lxy;
+  if (sizeof(XT) == 4 && sizeof(YT) == 4) lxy = (double)__fadd_rn((float)lx, (float)ly);  // float32 + float32
+  else lxy = (double)lx + (double)ly;
+  const double l = lxy - l_prior;
+  return 1.0 - 1.0 / (1.0 + exp(l));  // mappings.py:121-124 literally, in float64
+}
+
+// Mapping.apply_update: x clamped in place (in its dtype), out float64.  y: array or one scalar of type YT.
+template <typename XT, typename YT>
+__global__ void update_cells_kernel(XT* __restrict__ x, const YT* __restrict__ y, const int y_is_scalar,
+                                    const double l_prior, const int64_t n, double* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float pc = clamp_p(cfg, x[i]);
-    x[i] = pc;
-    const float yy = y_is_scalar ? y_scalar : y[i];
-    out[i] = from_odds(odds_pass(to_odds(pc), k_of_y(yy, o_prior), cfg.o_min, cfg.o_max));
+    XT xv = x[i];
+    out[i] = flow_update<XT, YT>(xv, y_is_scalar ? y[0] : y[i], l_prior);
+    x[i] = xv;
   }
 }
 
-__global__ void entropy_kernel(const __grid_constant__ ipp_config cfg, float* __restrict__ p, const int64_t n,
-                               float* __restrict__ out) {
+// Mapping.fuse_map: own (already cast to float32 by `np.float32(own.copy())`, mappings.py:83,93,100) fused with
+// n_others float32 maps in order; the first pass reads float32 and returns float64, the others run in float64.
+__global__ void fuse_map_kernel(const float* __restrict__ own, const float* __restrict__ others, const int n_others,
+                                const double l_prior, const int64_t n, double* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float pc = clamp_p(cfg, p[i]);
-    p[i] = pc;  // utils/state.py:119-120 clamps its argument in place
-    out[i] = shannon(cfg, pc);
+    float x0 = own[i];
+    double v = (double)x0;
+    for (int k = 0; k < n_others; ++k) {
+      const float y = others[(int64_t)k * n + i];
+      if (k == 0) v = flow_update<float, float>(x0, y, l_prior);
+      else v = flow_update<double, float>(v, y, l_prior);
+    }
+    out[i] = v;
   }
 }
 
-__global__ void __launch_bounds__(256) utility_partial_kernel(const __grid_constant__ ipp_config cfg,
-                                                              const float* __restrict__ last,
-                                                              const float* __restrict__ next, const int64_t n,
-                                                              double* __restrict__ partial) {
+// get_shannon_entropy (utils/state.py:118-121): clamps IN PLACE, H in the dtype of p
+template <typename T>
+__global__ void entropy_kernel(T* __restrict__ p, const int64_t n, T* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const T pc = Flow<T>::clamp(p[i]);
+    p[i] = pc;
+    out[i] = Flow<T>::entropy(pc);
+  }
+}
+
+// get_utility_reward (utils/reward.py:68-82) with the "reward" branch of get_w_entropy_map (utils/state.py:14-76):
+// both maps are COPIED, clamped and their entropies taken in their own dtypes; weights from the next map
+// (> 0.501 -> 1, < 0.499 -> 0, else 0.5); products and means in the promoted dtype (float64 unless both are float32).
+template <typename LT, typename NT>
+__global__ void __launch_bounds__(256) utility_partial_kernel(const LT* __restrict__ last, const NT* __restrict__ next,
+                                                              const int64_t n, double* __restrict__ partial) {
   __shared__ double s_red[2][8];
   double s1 = 0.0, s2 = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float hl = shannon(cfg, last[i]);
-    const float hn = shannon(cfg, next[i]);
-    const float w = weight_of(next[i]);
-    s1 += (double)(w * (hl - hn));
-    s2 += (double)(w * hl);
+    const NT nv = next[i];
+    const double w = Flow<NT>::gt(nv, 0.501) ? 1.0 : (Flow<NT>::lt(nv, 0.499) ? 0.0 : 0.5);
+    const LT hl = Flow<LT>::entropy(Flow<LT>::clamp(last[i]));
+    const NT hn = Flow<NT>::entropy(Flow<NT>::clamp(nv));
+    if (sizeof(LT) == 4 && sizeof(NT) == 4) {
+      s1 += (double)__fmul_rn((float)w, __fsub_rn((float)hl, (float)hn));
+      s2 += (double)__fmul_rn((float)w, (float)hl);
+    } else {
+      s1 += w * ((double)hl - (double)hn);
+      s2 += w * (double)hl;
+    }
   }
   for (int off = 16; off > 0; off >>= 1) {
     s1 += __shfl_down_sync(0xFFFFFFFFu, s1, off);
@@ -108,25 +178,49 @@ static int grid_for(int64_t n, int threads, int cap) {
   return (int)b;
 }
 
-cudaError_t launch_update_cells(const ipp_config& cfg, float* x, const float* y, int y_is_scalar, float y_scalar,
-                                int64_t n, float* out, cudaStream_t s) {
-  update_cells_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(cfg, x, y, y_is_scalar, y_scalar, n, out);
+cudaError_t launch_update_cells(void* x, int x_f64, const void* y, int y_f64, int y_is_scalar, double l_prior,
+                                int64_t n, double* out, cudaStream_t s) {
+  const int g = grid_for(n, 256, 148 * 8);
+  if (x_f64 && y_f64)
+    update_cells_kernel<double, double><<<g, 256, 0, s>>>((double*)x, (const double*)y, y_is_scalar, l_prior, n, out);
+  else if (x_f64)
+    update_cells_kernel<double, float><<<g, 256, 0, s>>>((double*)x, (const float*)y, y_is_scalar, l_prior, n, out);
+  else if (y_f64)
+    update_cells_kernel<float, double><<<g, 256, 0, s>>>((float*)x, (const double*)y, y_is_scalar, l_prior, n, out);
+  else
+    update_cells_kernel<float, float><<<g, 256, 0, s>>>((float*)x, (const float*)y, y_is_scalar, l_prior, n, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_entropy(const ipp_config& cfg, float* p, int64_t n, float* out, cudaStream_t s) {
-  entropy_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(cfg, p, n, out);
+cudaError_t launch_fuse_map(const float* own, const float* others, int n_others, double l_prior, int64_t n,
+                            double* out, cudaStream_t s) {
+  fuse_map_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(own, others, n_others, l_prior, n, out);
   return cudaGetLastError();
 }
 
-// out2 must have room for 2 + 2*UTILITY_BLOCKS doubles (result first, partials after)
-cudaError_t launch_utility_reward(const ipp_config& cfg, const float* last, const float* next, int64_t n,
+cudaError_t launch_entropy(void* p, int is_f64, int64_t n, void* out, cudaStream_t s) {
+  const int g = grid_for(n, 256, 148 * 8);
+  if (is_f64) entropy_kernel<double><<<g, 256, 0, s>>>((double*)p, n, (double*)out);
+  else entropy_kernel<float><<<g, 256, 0, s>>>((float*)p, n, (float*)out);
+  return cudaGetLastError();
+}
+
+// out2 must have room for 2 + 2*296 doubles (result first, partials after)
+cudaError_t launch_utility_reward(const void* last, int last_f64, const void* next, int next_f64, int64_t n,
                                   double* out2, cudaStream_t s) {
   const int blocks = grid_for(n, 256, 296);
-  utility_partial_kernel<<<blocks, 256, 0, s>>>(cfg, last, next, n, out2 + 2);
+  double* part = out2 + 2;
+  if (last_f64 && next_f64)
+    utility_partial_kernel<double, double><<<blocks, 256, 0, s>>>((const double*)last, (const double*)next, n, part);
+  else if (last_f64)
+    utility_partial_kernel<double, float><<<blocks, 256, 0, s>>>((const double*)last, (const float*)next, n, part);
+  else if (next_f64)
+    utility_partial_kernel<float, double><<<blocks, 256, 0, s>>>((const float*)last, (const double*)next, n, part);
+  else
+    utility_partial_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)last, (const float*)next, n, part);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  utility_final_kernel<<<1, 1, 0, s>>>(out2 + 2, blocks, n, out2);
+  utility_final_kernel<<<1, 1, 0, s>>>(part, blocks, n, out2);
   return cudaGetLastError();
 }
 

@@ -55,7 +55,7 @@ struct PlanShared {
 __device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const bool env_ok, const int a,
                                  const ipp_step_io& io, const ipp_state& st, const int32_t t, const bool do_comm,
                                  const bool do_move, PlanShared& sh, int32_t (*npos)[3],
-                                 uint32_t* __restrict__ step_meta) {
+                                 uint32_t* __restrict__ step_meta, const int32_t* __restrict__ gt_params) {
   const int32_t A = cfg.n_agents;
   const bool live = env_ok && a < A;
   int32_t p[3] = {0, 0, 0};
@@ -73,12 +73,15 @@ __device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const b
   uint32_t* rec = step_meta + (int64_t)b * 4 * A;  // this env's record for the map kernels (EnvMeta field order)
   if (live && do_comm && io.comm_out != nullptr) {
     const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)a, (uint32_t)t, PURPOSE_COMM);
+    // fix_range False (communication_log.py:22-31): range index = the episode's first randint(4) = the ground
+    // truth's split, stored by reset_prep_kernel
+    const int32_t d2_max = cfg.fix_range ? cfg.comm_d2_max : cfg.comm_d2_table[gt_params[(int64_t)b * 4] & 3];
     uint32_t row = 0;
     for (int32_t j = 0; j < A; ++j) {
       const int32_t dx = p[0] - sh.pos[j][0], dy = p[1] - sh.pos[j][1], dz = p[2] - sh.pos[j][2];
       const int32_t d2 = dx * dx + dy * dy + dz * dz;
       const uint32_t n24 = cell_hash(key, (uint32_t)j) >> 8;
-      const bool ok = (d2 == 0) || (d2 <= cfg.comm_d2_max && n24 >= cfg.fail_thresh24);
+      const bool ok = (d2 == 0) || (d2 <= d2_max && n24 >= cfg.fail_thresh24);
       row |= (ok ? 1u : 0u) << j;
     }
     io.comm_out[(int64_t)b * A + a] = (uint8_t)row;
@@ -265,7 +268,7 @@ constexpr int PLAN_MAX_ENVS = 32;  // most envs per block (the launcher picks: s
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
                 const int32_t do_comm, const int32_t do_move, const int32_t stage, uint32_t* __restrict__ step_meta,
-                const int32_t epb) {
+                const int32_t epb, const int32_t* __restrict__ gt_params) {
   extern __shared__ __align__(16) unsigned char plan_smem[];  // [PLAN_WARPS][gt_stride + code_stride] when stage
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t e0 = blockIdx.x * epb;  // epb envs per block, 16 <= epb <= PLAN_MAX_ENVS
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
         }
     } else {
       plan_moves_group(cfg, e0 + es, env_ok, a, io, st, t, do_comm != 0, do_move != 0, s_plan[es], s_npos[es],
-                       step_meta);
+                       step_meta, gt_params);
     }
   }
   if (!do_move) return;
@@ -683,7 +686,7 @@ cudaError_t launch_export_beliefs(const float* src, float* dst, int64_t n_floats
   }
 
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
-                        int do_move, uint32_t* step_meta, cudaStream_t s) {
+                        int do_move, uint32_t* step_meta, const int32_t* gt_params, cudaStream_t s) {
   // ground truth + new code row of one env per warp in shared memory (falls back to global for big grids)
   const int stage_gt = (do_move && (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) <= 96 * 1024) ? 1 : 0;
   const size_t smem = stage_gt ? (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) : 0;
@@ -714,7 +717,7 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
     if (e >= 1 && e <= PLAN_MAX_ENVS) epb = e;
   }
   plan_kernel<<<(cfg.n_envs + epb - 1) / epb, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm, do_move,
-                                                                         stage_gt | dbg, step_meta, epb);
+                                                                         stage_gt | dbg, step_meta, epb, gt_params);
   return cudaGetLastError();
 }
 

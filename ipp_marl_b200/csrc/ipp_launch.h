@@ -55,7 +55,7 @@ cudaError_t launch_features_critic(const ipp_config& cfg, const ipp_state& st, c
 // step_meta: device scratch [n_envs][4 * n_agents] uint32 — the EnvMeta record (ipp_cell.cuh) of every env, written
 // by the plan kernel (comm bits, LUT rows of the communicated / new measurements) and read by the map kernels
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
-                        int do_move, uint32_t* step_meta, cudaStream_t s);
+                        int do_move, uint32_t* step_meta, const int32_t* gt_params, cudaStream_t s);
 cudaError_t launch_step_dense(const ipp_config& cfg, const ipp_state& st, const float4* lut,
                               const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
                               double* partials, bool do_own, cudaStream_t s);
@@ -79,13 +79,15 @@ cudaError_t launch_ig_plan(const ipp_config& cfg, const ipp_state& st, const int
 cudaError_t launch_eval_metrics(const ipp_config& cfg, const ipp_state& st, double* entropy_out, double* f1_out,
                                 cudaStream_t s);
 
-// single-map helpers used by the facade entry points (device pointers)
-cudaError_t launch_update_cells(const ipp_config& cfg, float* x, const float* y, int y_is_scalar, float y_scalar,
-                                int64_t n, float* out, cudaStream_t s);
+// single-map helpers used by the facade entry points (device pointers; dtype flags: 0 = float32, 1 = float64)
+cudaError_t launch_update_cells(void* x, int x_f64, const void* y, int y_f64, int y_is_scalar, double l_prior,
+                                int64_t n, double* out, cudaStream_t s);
+cudaError_t launch_fuse_map(const float* own, const float* others, int n_others, double l_prior, int64_t n,
+                            double* out, cudaStream_t s);
 cudaError_t launch_measure(const ipp_config& cfg, const uint8_t* gt, const int32_t* rect, uint32_t key,
                            uint32_t thresh, float y_hi, float y_lo, float* out, cudaStream_t s);
-cudaError_t launch_entropy(const ipp_config& cfg, float* p, int64_t n, float* out, cudaStream_t s);
-cudaError_t launch_utility_reward(const ipp_config& cfg, const float* last, const float* next, int64_t n,
+cudaError_t launch_entropy(void* p, int is_f64, int64_t n, void* out, cudaStream_t s);
+cudaError_t launch_utility_reward(const void* last, int last_f64, const void* next, int next_f64, int64_t n,
                                   double* out2, cudaStream_t s);
 
 }  // namespace ipp

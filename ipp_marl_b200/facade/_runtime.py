@@ -39,6 +39,15 @@ def f32c(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def native(a):
+    """C-contiguous copy of ``a`` in the dtype the reference would compute in: float64 stays float64, everything
+    else is float32 (measurement arrays and prior maps are float32 in the reference).  -> (array, is_f64)."""
+    a = np.asarray(a)
+    if a.dtype == np.float64:
+        return np.array(a, dtype=np.float64, order="C", copy=True), 1
+    return np.array(a, dtype=np.float32, order="C", copy=True), 0
+
+
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -58,19 +58,20 @@ class Mapping:
         return map_state, cell_update, clipped, map2communicate, footprint_img
 
     def fuse_map(self, own_map_state, other_map_states, agent_id, fusion_mode):
-        """mappings.py:80-104: never mutates its inputs; successive whole-map passes."""
+        """mappings.py:80-104: never mutates its inputs; successive whole-map passes.  Like the reference under
+        numpy >= 2 the result is float64 as soon as one peer was fused (a float32 copy otherwise)."""
         if fusion_mode == "local":
             others = [other_map_states[k]["map2communicate"] for k in other_map_states if k != agent_id]
         elif isinstance(other_map_states, dict):
             others = [other_map_states[k]["map2communicate"] for k in other_map_states]
         else:
             others = list(other_map_states)
-        own = R.f32c(own_map_state)
+        own = np.array(own_map_state, dtype=np.float32, order="C", copy=True)  # np.float32(own.copy())
         if not others:
-            return own.copy()
+            return own
         rt = R.runtime(self.params)
         stack = np.ascontiguousarray(np.stack([R.f32c(o) for o in others]), dtype=np.float32)
-        out = np.empty_like(own)
+        out = np.empty(own.shape, dtype=np.float64)
         rc = rt.lib.ipp_fuse_map(rt.h, R.ptr(own), R.ptr(stack), len(others), own.size, R.ptr(out))
         rt.check(rc, "ipp_fuse_map")
         return out
@@ -79,14 +80,18 @@ class Mapping:
         return self.apply_update(map_section, measurement, mode)
 
     def apply_update(self, x, y, mode):
-        """mappings.py:109-119: x is clamped IN PLACE; y is an array or a Python float
-        (IG_baseline.py:240-245)."""
+        """mappings.py:109-119: x is clamped IN PLACE (in its own dtype); y is an array (float32 measurement) or a
+        Python float (IG_baseline.py:240-245: float64 scalar); returns float64 like the reference under numpy >= 2."""
         rt = R.runtime(self.params)
-        xc = R.f32c(x)
+        xc, x64 = R.native(x)
         scalar = np.ndim(y) == 0
-        yc = np.full(1, y, dtype=np.float32) if scalar else R.f32c(np.broadcast_to(y, np.shape(x)))
-        out = np.empty_like(xc)
-        rc = rt.lib.ipp_update_cells(rt.h, R.ptr(xc), R.ptr(yc), 1 if scalar else 0, xc.size, R.ptr(out))
+        if scalar:
+            y64 = 0 if isinstance(y, np.float32) else 1
+            yc = np.full(1, y, dtype=np.float64 if y64 else np.float32)
+        else:
+            yc, y64 = R.native(np.broadcast_to(y, np.shape(x)))
+        out = np.empty(xc.shape, dtype=np.float64)
+        rc = rt.lib.ipp_update_cells(rt.h, R.ptr(xc), x64, R.ptr(yc), y64, 1 if scalar else 0, xc.size, R.ptr(out))
         rt.check(rc, "ipp_update_cells")
         if isinstance(x, np.ndarray):
             x[...] = xc  # the reference's in-place clamp (mappings.py:110-111)

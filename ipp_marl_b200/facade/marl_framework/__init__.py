@@ -14,8 +14,9 @@ import sys
 _FACADE_PKGS = ("mapping", "sensors", "agent")
 _FACADE_UTILS = ("utils.reward", "utils.state")
 
-_ref = os.path.join(os.environ.get("IPP_REFERENCE_ROOT", "/root/reference"), "marl_framework")
-if os.path.isdir(_ref) and _ref not in __path__:
+_root = os.environ.get("IPP_REFERENCE_ROOT")  # set by facade.install(reference_root)
+_ref = os.path.join(_root, "marl_framework") if _root else None
+if _ref and os.path.isdir(_ref) and _ref not in __path__:
     __path__.append(_ref)
 
 

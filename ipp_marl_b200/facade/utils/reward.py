@@ -8,9 +8,9 @@ from utils import state as _state
 def get_utility_reward(state, state_, simulated_map, agent_state_space):
     """reward.py:68-82 -> (absolute, relative) utility of going from map `state` to `state_`."""
     rt = _state._rt()
-    a, b = R.f32c(state), R.f32c(state_)
+    (a, a64), (b, b64) = R.native(state), R.native(state_)
     out = np.zeros(2, dtype=np.float64)
-    rc = rt.lib.ipp_utility_reward(rt.h, R.ptr(a), R.ptr(b), a.size, R.ptr(out))
+    rc = rt.lib.ipp_utility_reward(rt.h, R.ptr(a), a64, R.ptr(b), b64, a.size, R.ptr(out))
     rt.check(rc, "ipp_utility_reward")
     return float(out[0]), float(out[1])
 

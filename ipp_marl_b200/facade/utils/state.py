@@ -19,11 +19,11 @@ def _rt():
 
 
 def get_shannon_entropy(p):
-    """state.py:118-121 — clamps its argument IN PLACE, returns H(p) in bits."""
+    """state.py:118-121 — clamps its argument IN PLACE, returns H(p) in bits in the dtype of p."""
     rt = _rt()
-    pc = R.f32c(p)
+    pc, is64 = R.native(p)
     out = np.empty_like(pc)
-    rc = rt.lib.ipp_shannon_entropy(rt.h, R.ptr(pc), pc.size, R.ptr(out))
+    rc = rt.lib.ipp_shannon_entropy(rt.h, R.ptr(pc), is64, pc.size, R.ptr(out))
     rt.check(rc, "ipp_shannon_entropy")
     if isinstance(p, np.ndarray):
         p[...] = pc

@@ -18,6 +18,17 @@ from . import _native as N
 NOISE_BY_ALTITUDE = {5: 0.01, 10: 0.265, 15: 0.375}  # sensors/models/sensor_models.py:13-22
 
 
+RANDOM_RANGES = (0, 15, 25, 100)  # agent/communication_log.py:22-31
+
+
+def comm_d2_of(r):
+    """Largest integer squared distance d2 (m^2) with sqrt(d2) <= r, evaluated like the reference's float64 test."""
+    d2 = int(np.floor(r * r)) + 2
+    while d2 > 0 and not (np.sqrt(np.float64(d2)) <= r):
+        d2 -= 1
+    return d2 if r >= 0 else -1
+
+
 class HostTables:
     def __init__(self, params):
         env = params["environment"]
@@ -74,6 +85,7 @@ class HostTables:
 
         # mappings.py:112-117: l_y in float32 (measurement is float32), l_p float64; k = exp(l_y - l_p)
         l_p = np.log(self.prior / (1 - self.prior))
+        self.l_prior = float(l_p)
         self.k_hi = np.zeros(self.n_alt, np.float32)
         self.k_lo = np.zeros(self.n_alt, np.float32)
         self.y_hi = np.zeros(self.n_alt, np.float32)
@@ -102,11 +114,12 @@ class HostTables:
         self.o_max = max(np.float32(0.9999 / 0.0001), self.p_max / (one - self.p_max))
 
         # communication_log.py:49-53: 0.001 <= ||dp|| <= range  <=>  0 < d2 <= comm_d2_max (d2 integer m^2)
-        r = self.comm_range
-        d2 = int(np.floor(r * r)) + 2
-        while d2 > 0 and not (np.sqrt(np.float64(d2)) <= r):
-            d2 -= 1
-        self.comm_d2_max = d2 if r >= 0 else -1
+        self.comm_d2_max = comm_d2_of(self.comm_range)
+        # communication_log.py:22-31: with fix_range False every CommunicationLog draws its range from
+        # np.random.seed(episode); randint(4) -> {0, 15, 25, 100} m — the same first draw that picks the ground
+        # truth's split (ground_truths.py:43-45), so the kernels index this table with the env's split
+        self.fix_range = bool(params["experiment"]["uav"].get("fix_range", True))
+        self.comm_d2_table = [comm_d2_of(float(r)) for r in RANDOM_RANGES]
         # r >= failure_rate with r = n / 2^24  <=>  n >= fail_thresh24
         fr = self.failure_rate
         n = int(np.ceil(fr * 16777216.0))
@@ -153,8 +166,12 @@ def make_config(tables, n_envs):
     c.x_dim_m, c.y_dim_m, c.budget = t.x_dim_m, t.y_dim_m, t.budget
     c.seed = t.seed & 0xFFFFFFFF
     c.comm_d2_max = min(int(t.comm_d2_max), 2**31 - 1)
+    c.fix_range = 1 if t.fix_range else 0
+    for i in range(4):
+        c.comm_d2_table[i] = int(t.comm_d2_table[i])
     c.fail_thresh24 = int(t.fail_thresh24)
     c.prior, c.k_out = float(t.prior), float(t.k_out)
+    c.l_prior = t.l_prior
     c.p_min, c.p_max, c.o_min, c.o_max = float(t.p_min), float(t.p_max), float(t.o_min), float(t.o_max)
     for i in range(t.n_alt):
         c.radius_x[i] = int(t.radius_x[i])

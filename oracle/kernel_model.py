@@ -80,11 +80,14 @@ class KernelTables:
         self.o_min = min(F32(0.0001 / 0.9999), o_lo32)
         self.o_max = max(F32(0.9999 / 0.0001), o_hi32)
         # comm range: largest integer squared distance still within range (communication_log.py:49-53)
-        r = float(geo.comm_range)
-        d2 = int(np.floor(r * r)) + 2
-        while d2 > 0 and not (np.sqrt(np.float64(d2)) <= r):
-            d2 -= 1
-        self.comm_d2_max = d2 if r >= 0 else -1
+        def d2_of(r):
+            d2 = int(np.floor(r * r)) + 2
+            while d2 > 0 and not (np.sqrt(np.float64(d2)) <= r):
+                d2 -= 1
+            return d2 if r >= 0 else -1
+
+        self.comm_d2_max = d2_of(float(geo.comm_range))
+        self.comm_d2_table = np.array([d2_of(float(r)) for r in (0, 15, 25, 100)], dtype=np.int64)
         fr = float(geo.failure_rate)
         # r >= failure_rate with r = n / 2^24  <=>  n >= ceil(fr * 2^24)
         n = int(np.ceil(fr * 16777216.0))
@@ -201,13 +204,17 @@ class KernelModelEnv:
     def comm(self):
         tab, A = self.tab, self.A
         out = np.zeros((self.B, A, A), dtype=bool)
+        d2_max = tab.comm_d2_max
+        if not self.geo.fix_range:  # per-env range index = first randint(4) of the episode's MT19937 stream
+            idx = np.array([np.random.RandomState(int(e)).randint(4) for e in np.asarray(self.episodes).ravel()])
+            d2_max = tab.comm_d2_table[idx]
         for i in range(A):
             key = hn.stream_key(self.geo.seed, self.episodes, i, self.t, hn.PURPOSE_COMM)
             for j in range(A):
                 d = self.pos[:, i] - self.pos[:, j]
                 d2 = (d * d).sum(-1)
                 n24 = hn.cell_hash(key, j) >> np.uint32(8)
-                out[:, i, j] = (d2 == 0) | ((d2 <= tab.comm_d2_max) & (n24 >= tab.fail_thresh24))
+                out[:, i, j] = (d2 == 0) | ((d2 <= d2_max) & (n24 >= tab.fail_thresh24))
         return out
 
     # ---- masks / moves ------------------------------------------------------------------------

@@ -52,7 +52,7 @@ def x_of(params):
     return params["environment"]["x_dim"]
 
 
-def episodes():
+def episodes(only=None, default=True):
     cases = [
         # name, params, episodes, keep_steps
         ("g50_a4", rh.synthetic_params(50, 4), (1, 2, 5), None),
@@ -60,7 +60,11 @@ def episodes():
         ("g50_a4_comm15_fail30", rh.synthetic_params(50, 4, comm_range=15, failure_rate=0.3), (4,), None),
         ("g50_a3_prior40", rh.synthetic_params(50, 3, comm_range=100, prior=0.4), (2,), (0, 1, 7, 14)),
         ("g100_a8", rh.synthetic_params(100, 8), (1,), (0, 1, 7, 14)),
+        # fix_range False (agent/communication_log.py:22-31): episodes 1 / 2 / 5 draw the ranges 15 / 0 / 100 m
+        ("g50_a4_randrange", rh.synthetic_params(50, 4, fix_range=False), (1, 2, 5), (0, 1, 7, 14)),
     ]
+    if only is not None:
+        cases = [c for c in cases if c[0] in only]
     for name, params, eps, keep in cases:
         for ep in eps:
             rec = rh.run_reference_episode(params, ep, features=(x_of(params) == 50))
@@ -71,6 +75,8 @@ def episodes():
             path = os.path.join(OUT, "episode_%s_ep%d.npz" % (name, ep))
             np.savez_compressed(path, **out)
             print("wrote", path, os.path.getsize(path))
+    if not default:
+        return
     # reference default (G = 493): rewards, moves, checksums and the final global map only
     params = rh.default_params()
     rec = rh.run_reference_episode(params, 1, features=True)
@@ -206,13 +212,48 @@ def ig_episodes():
         print("wrote", path, os.path.getsize(path))
 
 
+def lawn_episodes():
+    """The reference's coverage baseline (lawn_mower.py:38-315, eight hard-coded paths) run unmodified through
+    tests/ref_callers.py: entropy / F1 curves and the final map (strided sample + checksums for the 493x493 grid)."""
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(OUT))
+    for name, params, ep in (("g50_a8", rh.synthetic_params(50, 8), 2), ("default_g493_a8", dict(rh.default_params()), 1)):
+        params = json.loads(json.dumps(params))
+        params["experiment"]["missions"]["n_agents"] = 8  # lawn_mower.py hard-codes eight agents
+        with tempfile.TemporaryDirectory() as tmp:
+            pj, o = os.path.join(tmp, "p.json"), os.path.join(tmp, "o.npz")
+            with open(pj, "w") as f:
+                json.dump(params, f)
+            subprocess.run([sys.executable, os.path.join(root, "tests", "ref_callers.py"), "lawn", pj, str(ep), o, "ref"],
+                           check=True)
+            z = np.load(o)
+            out = {"entropy": z["entropy"], "f1": z["f1"], "update_calls": z["update_calls"],
+                   "map_sum": np.array(z["map"].sum()), "map_sumsq": np.array((z["map"] ** 2).sum()),
+                   "map_sample": z["map"][::7, ::7].copy() if z["map"].shape[0] > 100 else z["map"].copy(),
+                   "map_sample_stride": np.array(7 if z["map"].shape[0] > 100 else 1)}
+        out["params_json"] = np.array(json.dumps(params))
+        out["episode"] = np.array(ep)
+        out["versions_json"] = np.array(json.dumps(_versions()))
+        path = os.path.join(OUT, "lawn_%s_ep%d.npz" % (name, ep))
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     import sys
 
     if "ig" in sys.argv[1:]:
         ig_episodes()
+    elif "lawn" in sys.argv[1:]:
+        lawn_episodes()
+    elif "randrange" in sys.argv[1:]:
+        episodes(only=("g50_a4_randrange",), default=False)
     else:
         kats()
         episodes()
         ig_episodes()
+        lawn_episodes()

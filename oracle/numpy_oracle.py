@@ -42,6 +42,7 @@ class Geometry:
         self.n_agents = params["experiment"]["missions"]["n_agents"]
         self.prior = params["mapping"]["prior"]
         self.comm_range = params["experiment"]["uav"]["communication_range"]
+        self.fix_range = params["experiment"]["uav"].get("fix_range", True)
         self.failure_rate = params["experiment"]["uav"]["failure_rate"]
         self.angle_x = sen["field_of_view"]["angle_x"]
         self.angle_y = sen["field_of_view"]["angle_y"]
@@ -153,13 +154,16 @@ def comm_matrix(geo, positions, episode, t):
     """agent/communication_log.py:39-58: row i = agents whose message i receives (incl. itself)."""
     n = len(positions)
     out = np.zeros((n, n), dtype=np.uint8)
+    comm_range = geo.comm_range
+    if not geo.fix_range:  # communication_log.py:22-31: re-drawn (identically) by every CommunicationLog(params, episode)
+        comm_range = (0, 15, 25, 100)[np.random.RandomState(episode).randint(4)]
     for i in range(n):
         key = hn.stream_key(geo.seed, episode, i, t, hn.PURPOSE_COMM)
         for j in range(n):
             d = np.linalg.norm(np.asarray(positions[i]) - np.asarray(positions[j]), ord=2)
             r = float(hn.uniform01(hn.cell_hash(key, j)))
             ok = d < 0.001
-            if 0.001 <= d <= geo.comm_range and r >= geo.failure_rate:
+            if 0.001 <= d <= comm_range and r >= geo.failure_rate:
                 ok = True
             out[i, j] = ok
     return out

@@ -1,10 +1,11 @@
-"""Drive the UNMODIFIED reference (dmar-bonn/ipp-marl) from /root/reference.
+"""Drive the UNMODIFIED reference (dmar-bonn/ipp-marl).
 
-TEST INFRASTRUCTURE, build-container only: /root/reference does not exist on
-the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or ``bench.py``
-imports this module.  It is used by ``oracle/make_golden.py`` to write the
-fixtures in ``tests/golden/`` and by the ``not gpu`` tests that re-check the
-numpy restatement against the live reference when it is present.
+TEST INFRASTRUCTURE.  The reference tree is looked up, in this order, at ``$IPP_REFERENCE_ROOT``,
+``baseline/_ref`` (the verbatim install made by ``scripts/install_ref.py`` during ``build()``; git-ignored,
+it travels to the GPU box with the snapshot) and ``/root/reference`` (build container only).  Used by
+``oracle/make_golden.py`` to write the fixtures in ``tests/golden/``, by the tests that re-check the numpy
+restatement / the CUDA path against the live reference, and by ``bench.py``'s CPU-baseline legs
+(``oracle/ref_timing.py``).  Never imported by the product package.
 
 What is patched (and why) — nothing else of the reference is touched:
   * ``matplotlib`` / ``seaborn`` / ``cma`` are stubbed in ``sys.modules`` (absent
@@ -30,7 +31,20 @@ import numpy as np
 
 from . import noise as hn
 
-REFERENCE_ROOT = os.environ.get("IPP_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def reference_root():
+    env = os.environ.get("IPP_REFERENCE_ROOT")
+    if env:
+        return env
+    local = os.path.join(_REPO, "baseline", "_ref")
+    if os.path.isdir(os.path.join(local, "marl_framework")):
+        return local
+    return "/root/reference"
+
+
+REFERENCE_ROOT = reference_root()
 _FRAMEWORK = os.path.join(REFERENCE_ROOT, "marl_framework")
 
 
@@ -115,7 +129,8 @@ def default_params():
     return ns.load_params(os.path.join(_FRAMEWORK, "params.yaml"))
 
 
-def synthetic_params(x_dim=50, n_agents=4, comm_range=25, failure_rate=0, seed=3, budget=14, prior=0.5):
+def synthetic_params(x_dim=50, n_agents=4, comm_range=25, failure_rate=0, seed=3, budget=14, prior=0.5,
+                     fix_range=True):
     """SURVEY.md section 8d synthetic family: FoV 90/90, 10x10 px -> 1 cell = 1 m."""
     p = copy.deepcopy(default_params())
     p["environment"]["x_dim"] = x_dim
@@ -128,6 +143,7 @@ def synthetic_params(x_dim=50, n_agents=4, comm_range=25, failure_rate=0, seed=3
     p["experiment"]["missions"]["n_agents"] = n_agents
     p["experiment"]["uav"]["communication_range"] = comm_range
     p["experiment"]["uav"]["failure_rate"] = failure_rate
+    p["experiment"]["uav"]["fix_range"] = fix_range
     p["experiment"]["constraints"]["budget"] = budget
     p["mapping"]["prior"] = prior
     return p

@@ -37,9 +37,11 @@ def test_facade_host_logic(tmp_path, name):
 
 def test_reference_callers_import_on_top_of_facade():
     """coma_wrapper.py / IG_baseline.py / lawn_mower.py (unchanged) resolve their env imports to the facade."""
-    ref = os.environ.get("IPP_REFERENCE_ROOT", "/root/reference")
+    from oracle import ref_harness as rh
+
+    ref = rh.reference_root()
     if not os.path.isdir(os.path.join(ref, "marl_framework")):
-        pytest.skip("reference checkout not present (GPU box)")
+        pytest.skip("reference tree not installed (scripts/install_ref.py)")
     code = r"""
 import sys, types
 sys.path.insert(0, %r)
@@ -70,7 +72,8 @@ print('ok')
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["g50_a4_ep2", "g50_a4_comm15_fail30_ep4", "g50_a2_ep3"])
+@pytest.mark.parametrize("name", ["g50_a4_ep2", "g50_a4_comm15_fail30_ep4", "g50_a2_ep3", "g50_a3_prior40_ep2",
+                                  "g50_a4_randrange_ep5"])
 def test_facade_episode_vs_reference_golden(tmp_path, name):
     path = [p for p in golden_episodes() if name in p][0]
     g = load_episode(path)
@@ -80,11 +83,9 @@ def test_facade_episode_vs_reference_golden(tmp_path, name):
         assert np.array_equal(r[key], g[key]), key
     assert np.array_equal(r["mask"], g["mask"])
     for key in ("global", "local_fused", "local_after_move"):
-        s = gate_stats(g[key], r[key])
-        # The facade hands float32 arrays back after EVERY call (fuse, update), i.e. it rounds twice per
-        # step where the reference (float64 between fuse and update) and the batched kernels round once;
-        # near the 0.9999 clamp one float32 ulp of p is 6e-4 in log-odds, so a handful of cells that later
-        # receive contrary evidence can leave the 1e-5 gate.  Bound: <= 1 cell in 20 000, max 1e-4.
-        assert s["fail_gate"] <= max(1, s["n"] // 20000) and s["max_abs"] < 1e-4, (key, s)
+        s = gate_stats(g[key], r[key][g["map_steps"]])
+        # the single-map entry points follow the reference's dtype flow (float64 out of fuse / update, float32 only
+        # where the reference stores float32), so the north-star gate holds without exceptions
+        assert s["fail_gate"] == 0 and s["max_abs"] < 2e-6, (key, s)
     assert np.allclose(r["reward_rel"], g["reward_rel"], rtol=1e-5, atol=1e-5)
     assert np.allclose(r["reward_abs"], g["reward_abs"], rtol=1e-5, atol=1e-5)

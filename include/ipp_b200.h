@@ -82,6 +82,9 @@ typedef struct ipp_config {
   int32_t fix_range;       /* experiment.uav.fix_range; 0 = per-episode random range (communication_log.py:22-31): */
   int32_t comm_d2_table[4];/* comm_d2_max of the ranges {0, 15, 25, 100} m, indexed by the episode's first         */
                            /* randint(4) after np.random.seed(episode) (drawn by ipp_reset: call it on this handle) */
+  int32_t n_meas;          /* measurement values the simulation can produce (mapping/simulations.py:47-50) and their   */
+  float meas_y[16];        /* float32 logits AS NUMPY EVALUATES THEM (np.log(y / (1 - y)) on float32, mappings.py:113):  */
+  float meas_ly[16];       /* y_hi / y_lo of every altitude and 0.5; used by the single-map entry points               */
   double l_prior;          /* np.log(prior / (1 - prior)) in float64: mapping/mappings.py:116 (single-map entry points) */
 } ipp_config;
 

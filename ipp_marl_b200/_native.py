@@ -28,6 +28,7 @@ class IppConfig(C.Structure):
         ("flip_thresh", C.c_uint32 * MAX_ALT),
         ("cell_x", C.c_int32 * MAX_LATTICE), ("cell_y", C.c_int32 * MAX_LATTICE),
         ("fix_range", C.c_int32), ("comm_d2_table", C.c_int32 * 4),
+        ("n_meas", C.c_int32), ("meas_y", C.c_float * 16), ("meas_ly", C.c_float * 16),
         ("l_prior", C.c_double),
     ]
 

@@ -467,7 +467,7 @@ int ipp_update_cells(ipp_handle* h, void* x_host, int32_t x_f64, const void* y_h
   double* dout = reinterpret_cast<double*>(base + xb_al + yb_al);
   IPP_CUDA(h, cudaMemcpy(dx, x_host, xb, cudaMemcpyHostToDevice));
   IPP_CUDA(h, cudaMemcpy(dy, y_host, yb, cudaMemcpyHostToDevice));
-  IPP_CUDA(h, ipp::launch_update_cells(dx, x_f64, dy, y_f64, y_is_scalar, h->cfg.l_prior, n, dout, 0));
+  IPP_CUDA(h, ipp::launch_update_cells(h->cfg, dx, x_f64, dy, y_f64, y_is_scalar, n, dout, 0));
   IPP_CUDA(h, cudaMemcpy(x_host, dx, xb, cudaMemcpyDeviceToHost));
   IPP_CUDA(h, cudaMemcpy(out_host, dout, 8 * (size_t)n, cudaMemcpyDeviceToHost));
   return IPP_OK;
@@ -509,7 +509,7 @@ int ipp_fuse_map(ipp_handle* h, const float* own_host, const float* others_host,
   double* dout = reinterpret_cast<double*>(base + nb_al + ob_al);
   IPP_CUDA(h, cudaMemcpy(down, own_host, nb, cudaMemcpyHostToDevice));
   if (n_others > 0) IPP_CUDA(h, cudaMemcpy(doth, others_host, ob, cudaMemcpyHostToDevice));
-  IPP_CUDA(h, ipp::launch_fuse_map(down, doth, n_others, h->cfg.l_prior, cells, dout, 0));
+  IPP_CUDA(h, ipp::launch_fuse_map(h->cfg, down, doth, n_others, cells, dout, 0));
   IPP_CUDA(h, cudaMemcpy(out_host, dout, 8 * (size_t)cells, cudaMemcpyDeviceToHost));
   return IPP_OK;
 }

@@ -44,11 +44,24 @@ struct Flow<double> {
   static __device__ __forceinline__ bool lt(double v, double c) { return v < c; }
 };
 
+// logit(y) of a measurement value: float32 measurements come from a handful of values (y_hi / y_lo per altitude, 0.5)
+// whose float32 logits the host evaluated with numpy itself (ipp_config.meas_y / meas_ly); anything else is computed
+struct MeasTable {
+  int n;
+  float y[16], ly[16];
+};
+__device__ __forceinline__ float logit_y(const MeasTable& mt, float y) {
+  for (int i = 0; i < mt.n; ++i)
+    if (mt.y[i] == y) return mt.ly[i];
+  return Flow<float>::logit(y);
+}
+__device__ __forceinline__ double logit_y(const MeasTable&, double y) { return Flow<double>::logit(y); }
+
 template <typename XT, typename YT>
-__device__ __forceinline__ double flow_update(XT& x, const YT y, const double l_prior) {
+__device__ __forceinline__ double flow_update(XT& x, const YT y, const double l_prior, const MeasTable& mt) {
   x = Flow<XT>::clamp(x);
   const XT lx = Flow<XT>::logit(x);
-  const YT ly = Flow<YT>::logit(y);
+  const YT ly = logit_y(mt, y);
   double lxy;
   if (sizeof(XT) == 4 && sizeof(YT) == 4) lxy = (double)__fadd_rn((float)lx, (float)ly);  // float32 + float32
   else lxy = (double)lx + (double)ly;
@@ -59,10 +72,11 @@ __device__ __forceinline__ double flow_update(XT& x, const YT y, const double l_
 // Mapping.apply_update: x clamped in place (in its dtype), out float64.  y: array or one scalar of type YT.
 template <typename XT, typename YT>
 __global__ void update_cells_kernel(XT* __restrict__ x, const YT* __restrict__ y, const int y_is_scalar,
-                                    const double l_prior, const int64_t n, double* __restrict__ out) {
+                                    const double l_prior, const __grid_constant__ MeasTable mt, const int64_t n,
+                                    double* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     XT xv = x[i];
-    out[i] = flow_update<XT, YT>(xv, y_is_scalar ? y[0] : y[i], l_prior);
+    out[i] = flow_update<XT, YT>(xv, y_is_scalar ? y[0] : y[i], l_prior, mt);
     x[i] = xv;
   }
 }
@@ -70,14 +84,15 @@ __global__ void update_cells_kernel(XT* __restrict__ x, const YT* __restrict__ y
 // Mapping.fuse_map: own (already cast to float32 by `np.float32(own.copy())`, mappings.py:83,93,100) fused with
 // n_others float32 maps in order; the first pass reads float32 and returns float64, the others run in float64.
 __global__ void fuse_map_kernel(const float* __restrict__ own, const float* __restrict__ others, const int n_others,
-                                const double l_prior, const int64_t n, double* __restrict__ out) {
+                                const double l_prior, const __grid_constant__ MeasTable mt, const int64_t n,
+                                double* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float x0 = own[i];
     double v = (double)x0;
     for (int k = 0; k < n_others; ++k) {
       const float y = others[(int64_t)k * n + i];
-      if (k == 0) v = flow_update<float, float>(x0, y, l_prior);
-      else v = flow_update<double, float>(v, y, l_prior);
+      if (k == 0) v = flow_update<float, float>(x0, y, l_prior, mt);
+      else v = flow_update<double, float>(v, y, l_prior, mt);
     }
     out[i] = v;
   }
@@ -178,23 +193,36 @@ static int grid_for(int64_t n, int threads, int cap) {
   return (int)b;
 }
 
-cudaError_t launch_update_cells(void* x, int x_f64, const void* y, int y_f64, int y_is_scalar, double l_prior,
+static MeasTable meas_table(const ipp_config& cfg) {
+  MeasTable mt;
+  mt.n = cfg.n_meas < 0 ? 0 : (cfg.n_meas > 16 ? 16 : cfg.n_meas);
+  for (int i = 0; i < 16; ++i) {
+    mt.y[i] = cfg.meas_y[i];
+    mt.ly[i] = cfg.meas_ly[i];
+  }
+  return mt;
+}
+
+cudaError_t launch_update_cells(const ipp_config& cfg, void* x, int x_f64, const void* y, int y_f64, int y_is_scalar,
                                 int64_t n, double* out, cudaStream_t s) {
   const int g = grid_for(n, 256, 148 * 8);
+  const double l_prior = cfg.l_prior;
+  const MeasTable mt = meas_table(cfg);
   if (x_f64 && y_f64)
-    update_cells_kernel<double, double><<<g, 256, 0, s>>>((double*)x, (const double*)y, y_is_scalar, l_prior, n, out);
+    update_cells_kernel<double, double><<<g, 256, 0, s>>>((double*)x, (const double*)y, y_is_scalar, l_prior, mt, n, out);
   else if (x_f64)
-    update_cells_kernel<double, float><<<g, 256, 0, s>>>((double*)x, (const float*)y, y_is_scalar, l_prior, n, out);
+    update_cells_kernel<double, float><<<g, 256, 0, s>>>((double*)x, (const float*)y, y_is_scalar, l_prior, mt, n, out);
   else if (y_f64)
-    update_cells_kernel<float, double><<<g, 256, 0, s>>>((float*)x, (const double*)y, y_is_scalar, l_prior, n, out);
+    update_cells_kernel<float, double><<<g, 256, 0, s>>>((float*)x, (const double*)y, y_is_scalar, l_prior, mt, n, out);
   else
-    update_cells_kernel<float, float><<<g, 256, 0, s>>>((float*)x, (const float*)y, y_is_scalar, l_prior, n, out);
+    update_cells_kernel<float, float><<<g, 256, 0, s>>>((float*)x, (const float*)y, y_is_scalar, l_prior, mt, n, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fuse_map(const float* own, const float* others, int n_others, double l_prior, int64_t n,
+cudaError_t launch_fuse_map(const ipp_config& cfg, const float* own, const float* others, int n_others, int64_t n,
                             double* out, cudaStream_t s) {
-  fuse_map_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(own, others, n_others, l_prior, n, out);
+  fuse_map_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(own, others, n_others, cfg.l_prior, meas_table(cfg), n,
+                                                            out);
   return cudaGetLastError();
 }
 

@@ -80,9 +80,9 @@ cudaError_t launch_eval_metrics(const ipp_config& cfg, const ipp_state& st, doub
                                 cudaStream_t s);
 
 // single-map helpers used by the facade entry points (device pointers; dtype flags: 0 = float32, 1 = float64)
-cudaError_t launch_update_cells(void* x, int x_f64, const void* y, int y_f64, int y_is_scalar, double l_prior,
+cudaError_t launch_update_cells(const ipp_config& cfg, void* x, int x_f64, const void* y, int y_f64, int y_is_scalar,
                                 int64_t n, double* out, cudaStream_t s);
-cudaError_t launch_fuse_map(const float* own, const float* others, int n_others, double l_prior, int64_t n,
+cudaError_t launch_fuse_map(const ipp_config& cfg, const float* own, const float* others, int n_others, int64_t n,
                             double* out, cudaStream_t s);
 cudaError_t launch_measure(const ipp_config& cfg, const uint8_t* gt, const int32_t* rect, uint32_t key,
                            uint32_t thresh, float y_hi, float y_lo, float* out, cudaStream_t s);

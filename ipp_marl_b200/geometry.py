@@ -105,6 +105,13 @@ class HostTables:
             self.k_lo[i] = np.float32(np.exp(np.float64(l_lo) - l_p))
             self.flip_thresh[i] = np.uint32(int(np.floor(float(noise) * 4294967296.0)))
             self.noise[i] = noise
+        # the measurement values and their float32 logits exactly as numpy evaluates them (mappings.py:113); the
+        # single-map kernels look logit(y) up here so that cancelling evidence (e.g. 0.625 then 0.375: the two float32
+        # logits differ in the last bit) lands on the same side of 0.5 as in the reference
+        ys = sorted({float(v) for v in list(self.y_hi) + list(self.y_lo)} | {0.5})[:16]
+        self.meas_y = np.array(ys, dtype=np.float32)
+        with np.errstate(divide="ignore"):
+            self.meas_ly = np.log(self.meas_y / (np.float32(1) - self.meas_y)).astype(np.float32)
         half = np.float32(0.5)
         self.k_out = np.float32(np.exp(np.float64(np.log(half / (1 - half))) - l_p))
         self.p_min = np.float32(0.0001)   # mappings.py:110-111 evaluated in float32 on the first pass
@@ -172,6 +179,10 @@ def make_config(tables, n_envs):
     c.fail_thresh24 = int(t.fail_thresh24)
     c.prior, c.k_out = float(t.prior), float(t.k_out)
     c.l_prior = t.l_prior
+    c.n_meas = len(t.meas_y)
+    for i in range(len(t.meas_y)):
+        c.meas_y[i] = float(t.meas_y[i])
+        c.meas_ly[i] = float(t.meas_ly[i])
     c.p_min, c.p_max, c.o_min, c.o_max = float(t.p_min), float(t.p_max), float(t.o_min), float(t.o_max)
     for i in range(t.n_alt):
         c.radius_x[i] = int(t.radius_x[i])

@@ -52,7 +52,6 @@ def main():
         import mapping.mappings as m1
 
         mapping_modules = (m1,)
-        NC.seed_episode = None
     else:
         ns = rh.load()
         rh.install_noise_patch()
@@ -62,14 +61,19 @@ def main():
 
     # ---- measurement streams by call count (class-level wrapper: the callers build their own Mapping objects) ----
     n_streams = 8 if mode == "lawn" else A
-    calls = {"n": 0}
+    calls = {"n": 0, "seen": None}  # seen: union of all footprints so far (for the F1 knife-edge bounds)
     for mod in mapping_modules:
         real = mod.Mapping.update_grid_map
 
         def update_grid_map(self, *a, _real=real, **k):
             NC.agent, NC.index = calls["n"] % n_streams, calls["n"] // n_streams
             calls["n"] += 1
-            return _real(self, *a, **k)
+            out = _real(self, *a, **k)
+            yu, yd, xl, xr = (int(v) for v in out[2])
+            if calls["seen"] is None:
+                calls["seen"] = np.zeros(np.shape(out[0]), dtype=bool)
+            calls["seen"][xl:xr, yu:yd] = True
+            return out
 
         mod.Mapping.update_grid_map = update_grid_map
 
@@ -88,6 +92,26 @@ def main():
 
     writer = rh._Stub("writer")
     res = {}
+    f1_lo, f1_hi = [], []
+
+    def wrap_wrmse(mod):
+        """Record, next to every F1 the caller computes (utils/utils.py:43-76), the range it can take when the cells
+        within 2e-5 of the 0.5 threshold that some footprint has reached are counted either way
+        (tests/helpers.py::f1_bounds)."""
+        from tests.helpers import f1_bounds
+
+        real = mod.get_wrmse
+
+        def get_wrmse(map_state, map_simulation):
+            lo, hi = f1_bounds(map_state, map_simulation, seen=calls["seen"])
+            if os.environ.get("IPP_DUMP_WRMSE"):
+                res.setdefault("_maps", []).append(np.array(map_state, dtype=np.float64))
+            f1_lo.append(lo)
+            f1_hi.append(hi)
+            return real(map_state, map_simulation)
+
+        mod.get_wrmse = get_wrmse
+
     if mode == "coma":
         from marl_framework.batch_memory import BatchMemory
         from marl_framework.coma_wrapper import COMAWrapper
@@ -134,6 +158,7 @@ def main():
     elif mode == "ig":
         import IG_baseline as ig_mod
 
+        wrap_wrmse(ig_mod)
         base = ig_mod.IG_baseline(params, writer, episode)
         rec = {"action": [], "gains": []}
         real_ind, real_sel = base.get_individual_ig, base.select_action
@@ -159,6 +184,7 @@ def main():
     elif mode == "lawn":
         import lawn_mower as lm_mod
 
+        wrap_wrmse(lm_mod)
         lm = lm_mod.LawnMower(params, writer, episode)
         _, entropies, f1s = lm.execute()
         res["entropy"] = np.array([float(v) for v in entropies])
@@ -166,7 +192,10 @@ def main():
         res["map"] = np.array(lm.map, dtype=np.float64)
     else:
         raise SystemExit("unknown mode " + mode)
+    if "_maps" in res:
+        res["wrmse_maps"] = np.array(res.pop("_maps"))
     res["update_calls"] = np.array(calls["n"])
+    res["f1_lo"], res["f1_hi"] = np.array(f1_lo), np.array(f1_hi)
     np.savez(out, **res)
 
 

@@ -62,7 +62,7 @@ def test_update_cells_kat_float32_and_python_float():
     assert np.array_equal(x, xc)
     ly = np.log(y / (1 - y))
     ref = 1 - 1 / (1 + np.exp(np.log(xc / (1 - xc)) + ly - 0.0))
-    assert np.allclose(out, ref, rtol=1e-7, atol=0)
+    assert np.allclose(out, ref, rtol=1e-6, atol=0)  # float32 log of y: numpy's SIMD logf vs a correctly rounded one
 
 
 def test_shannon_entropy_kat_and_in_place_clamp():

@@ -57,6 +57,15 @@ def _check_coma(r, g, maps=True):
         _gate(g["global_final_f32"], r["global"][-1], "final global map")
 
 
+def _check_f1(r, f1_ref):
+    """F1 thresholds the map at > 0.5 (utils/utils.py:66-68); cells where evidence cancels sit at 0.5 +- 1e-8 and
+    their side is decided by the last bit of numpy's float32 log in the reference.  The reference's F1 must lie in
+    the range the facade's map allows when exactly those cells are counted either way, and our own F1 inside it too."""
+    assert len(r["f1"]) == len(f1_ref) == len(r["f1_lo"])
+    assert np.all(r["f1_lo"] - 1e-12 <= f1_ref) and np.all(f1_ref <= r["f1_hi"] + 1e-12), (r["f1_lo"], f1_ref, r["f1_hi"])
+    assert np.all(r["f1_lo"] - 1e-12 <= r["f1"]) and np.all(r["f1"] <= r["f1_hi"] + 1e-12)
+
+
 def test_unchanged_callers_reproduce_the_goldens_on_the_reference_itself(tmp_path):
     """Pins the runner: coma_wrapper / episode_generator driven by tests/ref_callers.py on the reference's own
     modules give the committed golden episode bit for bit (incl. the observation / critic-state tensors)."""
@@ -78,8 +87,22 @@ def test_coma_wrapper_unchanged_on_facade(tmp_path, name):
     r = _run("coma", g["params"], g["episode"], "facade", tmp_path)
     _check_coma(r, g, maps="global" in g)
     # network inputs built by the reference's actor/critic transformations from facade outputs
-    so = gate_stats(g["obs"], r["obs"], atol=2e-5)
-    ss = gate_stats(g["state"], r["state"], atol=2e-5)
+    # The weighted-entropy channels (3: local, 8: global) multiply H by w = 1 / 0 / 0.5 chosen by comparing the POOLED
+    # probability (channels 5 / 9) with 0.501 / 0.499 (utils/state.py:67-73): a pooled cell within 1e-6 of a threshold
+    # may take either weight (its probability itself agrees to 1e-7), so those cells are exempt in channels 3 / 8.
+    ref_o, got_o = np.array(g["obs"], dtype=np.float64), np.array(r["obs"], dtype=np.float64)
+    ref_s, got_s = np.array(g["state"], dtype=np.float64), np.array(r["state"], dtype=np.float64)
+
+    def edge(prob):
+        return (np.abs(prob - 0.501) < 1e-6) | (np.abs(prob - 0.499) < 1e-6)
+
+    e_loc, e_glob = edge(ref_o[..., 5]), edge(ref_s[..., 9])
+    got_o[..., 3] = np.where(e_loc, ref_o[..., 3], got_o[..., 3])
+    got_s[..., 3] = np.where(e_loc, ref_s[..., 3], got_s[..., 3])
+    got_s[..., 8] = np.where(e_glob, ref_s[..., 8], got_s[..., 8])
+    assert e_loc.mean() < 0.01 and e_glob.mean() < 0.01  # a pooled cell on a threshold stays there while unobserved
+    so = gate_stats(ref_o, got_o, atol=2e-5)
+    ss = gate_stats(ref_s, got_s, atol=2e-5)
     assert so["fail_gate"] == 0 and ss["fail_gate"] == 0, (so, ss)
 
 
@@ -94,7 +117,7 @@ def test_ig_baseline_unchanged_on_facade(tmp_path, name):
     assert np.array_equal(r["action"], z["action"])
     assert np.allclose(r["gains"], z["gains"], rtol=1e-5, atol=1e-7)
     assert np.allclose(r["entropy"], z["entropy"], rtol=1e-5, atol=1e-6)
-    assert np.allclose(r["f1"], z["f1"], rtol=0, atol=1e-12)
+    _check_f1(r, z["f1"])
 
 
 @pytest.mark.gpu
@@ -107,7 +130,7 @@ def test_lawn_mower_unchanged_on_facade(tmp_path, name):
     r = _run("lawn", params, ep, "facade", tmp_path)
     assert int(r["update_calls"]) == int(z["update_calls"])
     assert np.allclose(r["entropy"], z["entropy"], rtol=1e-5, atol=1e-6)
-    assert np.allclose(r["f1"], z["f1"], rtol=0, atol=1e-12)
+    _check_f1(r, z["f1"])
     k = int(z["map_sample_stride"])
     _gate(z["map_sample"], r["map"][::k, ::k], "final map")
     assert abs(float(r["map"].sum()) - float(z["map_sum"])) <= 1e-6 * float(z["map_sum"])

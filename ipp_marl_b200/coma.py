@@ -2,7 +2,7 @@
 
 Stays PyTorch (tensor cores through cuDNN / cuBLAS): the actor / critic CNNs are the reference's
 architectures (actor/network.py:19-28, critic/network.py:18-26 — `fc2` is constructed but unused there;
-kept so that the reference's checkpoints load), the counterfactual-baseline policy gradient follows
+kept so that the reference's layer names / checkpoints map one to one), the counterfactual-baseline policy gradient follows
 actor/learner.py:52-101 and the critic regression critic/learner.py:76-99.  What changes is the shape
 of the data: B environments are rolled out in lock-step on the GPU (env kernels + feature kernels),
 the actor runs once per timestep on [B*A, 11, 11, 7], and TD(lambda) targets are computed for all
@@ -18,7 +18,11 @@ Differences from the reference, all deliberate and listed:
   * `reference_frozen_target=True` reproduces the reference's never-updated target critic
     (coma_mission.py:90 hands build_td_targets the construction-time copy, coma_wrapper.py:34); set it
     to False for the conventional hard update every `copy_rate` updates;
-  * mini-batches are large (default 8192 transitions) instead of 60.
+  * mini-batches are large (default 8192 transitions) instead of 60;
+  * one rollout collects B * world episodes, so the epsilon schedule (annealed per EPISODE in the reference,
+    actor/network.py:53-58) advances by that many episodes per rollout (`COMATrainer.episodes_per_rollout`);
+  * arithmetic is float32 like the reference by default; bf16 autocast is opt-in (`compute_dtype`);
+  * checkpoints are state dicts, not pickled modules (`mission.save_actor` / `mission.load_actor_state` reads both).
 """
 import math
 
@@ -133,37 +137,100 @@ def coma_critic_loss(q_values, actions, td_targets):
 
 
 class FlatGradAllReduce:
-    """One NCCL all-reduce (mean) of all gradients of a module per optimizer step."""
+    """The only collective of the path: the mean of a network's gradients over the ranks, once
+    per optimizer step, over NCCL.
 
-    def __init__(self, module):
+    The gradients of all parameters live in ONE flat float32 buffer (every ``p.grad`` is a view into it, so nothing is
+    copied in or out) that is cut into a few contiguous buckets.  Backward fills the buckets from the last layer to
+    the first; a post-accumulate hook launches a bucket's asynchronous all-reduce as soon as its last gradient has
+    arrived, so the transfer of the late layers overlaps the backward pass of the early ones.  ``finish()`` (=
+    ``__call__``) waits for the outstanding work and scales by 1 / world.  Parameters that never receive a gradient
+    (the reference's unused ``fc2``) are found during the first backward, which is reduced in one piece.
+    Use ``zero_grad(set_to_none=False)`` with it: the views must survive."""
+
+    def __init__(self, module, bucket_bytes=4 << 20):
         self.params = [p for p in module.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.params[0].device)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        # buckets = contiguous ranges of the flat buffer, at least bucket_bytes each, built from the LAST parameter
+        # backwards (the order in which backward produces gradients)
+        self.buckets = []  # (lo, hi, [param indices])
+        hi, members = n, []
+        for i in range(len(self.params) - 1, -1, -1):
+            members.append(i)
+            if (hi - self.offsets[i]) * 4 >= bucket_bytes or i == 0:
+                self.buckets.append((self.offsets[i], hi, members))
+                hi, members = self.offsets[i], []
+        self.bucket_of = {}
+        for b, (_, _, mem) in enumerate(self.buckets):
+            for i in mem:
+                self.bucket_of[i] = b
+        self.used = None          # indices of the parameters that receive gradients (known after the first backward)
+        self._seen = set()
+        self._pending = []
+        self._launched = set()
+        self.bytes_reduced = 0    # bookkeeping for the benchmarks
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
 
-    def __call__(self):
+    @staticmethod
+    def _world():
         import torch.distributed as dist
 
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            self.flat[off:off + n].copy_((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1))
-            off += n
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.div_(dist.get_world_size())
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = torch.empty_like(p)
-            p.grad.copy_(self.flat[off:off + n].view_as(p))
-            off += n
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _make_hook(self, i):
+        def hook(param):
+            self._seen.add(i)
+            if self.used is None or self._world() == 1:
+                return
+            b = self.bucket_of[i]
+            if b in self._launched:
+                return
+            if all((j in self._seen) or (j not in self.used) for j in self.buckets[b][2]):
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        import torch.distributed as dist
+
+        lo, hi, _ = self.buckets[b]
+        self._launched.add(b)
+        self._pending.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        self.bytes_reduced += 4 * (hi - lo)
+
+    def finish(self):
+        world = self._world()
+        if self.used is None:
+            self.used = set(self._seen)
+        if world > 1:
+            for b in range(len(self.buckets)):  # whatever backward did not trigger (first call; unused layers)
+                if b not in self._launched:
+                    self._launch(b)
+            for w in self._pending:
+                w.wait()
+            self.flat.div_(world)
+        self._pending, self._launched, self._seen = [], set(), set()
+
+    __call__ = finish
 
 
 class COMATrainer:
-    def __init__(self, env, params, minibatch=8192, data_passes=None, compute_dtype=torch.bfloat16,
-                 reference_frozen_target=True, seed=0):
+    """``compute_dtype``: float32 like the reference (default; TF32 is NOT enabled by this class) or
+    ``torch.bfloat16`` (autocast of the CNN forward / backward, opt-in, faster on tensor cores).
+
+    Epsilon schedule: the reference anneals eps linearly in the EPISODE index (actor/network.py:53-58,
+    ``eps_anneal_phase`` = 10 000 episodes).  One rollout here collects ``B * world`` episodes, so the counter advances
+    by that many per rollout (``episodes_per_rollout``; pass 1 to anneal per rollout instead)."""
+
+    def __init__(self, env, params, minibatch=8192, data_passes=None, compute_dtype=torch.float32,
+                 reference_frozen_target=True, seed=0, episodes_per_rollout=None):
         self.env = env
         self.params = params
         net = params["networks"]
@@ -187,6 +254,9 @@ class COMATrainer:
         self.sync_critic = FlatGradAllReduce(self.critic)
         self.updates = 0
         self.episodes_done = 0
+        world = FlatGradAllReduce._world()
+        self.episodes_per_rollout = env.B * world if episodes_per_rollout is None else int(episodes_per_rollout)
+        self._last_eps_episode = 0
         B, A, T, P = env.B, env.A, env.T, env.tables.px
         self.buf_obs = torch.empty((T, B, A, P, P, 7), dtype=torch.float32, device=dev)
         self.buf_state = torch.empty((T, B, A, P, P, 12), dtype=torch.float32, device=dev)
@@ -204,6 +274,7 @@ class COMATrainer:
         env = self.env
         env.reset(episodes)
         eps = epsilon(self.episodes_done, *self.eps_cfg)
+        self._last_eps_episode = self.episodes_done
         B, A = env.B, env.A
         for t in range(env.T):
             rel, ab = env.observe()
@@ -216,17 +287,40 @@ class COMATrainer:
             self.buf_mask[t].copy_(env.masks)
             self.buf_rew[t].copy_(rel)
             self.buf_abs[t].copy_(ab)
-        self.episodes_done += 1
+        self.episodes_done += self.episodes_per_rollout
         return self.buf_rew.sum(0).mean()
 
     def _masks6(self, m_u8):
         return ((m_u8[..., None].int() >> torch.arange(N_ACTIONS, device=m_u8.device)) & 1).float()
 
+    def learn_minibatch(self, state, obs, act, masks, td, eps):
+        """One critic step then one actor step on a mini-batch (coma_mission.py:93-98): critic regression on the TD
+        targets (critic/learner.py:76-99), Q re-evaluated after the step without grad (:101-105), counterfactual
+        policy gradient (actor/learner.py:52-101).  The gradient all-reduce of each network overlaps its backward.
+        Returns (critic_loss, actor_loss, advantage, q_after)."""
+        with self._autocast():
+            q = self.critic(state)
+        loss_c = coma_critic_loss(q, act, td)
+        self.opt_critic.zero_grad(set_to_none=False)
+        loss_c.backward()
+        self.sync_critic.finish()
+        self.opt_critic.step()
+        with torch.no_grad(), self._autocast():
+            q_new = self.critic(state)
+        with self._autocast():
+            probs = self.actor(obs, eps)
+        loss_a, adv = coma_actor_loss(probs, q_new, act, masks)
+        self.opt_actor.zero_grad(set_to_none=False)
+        loss_a.backward()
+        self.sync_actor.finish()
+        self.opt_actor.step()
+        return loss_c.detach(), loss_a.detach(), adv, q_new
+
     def update(self):
         """TD(lambda) targets + `data_passes` passes of critic / actor mini-batch steps (coma_mission.py:89-98)."""
         env = self.env
         T, B, A = env.T, env.B, env.A
-        eps = epsilon(max(self.episodes_done - 1, 0), *self.eps_cfg)
+        eps = epsilon(self._last_eps_episode, *self.eps_cfg)  # the eps of the last collected episode (coma_mission.py:78)
         obs = self.buf_obs.flatten(0, 2)
         state = self.buf_state.flatten(0, 2)
         act = self.buf_act.flatten()
@@ -244,27 +338,16 @@ class COMATrainer:
             perm = torch.randperm(n, device=obs.device)
             for i in range(0, n, self.minibatch):
                 idx = perm[i:i + self.minibatch]
-                with self._autocast():
-                    q = self.critic(state[idx])
-                loss_c = coma_critic_loss(q, act[idx], td[idx])
-                self.opt_critic.zero_grad(set_to_none=False)
-                loss_c.backward()
-                self.sync_critic()
-                self.opt_critic.step()
-                with torch.no_grad(), self._autocast():
-                    q_new = self.critic(state[idx])  # critic/learner.py:101-105: Q after the critic step
-                with self._autocast():
-                    probs = self.actor(obs[idx], eps)
-                loss_a, adv = coma_actor_loss(probs, q_new, act[idx], masks[idx])
-                self.opt_actor.zero_grad(set_to_none=False)
-                loss_a.backward()
-                self.sync_actor()
-                self.opt_actor.step()
-                stats = {"critic_loss": loss_c.detach(), "actor_loss": loss_a.detach(), "adv_mean": adv.mean()}
+                loss_c, loss_a, adv, _ = self.learn_minibatch(state[idx], obs[idx], act[idx], masks[idx], td[idx], eps)
+                stats = {"critic_loss": loss_c, "actor_loss": loss_a, "adv_mean": adv.mean()}
         self.updates += 1
         if not self.frozen_target and self.updates % self.copy_rate == 0:
             self.target_critic.load_state_dict(self.critic.state_dict())
         return stats
+
+    def optimizer_steps_per_update(self):
+        n = self.env.T * self.env.B * self.env.A
+        return 2 * self.data_passes * ((n + self.minibatch - 1) // self.minibatch)
 
     def flops_per_update(self):
         """Forward MACs: 20.1 M per actor observation, 21.7 M per critic state."""

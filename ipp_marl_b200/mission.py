@@ -68,10 +68,36 @@ class BestModel:
         running = sum(self.returns) / len(self.returns)
         if len(self.returns) >= self.patience and running > self.best:
             self.best = running
-            if actor is not None and self.path is not None:
-                torch.save(actor.state_dict(), self.path)
+            if actor is not None and self.path is not None and _rank() == 0:  # every rank keeps the books, one writes
+                save_actor(actor, self.path)
             return True
         return False
+
+
+def _rank():
+    import torch.distributed as dist
+
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def save_actor(actor, path):
+    """Checkpoint format: the actor's ``state_dict()`` (tensors only).  The reference pickles the whole
+    ``ActorNetwork`` module (missions/coma_mission.py:435 ``torch.save(actor_network, ...)``), which ties a checkpoint
+    to the reference's class path; ``load_actor_state`` below reads both forms."""
+    torch.save(actor.state_dict(), path)
+
+
+def load_actor_state(path, map_location="cpu"):
+    """State dict of an actor checkpoint written either by ``save_actor`` (a state dict) or by the reference
+    (a pickled ``ActorNetwork`` module, coma_mission.py:435 / coma_test.py:52 — needs the reference's classes
+    importable, e.g. after ``facade.install``).  Layer names are the same in both (conv1-3, fc1-3)."""
+    try:
+        obj = torch.load(path, map_location=map_location, weights_only=True)
+    except Exception:
+        obj = torch.load(path, map_location=map_location, weights_only=False)
+    if hasattr(obj, "state_dict"):
+        obj = obj.state_dict()
+    return {k: v for k, v in obj.items()}
 
 
 def _stats(log, prefix, values, step):
@@ -126,7 +152,7 @@ class COMAMission:
     @torch.no_grad()
     def evaluate(self):
         tr, env = self.trainer, self.env
-        done_before = tr.episodes_done
+        done_before, eps_before = tr.episodes_done, tr._last_eps_episode
         ent_curve = f1_curve = None
         for _ in range(self.eval_rollouts):
             tr.rollout(episodes=self._episodes(), greedy=True)
@@ -137,7 +163,7 @@ class COMAMission:
         ent_curve, f1_curve = ent.mean(), f1.mean()
         self.log.add_scalar("evalMetrics/entropy_final", ent_curve, self.training_step_idx)
         self.log.add_scalar("evalMetrics/f1_final", f1_curve, self.training_step_idx)
-        tr.episodes_done = done_before  # evaluation episodes do not advance the epsilon schedule
+        tr.episodes_done, tr._last_eps_episode = done_before, eps_before  # evaluation does not advance the eps schedule
         return float(ent_curve), float(f1_curve)
 
     # ---- the training loop (coma_mission.py:49-172) -------------------------------------------------------------

@@ -75,18 +75,73 @@ def test_critic_and_actor_losses_match_reference_learners():
 
 
 def test_flat_grad_allreduce_is_identity_without_process_group():
-    net = coma.CriticNet()
-    loss = net(torch.rand(2, 11, 11, 12)).sum()
-    loss.backward()
-    before = [p.grad.clone() for p in net.parameters() if p.grad is not None]
-    coma.FlatGradAllReduce(net)()
-    after = [p.grad for p in net.parameters() if p.grad is not None]
-    assert all(torch.equal(a, b) for a, b in zip(before, after))
+    """Gradients live as views in one flat buffer; without a process group finish() changes nothing, and the views
+    give the same gradients as an untouched copy of the network."""
+    torch.manual_seed(5)
+    net, twin = coma.CriticNet(), coma.CriticNet()
+    twin.load_state_dict(net.state_dict())
+    sync = coma.FlatGradAllReduce(net, bucket_bytes=1 << 20)
+    assert [hi - lo for lo, hi, _ in sync.buckets] and sync.buckets[0][1] == sync.flat.numel() and sync.buckets[-1][0] == 0
+    assert sum(hi - lo for lo, hi, _ in sync.buckets) == 2307846
+    x = torch.rand(2, 11, 11, 12)
+    for _ in range(2):  # second pass: the views survive zero_grad(set_to_none=False) and accumulate in place
+        net.zero_grad(set_to_none=False)
+        twin.zero_grad(set_to_none=True)
+        net(x).sum().backward()
+        twin(x).sum().backward()
+        sync.finish()
+        for (n, p), q in zip(net.named_parameters(), twin.parameters()):
+            assert p.grad.data_ptr() >= sync.flat.data_ptr()
+            if q.grad is None:  # fc2: constructed but unused
+                assert n.startswith("fc2") and float(p.grad.abs().sum()) == 0.0
+            else:
+                assert torch.allclose(p.grad, q.grad, rtol=1e-6, atol=1e-8), n
+    assert sync.used is not None and len(sync.used) == 10  # 12 parameter tensors, fc2.weight / fc2.bias unused
 
 
 def test_epsilon_schedule():
     assert coma.epsilon(0) == 0.5 and coma.epsilon(20000) == 0.02
     assert abs(coma.epsilon(5000) - (0.5 - 0.5 * 0.48)) < 1e-12
+
+
+@pytest.mark.gpu
+def test_learn_minibatch_fp32_matches_reference_learners_on_gpu():
+    """COMATrainer.learn_minibatch (the arithmetic of one critic + one actor optimizer step, as update() runs it) on
+    the GPU in float32 against the values of the reference's CriticLearner / ActorLearner (coma_kats.npz): critic
+    loss, post-step Q values, actor loss and mean advantage."""
+    import json
+
+    from ipp_marl_b200 import BatchedIPPEnv
+
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        params = json.load(open(os.path.join(root, "tests", "golden", "kats.json")))["synthetic50"]["params"]
+        env = BatchedIPPEnv(params, 8, device="cuda:0")
+        tr = coma.COMATrainer(env, params)
+        assert tr.compute_dtype == torch.float32
+        seed = int(K["seed"])
+        torch.manual_seed(seed + 1)
+        tr.actor.load_state_dict(coma.ActorNet().state_dict())
+        torch.manual_seed(seed + 2)
+        tr.critic.load_state_dict(coma.CriticNet().state_dict())
+        dev = env.device
+        st = torch.from_numpy(K["lb_state"]).to(dev)
+        obs = torch.from_numpy(K["lb_obs"]).float().to(dev)
+        act = torch.from_numpy(K["lb_act"])[:, 0].to(dev)
+        td = torch.from_numpy(K["lb_td"])[:, 0].to(dev)
+        masks = torch.from_numpy(K["lb_masks"]).to(dev)
+        with torch.no_grad():
+            assert np.allclose(tr.critic(st).cpu().numpy(), K["critic_q_before"], rtol=1e-4, atol=1e-5)
+        loss_c, loss_a, adv, q_after = tr.learn_minibatch(st, obs, act, masks, td, float(K["lb_eps"]))
+        assert abs(float(loss_c) - float(K["critic_loss"])) <= 1e-6 + 1e-4 * abs(float(K["critic_loss"]))
+        assert np.allclose(q_after.cpu().numpy(), K["critic_q_after"], rtol=2e-4, atol=2e-5)
+        assert abs(float(loss_a) - float(K["actor_loss"])) <= 2e-6 + 2e-4 * abs(float(K["actor_loss"]))
+        assert abs(float(adv.mean()) - float(K["actor_adv_mean"])) <= 2e-5
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
 @pytest.mark.gpu
@@ -157,9 +212,25 @@ def test_mission_loop_runs_logs_and_checkpoints(tmp_path):
               "trainActions/0", "trainAltitudes/15"):
         assert t in tags, t
     actor = coma.ActorNet()
-    actor.load_state_dict(torch.load(tmp_path / "best_model.pth", map_location="cpu"))
+    actor.load_state_dict(mission.load_actor_state(tmp_path / "best_model.pth"))
     ent = [json.loads(x) for x in open(tmp_path / "scalars.jsonl") if "entropy_final" in x][0]["value"]
     assert 0.0 < ent <= 1.0
+
+
+def test_checkpoint_loader_reads_state_dicts_and_pickled_modules(tmp_path):
+    """mission.load_actor_state: our own format (state dict) and the reference's (whole pickled module,
+    coma_mission.py:435)."""
+    from ipp_marl_b200 import mission
+
+    torch.manual_seed(1)
+    actor = coma.ActorNet()
+    mission.save_actor(actor, tmp_path / "a.pth")
+    torch.save(actor, tmp_path / "b.pth")  # what the reference does with its ActorNetwork
+    for name in ("a.pth", "b.pth"):
+        sd = mission.load_actor_state(tmp_path / name)
+        other = coma.ActorNet()
+        other.load_state_dict(sd)
+        assert all(torch.equal(x, y) for x, y in zip(actor.state_dict().values(), other.state_dict().values()))
 
 
 def test_flat_grad_allreduce_gloo(tmp_path):
@@ -184,17 +255,25 @@ net = coma.CriticNet()
 sync = coma.FlatGradAllReduce(net)
 opt = torch.optim.SGD(net.parameters(), lr=0.1)
 torch.manual_seed(100 + rank)             # different data per rank
-x = torch.rand(4, 11, 11, 12)
-loss = net(x).square().mean()
-loss.backward()
-local = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in net.parameters()]  # fc2 is unused
-sync()
+twin = coma.CriticNet()                   # plain copy: the rank-local gradients
 ok = True
-for p, g in zip(net.parameters(), local):
-    both = [torch.zeros_like(g) for _ in range(world)]
-    dist.all_gather(both, g)
-    ok = ok and torch.allclose(p.grad, sum(both) / world, rtol=1e-6, atol=1e-8)
-opt.step()
+launched_by_hooks = []
+for it in range(2):                       # step 0: one-piece reduce (discovers the unused fc2); step 1: bucket hooks
+    twin.load_state_dict(net.state_dict())
+    x = torch.rand(4, 11, 11, 12)
+    opt.zero_grad(set_to_none=False)
+    twin.zero_grad(set_to_none=True)
+    net(x).square().mean().backward()
+    launched_by_hooks.append(len(sync._launched))
+    twin(x).square().mean().backward()
+    local = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in twin.parameters()]
+    sync()
+    for p, g in zip(net.parameters(), local):
+        both = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(both, g)
+        ok = ok and torch.allclose(p.grad, sum(both) / world, rtol=1e-6, atol=1e-8)
+    opt.step()
+ok = ok and launched_by_hooks[0] == 0 and launched_by_hooks[1] == len(sync.buckets)
 w = torch.cat([p.detach().flatten() for p in net.parameters()])
 ws = [torch.zeros_like(w) for _ in range(world)]
 dist.all_gather(ws, w)

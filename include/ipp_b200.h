@@ -22,7 +22,7 @@
  *   ground truth  uint8   [n_envs, gt_stride]    (mapping/ground_truths.py:42-56 half-plane field)
  *   positions     int32   [n_envs, n_agents, 3]  metres (x, y, z), as agent/agent.py keeps them
  *   episodes      uint32  [n_envs]               episode number of each env (seeds + random streams)
- *   meas codes    uint8   [2, n_envs, code_stride]  latest measurement of every agent, 1 byte per (quad, agent)
+ *   meas codes    uint8   [n_envs, 2, code_stride]  latest measurement of every agent, 1 byte per (quad, agent)
  */
 #ifndef IPP_B200_H
 #define IPP_B200_H
@@ -95,9 +95,9 @@ typedef struct ipp_state {
   float* global_map;   /* [n_envs, map_stride]            accumulated_map_knowledge, as odds       */
   uint8_t* ground_truth; /* [n_envs, gt_stride]           Mapping.simulated_map                    */
   uint32_t* episodes;  /* [n_envs]                                                                  */
-  uint8_t* meas_codes; /* [2, n_envs, code_stride] compact form of Agent.map2communicate: one byte per   */
+  uint8_t* meas_codes; /* [n_envs, 2, code_stride] compact form of Agent.map2communicate: one byte per   */
                        /* (4-cell quad, agent): low nibble = cell inside the agent's latest footprint,   */
-                       /* high nibble = cell measured as occupied.  Half (t & 1) holds the measurements  */
+                       /* high nibble = cell measured as occupied.  Row (t & 1) of an env holds the measurements */
                        /* communicated at step t, the other half receives those taken after the moves.   */
   uint32_t* map_flags; /* [n_envs, n_seg, 8] (word i of a 32-byte record = local map i; 16-byte aligned):           */
                        /* bookkeeping of the reference's lazily applied clamp (mapping/mappings.py:110-111 clamps a */

@@ -19,7 +19,7 @@ HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("IPP_NVCC_EXTRA", "").split()  # development only (timing knobs: scripts/dbg_bench.py)
 
 
 def _digest():

@@ -156,7 +156,9 @@ class FlatGradAllReduce:
         off = 0
         for p in self.params:
             self.offsets.append(off)
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # a view of the flat buffer with the parameter's own (dense) strides: channels_last conv weights keep the
+            # layout autograd expects ("gradient layout contract"), the bytes stay in one contiguous range
+            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
             off += p.numel()
         # buckets = contiguous ranges of the flat buffer, at least bucket_bytes each, built from the LAST parameter
         # backwards (the order in which backward produces gradients)

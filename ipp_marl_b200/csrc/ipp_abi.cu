@@ -4,7 +4,7 @@
 #include <cstring>
 #include <new>
 
-#include "ipp_device.cuh"
+#include "ipp_cell.cuh"
 #include "ipp_launch.h"
 
 struct ipp_handle {
@@ -17,7 +17,7 @@ struct ipp_handle {
   double* partials;     // [n_envs, n_chunks, 2]
   int32_t* gt_params;   // [n_envs, 4]
   uint8_t* comm;        // [n_envs, n_agents] when the caller does not ask for comm_out
-  uint32_t* step_meta;  // [n_envs, 4 * n_agents] per-env record handed from the plan kernel to the map kernels
+  uint32_t* step_meta;  // [n_envs, n_seg, rec_words] ItemRec of every work item, handed from the plan kernel to the map kernels
   void* policy_in;      // [n_envs, n_agents, 6] float32 staging of ipp_step_host's policy input (lazily allocated)
   float4* lut;          // [n_alt, 256] odds multipliers of a quad for every measurement code byte
   ipp::PoolTables pool; // cv2.INTER_AREA tap tables of the feature builders
@@ -137,7 +137,7 @@ const char* ipp_status_string(int status) {
 
 const char* ipp_last_error(const ipp_handle* h) { return h != nullptr ? h->err : ""; }
 
-int ipp_version(void) { return 200; }
+int ipp_version(void) { return 210; }
 
 int ipp_create(const ipp_config* cfg, ipp_handle** out) {
   if (out == nullptr) return IPP_ERR_INVALID_ARG;
@@ -170,7 +170,7 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
   const size_t pb = sizeof(double) * 2 * (size_t)cfg->n_envs * max_chunks;
   const size_t gb = sizeof(int32_t) * 4 * (size_t)cfg->n_envs;
   const size_t cb = (size_t)cfg->n_envs * cfg->n_agents;
-  const size_t mb = sizeof(uint32_t) * 4 * (size_t)cfg->n_envs * cfg->n_agents;
+  const size_t mb = sizeof(uint32_t) * (size_t)ipp::rec_words(cfg->n_agents) * (size_t)cfg->n_envs * cfg->n_seg;
   if (cudaMalloc(&h->partials, pb) != cudaSuccess || cudaMalloc(&h->gt_params, gb) != cudaSuccess ||
       cudaMalloc(&h->comm, cb) != cudaSuccess || cudaMalloc(&h->step_meta, mb) != cudaSuccess) {
     ipp_destroy(h);

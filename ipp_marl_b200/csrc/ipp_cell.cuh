@@ -21,7 +21,7 @@
 
 namespace ipp {
 
-// Per-env facts the per-quad code needs (shared memory; filled from the record written by plan_moves).
+// Per-env facts the per-quad code needs (shared memory; part of the record written by the plan kernel).
 template <int A>
 struct EnvMeta {
   uint32_t comm[A];      // bit j: agent i fuses agent j's measurement (own bit cleared)
@@ -30,26 +30,42 @@ struct EnvMeta {
   uint32_t lut_next[A];  // same for the measurement after the move
 };
 
+constexpr int ITEM_TILES = IPP_FLAG_QUADS / 32;  // tiles (32 quads = 128 cells) per work item / flag segment
+
+// Record of one WORK ITEM = (env, segment of IPP_FLAG_QUADS quads), written by the plan kernel once per step and
+// read by the map kernels as a plain copy: the env-level facts plus, for this segment, which tiles of which local map
+// have work in this step — everything the map kernel's producer needs before it can fetch the item, worked out
+// where there are thousands of warps to do it.
+template <int A>
+struct ItemRec {
+  EnvMeta<A> env;
+  uint32_t need[A];   // bit t: tile t of local map i has work: flagged out of range while a fuse pass runs, reached by
+                      // an enabled peer's communicated footprint, or by the own new footprint (a superset is allowed)
+  uint32_t flags[A];  // the segment's range flags (ipp_state.map_flags) as they were before this step
+  uint16_t tile[ITEM_TILES];  // per tile: low byte bit j = agent j's communicated footprint reaches the tile; high
+                              // byte bit i = a fuse pass runs on local map i and the tile may hold out-of-range odds
+                              // (or k_out != 1): every quad of the tile changes
+};
+// words of one record in global memory (padded to 16 bytes, the bulk-copy granularity)
+__host__ __device__ constexpr int rec_words(int n_agents) { return (6 * n_agents + ITEM_TILES / 2 + 3) & ~3; }
+
 __device__ __forceinline__ uint32_t lut_row(const ipp_config& c, const int32_t* pos) {
   const int32_t iz = clampi(pos[2] / c.spacing - c.min_altitude / c.spacing, 0, c.n_alt - 1);
   return (uint32_t)iz * 256u;
 }
 
-// One env's record (4 * n_agents words, in the field order of EnvMeta): written by plan_moves once per step, read by
-// the map kernels as a plain 16A-byte copy.
-__device__ __forceinline__ void write_env_meta(const ipp_config& cfg, uint32_t* rec, const uint32_t* comm_rows,
-                                               const int32_t (*pos)[3], const int32_t (*npos)[3], bool have_next) {
-  const int A = cfg.n_agents;
-  for (int a = 0; a < A; ++a) {
-    const uint32_t en = comm_rows[a] & ~(1u << a);  // own measurement already used
-    uint32_t en4 = 0;
-    for (int j = 0; j < A; ++j)
-      if ((en >> j) & 1u) en4 |= 0xFu << (4 * j);
-    rec[a] = en;
-    rec[A + a] = en4;
-    rec[2 * A + a] = lut_row(cfg, pos[a]);
-    rec[3 * A + a] = have_next ? lut_row(cfg, npos[a]) : 0u;
-  }
+// Tiles of 128 cells reached by the footprint of a measurement taken at `pos` (same geometry as make_meas): the
+// footprint's rows xl..xr-1 hold cells [x*gy+yu, x*gy+yd), so everything it touches lies between its first and its
+// last cell.  (Exact when a tile is longer than the gap between two footprint rows, always a superset.)
+__device__ __forceinline__ uint32_t tile_range(const ipp_config& c, const int32_t* pos) {
+  const int32_t ix = clampi(pos[0] / c.spacing, 0, c.px - 1), iy = clampi(pos[1] / c.spacing, 0, c.py - 1);
+  const int32_t iz = clampi(pos[2] / c.spacing - c.min_altitude / c.spacing, 0, c.n_alt - 1);
+  const int32_t cx = c.cell_x[ix], cy = c.cell_y[iy], rx = c.radius_x[iz], ry = c.radius_y[iz];
+  const int32_t xl = clampi(cx - rx, 0, c.gx - 1), xr = clampi(cx + rx, 0, c.gx - 1);
+  const int32_t yu = clampi(cy - ry, 0, c.gy - 1), yd = clampi(cy + ry, 0, c.gy - 1);
+  if (xr <= xl || yd <= yu) return 1u;  // first 1 > last 0: empty footprint
+  const uint32_t first = (uint32_t)(xl * c.gy + yu), last = (uint32_t)((xr - 1) * c.gy + yd - 1);
+  return (first >> 7) | ((last >> 7) << 16);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -113,17 +129,17 @@ __device__ __forceinline__ CodeWord<A> load_code(const void* base, int32_t quad)
   return c;
 }
 
-// float32 reward terms; H in bits (utils/state.py:118-121) of a cell given its CLAMPED odds:
-// q = 1/(1+o), p = o*q, H = -(p lg p + q lg q)
+// float32 reward terms; H in bits (utils/state.py:118-121) of a cell given its CLAMPED odds (1 MUFU.RCP + 2 MUFU.LG2)
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ float entropy_bits_odds(float oc) {
-  const float qc = rcp_approx(1.0f + oc);
-  const float pc = oc * qc;
-  return -(pc * lg2_approx(pc) + qc * lg2_approx(qc));
+  // with t = 1 + o, q = 1/t, p = o q:  H = -(p lg p + q lg q) = lg t - p lg o   (lg p = lg o - lg t, p + q = 1)
+  const float t = 1.0f + oc;
+  const float pc = oc * rcp_approx(t);
+  return fmaf(-pc, lg2_approx(oc), lg2_approx(t));
 }
 
 // utils/state.py:67-73 thresholds p > 0.501 / p < 0.499 in odds space (oracle/kernel_model.py W_HI / W_LO)
@@ -131,32 +147,56 @@ __device__ __forceinline__ float entropy_bits_odds(float oc) {
 #define IPP_W_LO 0.9960079789161682f
 
 // ------------------------------------------------------------------------------------------------
+// One fuse chain on a quad: the passes of the ENABLED agents in id order; each pass clamps its input and multiplies
+// (mapping/mappings.py:106-124; by exactly k_out outside footprint j).  `touch` (warp-uniform) marks the passes whose
+// footprint reaches one of the warp's quads; with k_out == 1 the others multiply every cell of the warp by exactly 1,
+// so only their clamp can matter — and a clamp is the identity on a value that is known to lie inside
+// [o_min, o_max].  `oor` (warp-uniform, in/out) = "the value may lie outside the range": a clamp is executed exactly
+// when it is set.  Multipliers come from the LUT row of agent j's altitude, indexed by the quad's code byte.
+// ------------------------------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ F4 fuse_chain(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
+                                         const float4* lut, F4 o, const uint32_t enabled, const uint32_t touch,
+                                         bool& oor) {
+  const float lo = cfg.o_min, hi = cfg.o_max;
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    if (!((enabled >> j) & 1u)) continue;  // warp-uniform
+    if (oor) o = f4_clamp(o, lo, hi);
+    oor = false;
+    if ((touch >> j) & 1u) {
+      o = f4_mul(o, f4_from(lut[meta.lut_prev[j] + cw.byte(j)]));
+      oor = true;
+    }
+  }
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
 // GLOBAL map, one quad: all A fuse passes (coma_wrapper.py:93-95) + the reward terms
-// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).  Straight-line: a pass is
-// clamp + multiply, the multipliers of all four cells come from one LUT load per agent (k_out outside
-// the footprint), so no footprint logic is needed at all.  kj[] keeps the multipliers for the local maps.
+// s1 = sum w*(H(last)-H(next)), s2 = sum w*H(last) (utils/reward.py:68-82).
 // Must be called by all 32 lanes of the warp, converged (lanes without a quad pass valid = 0).
 // ------------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const CodeWord<A>& cw,
-                                              const float4* lut, const float4 o4, const uint32_t valid, F4 (&kj)[A],
-                                              float& s1, float& s2) {
+                                              const float4* lut, float4 o4, const uint32_t valid,
+                                              const uint32_t touch, float& s1, float& s2) {
   const float lo = cfg.o_min, hi = cfg.o_max;
-  const F4 oc = f4_clamp(f4_from(o4), lo, hi);
-  F4 o = oc;
-  uint32_t touched = 0;
-#pragma unroll
-  for (int j = 0; j < A; ++j) {
-    const uint32_t byte = cw.byte(j);
-    touched |= byte;
-    kj[j] = f4_from(lut[meta.lut_prev[j] + byte]);
-    if (j > 0) o = f4_clamp(o, lo, hi);
-    o = f4_mul(o, kj[j]);
+  // Cells that do not count for the reward — beyond gx*gy in the map's last quad, or all four of a lane without a
+  // quad — are given odds 0: clamped to o_min, never inside a footprint, their weight is 0 (o_min k_out^A < W_LO)
+  // and so are both of their reward terms.  (Rare, so a branch; what is stored for padding cells is never read.)
+  if (valid != 0xFu) {
+    if (!(valid & 1u)) o4.x = 0.0f;
+    if (!(valid & 2u)) o4.y = 0.0f;
+    if (!(valid & 4u)) o4.z = 0.0f;
+    if (!(valid & 8u)) o4.w = 0.0f;
   }
-  touched = (cfg.k_out == 1.0f) ? (touched & 0xFu) : 0xFu;
-  // H(next) only where some lane of the warp has a touched cell (warp-uniform branch: the caller runs all 32
-  // lanes converged); an untouched cell has next == clamp(last) bit for bit, so its H(next) == H(last) exactly
-  const bool any_touched = __any_sync(0xFFFFFFFFu, touched != 0u);
+  const F4 oc = f4_clamp(f4_from(o4), lo, hi);
+  bool oor = false;  // oc is clamped
+  const F4 o = fuse_chain<A>(cfg, meta, cw, lut, oc, (1u << A) - 1u, touch, oor);
+  // H(next) only where some footprint reaches the warp's tile (warp-uniform): an untouched cell has
+  // next == clamp(last) bit for bit, so its H(next) == H(last) exactly
+  const bool any_touched = touch != 0u || cfg.k_out != 1.0f;
   float a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -164,8 +204,7 @@ __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMe
     const float hl = entropy_bits_odds(f4_get(oc, c));
     float hn = hl;
     if (any_touched) hn = entropy_bits_odds(fminf(fmaxf(next, lo), hi));
-    float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
-    w = ((valid >> c) & 1u) ? w : 0.0f;  // cells beyond gx*gy (or of a lane without a quad) do not count
+    const float w = next > IPP_W_HI ? 1.0f : (next < IPP_W_LO ? 0.0f : 0.5f);
     a1 += w * (hl - hn);
     a2 += w * hl;
   }
@@ -176,45 +215,30 @@ __device__ __forceinline__ float4 global_quad(const ipp_config& cfg, const EnvMe
 
 // ------------------------------------------------------------------------------------------------
 // LOCAL map of agent i, one quad (agent/agent.py:62-71,91-94; mapping/mappings.py:80-124,32-61): the enabled
-// fuse passes in id order — each clamps and multiplies (by exactly 1 outside footprint j) — then, inside the new
-// own footprint only, clamp and multiply.  Straight-line; `en` is warp-uniform.  Returns true when a result left
-// [o_min, o_max] (the reference clamps lazily, at the next update that reads the cell).
+// fuse passes in id order, then, inside the new own footprint only, clamp and multiply.  `tile_dirty`
+// (warp-uniform): the stored odds of this tile may lie outside [o_min, o_max] (range flag).  Returns true when a
+// result left the range (the reference clamps lazily, at the next update that reads the cell).
 // ------------------------------------------------------------------------------------------------
 template <int A, bool DO_OWN>
-__device__ __forceinline__ bool local_quad(const ipp_config& cfg, const uint32_t en, const F4 (&kj)[A],
-                                           const uint32_t own_byte, const uint32_t lut_next, const float4* lut,
+__device__ __forceinline__ bool local_quad(const ipp_config& cfg, const EnvMeta<A>& meta, const uint32_t enabled,
+                                           const uint32_t touch, const bool tile_dirty, const int i,
+                                           const CodeWord<A>& cw, const uint32_t own_byte, const float4* lut,
                                            float4& v) {
   const float lo = cfg.o_min, hi = cfg.o_max;
-  F4 o = f4_from(v);
-#pragma unroll
-  for (int j = 0; j < A; ++j)
-    if ((en >> j) & 1u) o = f4_mul(f4_clamp(o, lo, hi), kj[j]);  // warp-uniform branch
-  if (DO_OWN) {
-    const uint32_t own = own_byte & 0xFu;
-    if (own != 0u) o = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[lut_next + own_byte])), o);
-  }
-  v = f4_to(o);
-  return f4_out_of_range(o, lo, hi);
-}
-
-// The same with the multipliers re-read from the LUT (L1-resident) instead of held in registers: the direct-load
-// kernel keeps its registers for loads in flight.
-template <int A, bool DO_OWN>
-__device__ __forceinline__ bool local_quad_lut(const ipp_config& cfg, const EnvMeta<A>& meta, const int i,
-                                               const CodeWord<A>& cw, const uint32_t own_byte, const float4* lut,
-                                               float4& v) {
-  const float lo = cfg.o_min, hi = cfg.o_max;
-  const uint32_t en = meta.comm[i];
-  F4 o = f4_from(v);
-#pragma unroll
-  for (int j = 0; j < A; ++j)
-    if ((en >> j) & 1u) o = f4_mul(f4_clamp(o, lo, hi), f4_from(lut[meta.lut_prev[j] + cw.byte(j)]));
+  bool oor = tile_dirty;
+  F4 o = fuse_chain<A>(cfg, meta, cw, lut, f4_from(v), enabled, touch, oor);
   if (DO_OWN) {
     const uint32_t own = own_byte & 0xFu;
     if (own != 0u) o = f4_select(own, f4_mul(f4_clamp(o, lo, hi), f4_from(lut[meta.lut_next[i] + own_byte])), o);
   }
   v = f4_to(o);
   return f4_out_of_range(o, lo, hi);
+}
+
+// some component of a differs from b bit for bit
+__device__ __forceinline__ bool quad_changed(const float4 a, const float4 b) {
+  return __float_as_uint(a.x) != __float_as_uint(b.x) || __float_as_uint(a.y) != __float_as_uint(b.y) ||
+         __float_as_uint(a.z) != __float_as_uint(b.z) || __float_as_uint(a.w) != __float_as_uint(b.w);
 }
 
 __device__ __forceinline__ uint32_t valid_mask4(int32_t c0, int32_t n_cells) {

@@ -47,6 +47,12 @@ struct Meas {
 
 __device__ __forceinline__ int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return min(max(v, lo), hi); }
 
+// Measurement codes: [n_envs][2][code_stride] — the two ping-pong halves of one env are adjacent (the map kernel
+// fetches both with one bulk copy); half (t & 1) holds the measurements communicated at step t.
+__host__ __device__ __forceinline__ int64_t code_row_offset(const ipp_config& c, int32_t half, int64_t b) {
+  return (b * 2 + (half & 1)) * (int64_t)c.code_stride;
+}
+
 __device__ __forceinline__ Meas make_meas(const ipp_config& c, const int32_t* pos, uint32_t episode, uint32_t agent,
                                           uint32_t index) {
   Meas m;

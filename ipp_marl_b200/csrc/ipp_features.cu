@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128)
   const uint32_t received = comm[(int64_t)b * A + i];  // includes the agent itself (communication_log.py:47)
   const AgentGeo me = s_geo[i];
   const float* local = st.local_maps + ((int64_t)b * A + i) * cfg.map_stride;
-  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const uint8_t* codes = st.meas_codes + code_row_offset(cfg, t, b);
   const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
   const Tab fx = get_tab(pt, 2 + 2 * me.iz), fy = get_tab(pt, 3 + 2 * me.iz);
   // where the clipped measurement block sits inside the raw footprint image (utils/utils.py:79-98);
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128)
   }
   __syncthreads();
   const float* glob = st.global_map + (int64_t)b * cfg.map_stride;
-  const uint8_t* codes = st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const uint8_t* codes = st.meas_codes + code_row_offset(cfg, t, b);
   const Tab tx = get_tab(pt, 0), ty = get_tab(pt, 1);
   for (int32_t c = threadIdx.x; c < cfg.px * cfg.py; c += blockDim.x) {
     const int32_t li = c / cfg.py, lj = c - li * cfg.py;
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(128, 9)
     ptx::mbar_arrive_expect_tx(bar, map_bytes + (uint32_t)cfg.code_stride);
     ptx::bulk_load(ptx::smem_u32(s_map), st.local_maps + ((int64_t)b * A + i) * cfg.map_stride, map_bytes, bar);
     ptx::bulk_load(ptx::smem_u32(codes),
-                   st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, (uint32_t)cfg.code_stride, bar);
+                   st.meas_codes + code_row_offset(cfg, t, b), (uint32_t)cfg.code_stride, bar);
   }
   // zero pads (disjoint from the bulk-copy destinations)
   for (int32_t k = 4 * n_quads + (int32_t)threadIdx.x; k < cfg.map_stride + FEAT_PAD; k += blockDim.x) s_map[k] = 0.0f;
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(128)
     ptx::mbar_arrive_expect_tx(bar, map_bytes + (uint32_t)cfg.code_stride);
     ptx::bulk_load(ptx::smem_u32(s_map), st.global_map + (int64_t)b * cfg.map_stride, map_bytes, bar);
     ptx::bulk_load(ptx::smem_u32(codes),
-                   st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, (uint32_t)cfg.code_stride, bar);
+                   st.meas_codes + code_row_offset(cfg, t, b), (uint32_t)cfg.code_stride, bar);
   }
   for (int32_t k = 4 * n_quads + (int32_t)threadIdx.x; k < cfg.map_stride + FEAT_PAD; k += blockDim.x) s_map[k] = 0.0f;
   for (int32_t k = threadIdx.x; k < MT * cfg.py; k += blockDim.x) s_cpad[k] = 0.0f;

@@ -54,8 +54,8 @@ struct PlanShared {
 
 __device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const bool env_ok, const int a,
                                  const ipp_step_io& io, const ipp_state& st, const int32_t t, const bool do_comm,
-                                 const bool do_move, PlanShared& sh, int32_t (*npos)[3],
-                                 uint32_t* __restrict__ step_meta, const int32_t* __restrict__ gt_params) {
+                                 const bool do_move, PlanShared& sh, int32_t (*npos)[3], uint32_t* rec,
+                                 const int32_t* __restrict__ gt_params) {
   const int32_t A = cfg.n_agents;
   const bool live = env_ok && a < A;
   int32_t p[3] = {0, 0, 0};
@@ -70,7 +70,8 @@ __device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const b
     if (a == 0) sh.stuck = 0u;
   }
   __syncwarp();
-  uint32_t* rec = step_meta + (int64_t)b * 4 * A;  // this env's record for the map kernels (EnvMeta field order)
+  // rec (shared memory): this env's facts for the map kernels — EnvMeta field order, then the tile ranges of the
+  // communicated and of the new footprints; build_item_records turns them into one ItemRec per map segment
   if (live && do_comm && io.comm_out != nullptr) {
     const uint32_t key = stream_key(cfg.seed, ep, (uint32_t)a, (uint32_t)t, PURPOSE_COMM);
     // fix_range False (communication_log.py:22-31): range index = the episode's first randint(4) = the ground
@@ -92,7 +93,11 @@ __device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const b
     rec[a] = en;
     rec[A + a] = en4;
     rec[2 * A + a] = lut_row(cfg, p);
-    if (!do_move) rec[3 * A + a] = 0u;  // ipp_observe: the map kernel fuses only
+    rec[4 * A + a] = tile_range(cfg, p);  // tiles the communicated measurement (taken at p) reaches
+    if (!do_move) {  // ipp_observe: the map kernel fuses only
+      rec[3 * A + a] = 0u;
+      rec[5 * A + a] = 1u;  // empty range
+    }
   }
   if (!do_move) return;
 
@@ -189,7 +194,10 @@ __device__ void plan_moves_group(const ipp_config& cfg, const int32_t b, const b
       if (io.actions_out != nullptr) io.actions_out[(int64_t)b * A + a] = act;
       if (io.mask_out != nullptr) io.mask_out[(int64_t)b * A + a] = (uint8_t)m;
       if (stuck != 0u) sh.stuck |= stuck;  // only this lane of the env is active in this turn
-      if (do_comm) rec[3 * A + a] = lut_row(cfg, np);
+      if (do_comm) {
+        rec[3 * A + a] = lut_row(cfg, np);
+        rec[5 * A + a] = tile_range(cfg, np);
+      }
     }
     __syncwarp();
   }
@@ -255,6 +263,58 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
   }
 }
 
+// One warp writes the ItemRec of every segment of one env (ipp_cell.cuh): lane t looks at tile t of the segment.
+// rec = the env's words from plan_moves_group: comm | comm4 | lut_prev | lut_next | rng_prev | rng_next (A each).
+__device__ void build_item_records(const ipp_config& cfg, const ipp_state& st, const int32_t b, const int lane,
+                                   const uint32_t* rec, const bool have_next, uint32_t* __restrict__ step_meta) {
+  const int A = cfg.n_agents;
+  const int rw = rec_words(A);
+  const bool kout_one = (cfg.k_out == 1.0f);
+  const int32_t n_quads = (cfg.gx * cfg.gy + 3) >> 2;
+  const uint32_t all_agents = (1u << A) - 1u;
+  for (int32_t c = 0; c < cfg.n_seg; ++c) {
+    const int32_t nq = min(IPP_FLAG_QUADS, n_quads - c * IPP_FLAG_QUADS);
+    const int32_t nt = (nq + 31) >> 5;
+    const bool tvalid = lane < nt;
+    const uint32_t tl = (uint32_t)(c * ITEM_TILES + lane);  // this lane's tile, numbered through the whole map
+    const uint32_t my_flags = lane < A ? st.map_flags[((int64_t)b * cfg.n_seg + c) * 8 + lane] : 0u;
+    uint32_t tch = 0, ownb = 0;
+    for (int j = 0; j < A; ++j) {
+      const uint32_t rp = rec[4 * A + j];
+      tch |= (tl >= (rp & 0xFFFFu) && tl <= (rp >> 16) ? 1u : 0u) << j;
+      if (have_next) {
+        const uint32_t rn = rec[5 * A + j];
+        ownb |= (tl >= (rn & 0xFFFFu) && tl <= (rn >> 16) ? 1u : 0u) << j;
+      }
+    }
+    if (!kout_one) tch = all_agents;  // every pass multiplies every cell
+    uint32_t drt = 0, needb = 0;
+    for (int i = 0; i < A; ++i) {
+      const uint32_t comm_i = rec[i];
+      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, my_flags, i);
+      const bool d = comm_i != 0u && (((fl >> lane) & 1u) != 0u || !kout_one);
+      drt |= (d ? 1u : 0u) << i;
+      needb |= ((d || ((ownb >> i) & 1u) != 0u || (comm_i & tch) != 0u) ? 1u : 0u) << i;
+    }
+    if (!tvalid) needb = 0u, tch = 0u, drt = 0u;
+    uint32_t* out = step_meta + ((int64_t)b * cfg.n_seg + c) * rw;
+    uint32_t my_need = 0;
+    for (int i = 0; i < A; ++i) {
+      const uint32_t mask_i = __ballot_sync(0xFFFFFFFFu, (needb >> i) & 1u);
+      if (lane == i) my_need = mask_i;
+    }
+    for (int w = lane; w < 4 * A; w += 32) out[w] = rec[w];
+    if (lane < A) {
+      out[4 * A + lane] = my_need;
+      out[5 * A + lane] = my_flags & ((nt >= 32) ? 0xFFFFFFFFu : ((1u << nt) - 1u));
+    }
+    // tile bytes, two tiles per word: lanes 0, 2, 4 .. write (own | neighbour << 16)
+    const uint32_t tb = tch | (drt << 8);
+    const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, tb, 1);
+    if (lane < ITEM_TILES && (lane & 1) == 0) out[6 * A + (lane >> 1)] = tb | (nb << 16);
+  }
+}
+
 constexpr int PLAN_WARPS = 16;     // warps per block: one env per warp and round in phase 2
 constexpr int PLAN_ENVS = 16;      // envs per block (default)
 constexpr int PLAN_MAX_ENVS = 32;  // most envs per block (the launcher picks: see launch_plan)
@@ -277,6 +337,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
   __shared__ int32_t s_npos[PLAN_MAX_ENVS][IPP_MAX_AGENTS][3];
   __shared__ Meas s_meas[PLAN_WARPS][IPP_MAX_AGENTS];
   __shared__ PlanShared s_plan[PLAN_MAX_ENVS];
+  __shared__ uint32_t s_rec[PLAN_MAX_ENVS][6 * IPP_MAX_AGENTS];
   // Phase 1: groups of W lanes (W = power of two >= A), one lane per agent, in the block's first warps
   int W = 1;
   while (W < A) W <<= 1;
@@ -292,8 +353,13 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
         }
     } else {
       plan_moves_group(cfg, e0 + es, env_ok, a, io, st, t, do_comm != 0, do_move != 0, s_plan[es], s_npos[es],
-                       step_meta, gt_params);
+                       s_rec[es], gt_params);
     }
+  }
+  if (do_comm && !do_move) {  // ipp_observe: the map kernel will run: one ItemRec per (env, map segment)
+    __syncthreads();
+    for (int32_t e = warp; e < n_here; e += PLAN_WARPS)
+      build_item_records(cfg, st, e0 + e, lane, s_rec[e], false, step_meta);
   }
   if (!do_move) return;
   if (stage & 4) return;  // debug: no code generation
@@ -310,7 +376,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
   for (int32_t e = warp; e < n_here; e += PLAN_WARPS) {
     const int32_t b = e0 + e;
     // code row of the measurements taken after the move: half (t+1)&1 of the ping-pong buffer
-    uint4* grow = reinterpret_cast<uint4*>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride);
+    uint4* grow = reinterpret_cast<uint4*>(st.meas_codes + code_row_offset(cfg, t + 1, b));
     const uint8_t* gt = st.ground_truth + (int64_t)b * cfg.gt_stride;
     uint8_t* row = reinterpret_cast<uint8_t*>(grow);
     if (stage & 1) {
@@ -325,6 +391,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32)
     uint4* rz = reinterpret_cast<uint4*>(row);
     for (int32_t i = lane; i < n16; i += 32) rz[i] = make_uint4(0u, 0u, 0u, 0u);
     if (lane < A) s_meas[warp][lane] = make_meas(cfg, s_npos[e][lane], st.episodes[b], (uint32_t)lane, (uint32_t)t + 1u);
+    if (do_comm) build_item_records(cfg, st, b, lane, s_rec[e], true, step_meta);  // ItemRec per (env, map segment)
     __syncwarp();  // zeroed row, staged ground truth and s_meas visible to all lanes
     write_all_codes<IPP_MAX_AGENTS>(cfg, s_meas[warp], A, ap, gt, row, lane);
     __syncwarp();
@@ -366,14 +433,14 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   float* loc = st.local_maps + (int64_t)b * A * stride + c0;
 
   // ---- loads that depend on nothing ----
-  const CodeWord<A> cw = load_code<A>(st.meas_codes + ((int64_t)(t & 1) * cfg.n_envs + b) * cfg.code_stride, q);
+  const CodeWord<A> cw = load_code<A>(st.meas_codes + code_row_offset(cfg, t, b), q);
   CodeWord<A> nw;
 #pragma unroll
   for (int w = 0; w < CodeWord<A>::WORDS; ++w) nw.w[w] = 0u;
-  if (DO_OWN) nw = load_code<A>(st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride, q);
+  if (DO_OWN) nw = load_code<A>(st.meas_codes + code_row_offset(cfg, t + 1, b), q);
   const float4 g4 = __ldcs(reinterpret_cast<const float4*>(glob));
-  if (tid < 4 * A) {  // the env's record from the plan kernel (comm bits, LUT rows)
-    reinterpret_cast<uint32_t*>(&s_meta)[tid] = step_meta[(int64_t)b * 4 * A + tid];
+  if (tid < 4 * A) {  // the env's facts from the item's record (comm bits, LUT rows)
+    reinterpret_cast<uint32_t*>(&s_meta)[tid] = step_meta[((int64_t)b * cfg.n_seg + chunk) * rec_words(A) + tid];
   } else if (tid < 5 * A) {
     s_dirty[tid - 4 * A] = st.map_flags[((int64_t)b * cfg.n_seg + chunk) * 8 + (tid - 4 * A)];
     s_bad[tid - 4 * A] = 0u;
@@ -387,11 +454,13 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
 #pragma unroll
   for (int j = 0; j < A; ++j) in_prev |= (cw.byte(j) & 0xFu) << (4 * j);
   float4 l4[A];
-  uint32_t mine = 0;
+  uint32_t mine = 0, pre = 0;
 #pragma unroll
   for (int i = 0; i < A; ++i) {
     const uint32_t en = s_meta.comm[i];
-    const bool all = en != 0u && (((s_dirty[i] >> (tid >> 5)) & 1u) != 0u || !kout_one);  // warp = tile
+    const bool dirty = en != 0u && ((s_dirty[i] >> (tid >> 5)) & 1u) != 0u;  // warp = tile
+    const bool all = dirty || (en != 0u && !kout_one);
+    pre |= (dirty ? 1u : 0u) << i;
     if (have && (all || ((in_prev & s_meta.comm4[i]) | (nw.byte(i) & 0xFu)) != 0u)) {
       mine |= 1u << i;
       l4[i] = __ldcs(reinterpret_cast<const float4*>(loc + (int64_t)i * stride));
@@ -401,10 +470,10 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
   // ---- global map + reward terms ----
   double s1, s2;
   {
-    F4 kj[A];  // (unused here: the local maps re-read their multipliers)
     float f1 = 0.0f, f2 = 0.0f;
-    const float4 gn = global_quad<A>(cfg, s_meta, cw, lut, g4, have ? valid_mask4((int32_t)c0, n_cells) : 0u, kj, f1, f2);
-    if (have) __stcs(reinterpret_cast<float4*>(glob), gn);
+    const float4 gn = global_quad<A>(cfg, s_meta, cw, lut, g4, have ? valid_mask4((int32_t)c0, n_cells) : 0u,
+                                     (1u << A) - 1u, f1, f2);
+    if (have && quad_changed(gn, g4)) __stcs(reinterpret_cast<float4*>(glob), gn);
     s1 = (double)warp_sum_f(f1);  // the same float32 sum over a warp's 32 quads as in the TMA kernel
     s2 = (double)warp_sum_f(f2);
   }
@@ -412,7 +481,9 @@ __global__ void __launch_bounds__(DIRECT_THREADS, A <= 4 ? 2 : 1)
 #pragma unroll
   for (int i = 0; i < A; ++i) {
     if (!((mine >> i) & 1u)) continue;
-    if (local_quad_lut<A, DO_OWN>(cfg, s_meta, i, cw, nw.byte(i), lut, l4[i])) atomicOr(&s_bad[i], 1u << (tid >> 5));
+    if (local_quad<A, DO_OWN>(cfg, s_meta, s_meta.comm[i], s_meta.comm[i], ((pre >> i) & 1u) != 0u, i, cw, nw.byte(i),
+                              lut, l4[i]))
+      atomicOr(&s_bad[i], 1u << (tid >> 5));
     __stcs(reinterpret_cast<float4*>(loc + (int64_t)i * stride), l4[i]);
   }
 
@@ -467,7 +538,7 @@ __global__ void __launch_bounds__(256)
                       const int32_t* __restrict__ pos_out, const int32_t t, const int32_t blocks_per_env) {
   const int32_t b = blockIdx.x / blocks_per_env;
   const int32_t n_quads = (cfg.gx * cfg.gy + 3) >> 2;
-  const uint8_t* code_next = st.meas_codes + ((int64_t)((t + 1) & 1) * cfg.n_envs + b) * cfg.code_stride;
+  const uint8_t* code_next = st.meas_codes + code_row_offset(cfg, t + 1, b);
   const int64_t stride = cfg.map_stride;
   __shared__ uint32_t s_row[A];
   if (threadIdx.x < A) s_row[threadIdx.x] = lut_row(cfg, pos_out + ((int64_t)b * A + threadIdx.x) * 3);
@@ -614,7 +685,7 @@ __global__ void __launch_bounds__(STEP_THREADS)
   const float prior = to_odds(cfg.prior);  // the maps hold odds: prior/(1-prior) in float32
   const F4 o_prior = f4_clamp(f4_splat(prior), cfg.o_min, cfg.o_max);
   constexpr int AP = A <= 4 ? 4 : 8;
-  uint8_t* codes = st.meas_codes + (int64_t)b * cfg.code_stride;  // half 0
+  uint8_t* codes = st.meas_codes + code_row_offset(cfg, 0, b);  // half 0
   const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
   for (int32_t q = chunk * quads_per_chunk + tid; q < q_end; q += STEP_THREADS) {
     const int32_t c0 = q << 2;
@@ -691,7 +762,10 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
   const int stage_gt = (do_move && (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) <= 96 * 1024) ? 1 : 0;
   const size_t smem = stage_gt ? (size_t)PLAN_WARPS * (cfg.gt_stride + cfg.code_stride) : 0;
   int dbg = 0;
-  if (const char* v = getenv("IPP_PLAN_DEBUG")) dbg = atoi(v) & 6;
+#ifdef IPP_PLAN_TIMING_KNOBS  // scripts/plan_bench.py: timing experiments only; not in the product build
+  static const int dbg_env = getenv("IPP_PLAN_DEBUG") ? atoi(getenv("IPP_PLAN_DEBUG")) & 6 : 0;
+  dbg = dbg_env;
+#endif
   static PerDevice attr_set;
   if (!attr_set.cur()) {
     cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -712,10 +786,10 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
   int epb = PLAN_ENVS;
   if ((cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS > n_slots && (cfg.n_envs + n_slots - 1) / n_slots <= PLAN_MAX_ENVS)
     epb = (cfg.n_envs + n_slots - 1) / n_slots;
-  if (const char* v = getenv("IPP_PLAN_EPB")) {  // A/B aid
-    const int e = atoi(v);
-    if (e >= 1 && e <= PLAN_MAX_ENVS) epb = e;
-  }
+#ifdef IPP_PLAN_TIMING_KNOBS
+  static const int epb_env = getenv("IPP_PLAN_EPB") ? atoi(getenv("IPP_PLAN_EPB")) : 0;  // A/B aid
+  if (epb_env >= 1 && epb_env <= PLAN_MAX_ENVS) epb = epb_env;
+#endif
   plan_kernel<<<(cfg.n_envs + epb - 1) / epb, PLAN_WARPS * 32, smem, s>>>(cfg, st, io, t, do_comm, do_move,
                                                                          stage_gt | dbg, step_meta, epb, gt_params);
   return cudaGetLastError();

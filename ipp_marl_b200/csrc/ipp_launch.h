@@ -9,7 +9,8 @@ namespace ipp {
 
 constexpr int STEP_THREADS = 256;   // direct-load variant: threads per (env, chunk) block
 constexpr int TMA_QPC = 640;             // TMA variant: quads per work item (20 tiles of 32 quads, 10 KB per map)
-// consumer warps pulling (item, tile) tasks (+ 1 producer warp + 1 finisher warp; a block has at most 1024 threads)
+// Warps of the TMA map kernel: consumer warps pulling (item, tile) tasks + 1 producer warp + 1 finisher warp.
+// A <= 4: 32 warps (64 registers per thread); A > 4: 28 warps (72 registers).
 __host__ __device__ constexpr int tma_consumer_warps(int n_agents) { return n_agents <= 4 ? 30 : 26; }
 __host__ __device__ constexpr int tma_threads(int n_agents) { return (tma_consumer_warps(n_agents) + 2) * 32; }
 

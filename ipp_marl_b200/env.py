@@ -42,7 +42,7 @@ class BatchedIPPEnv:
         self._glob = torch.empty((self.B, S), dtype=torch.float32, device=dev)
         self._gt = torch.zeros((self.B, t.gt_stride), dtype=torch.uint8, device=dev)
         self.episodes = torch.zeros((self.B,), dtype=torch.int32, device=dev)  # bit pattern = uint32
-        self._codes = torch.zeros((2, self.B, t.code_stride), dtype=torch.uint8, device=dev)
+        self._codes = torch.zeros((self.B, 2, t.code_stride), dtype=torch.uint8, device=dev)
         self._flags = torch.full((self.B, int(self.cfg.n_seg), 8), -1, dtype=torch.int32, device=dev)
         self.positions = torch.zeros((self.T + 1, self.B, self.A, 3), dtype=torch.int32, device=dev)
         # rewards + chosen actions in ONE block (ipp_step_host returns them to the host with a single copy)

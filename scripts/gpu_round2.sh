@@ -14,14 +14,14 @@ if [[ $SEC == *r* ]]; then echo "== reference arm"; timeout 600 python bench.py 
 if [[ $SEC == *c* ]]; then echo "== coma train"; timeout 600 python scripts/train_bench.py --envs 8192 --iters 3 2>$OUT/train_$TAG.err | tail -1 | tee $OUT/train_$TAG.json; fi
 if [[ $SEC == *l* ]]; then echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 200 --csv --log-file $OUT/launches_$TAG.csv \
-  python bench.py --steps 45 --warmup 15 --no-cpu-baseline > $OUT/ncu_list_$TAG.log 2>&1; fi
+  python bench.py --steps 45 --warmup 15 --no-cpu-baseline --no-shapes --no-train > $OUT/ncu_list_$TAG.log 2>&1; fi
 if [[ $SEC == *n* ]]; then echo "== ncu full (tma)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_tma -s 20 -c 1 -f -o $OUT/prof_tma_$TAG \
-  python bench.py --steps 45 --warmup 15 --no-cpu-baseline > $OUT/ncu_tma_$TAG.log 2>&1; fi
+  python bench.py --steps 45 --warmup 15 --no-cpu-baseline --no-shapes --no-train > $OUT/ncu_tma_$TAG.log 2>&1; fi
 if [[ $SEC == *d* ]]; then echo "== ncu full (direct)"
 IPP_STEP_VARIANT=direct timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_direct -s 20 -c 1 -f -o $OUT/prof_direct_$TAG \
-  python bench.py --steps 45 --warmup 15 --no-cpu-baseline > $OUT/ncu_direct_$TAG.log 2>&1; fi
+  python bench.py --steps 45 --warmup 15 --no-cpu-baseline --no-shapes --no-train > $OUT/ncu_direct_$TAG.log 2>&1; fi
 if [[ $SEC == *p* ]]; then echo "== ncu full (plan)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:plan_kernel -s 20 -c 1 -f -o $OUT/prof_plan_$TAG \
-  python bench.py --steps 45 --warmup 15 --no-cpu-baseline > $OUT/ncu_plan_$TAG.log 2>&1; fi
+  python bench.py --steps 45 --warmup 15 --no-cpu-baseline --no-shapes --no-train > $OUT/ncu_plan_$TAG.log 2>&1; fi
 ls -la $OUT | tail -20

@@ -242,7 +242,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def time_env_shape(torch, dist, dev, world, rank, params, B, A, G, steps, warmup, clocks_index=None):
+def time_env_shape(torch, dist, dev, world, rank, params, B, A, G, steps, warmup, clocks_index=None, graphs=True):
     """Device-resident throughput of `ipp_step` on one shape + the map kernel bracketed alone.  Returns a dict."""
     from ipp_marl_b200 import BatchedIPPEnv
 
@@ -250,8 +250,20 @@ def time_env_shape(torch, dist, dev, world, rank, params, B, A, G, steps, warmup
     counts = {"n": 0}
     per_step = 2 if env.tables.n_cells <= 2560 else 3  # plan + map (+ reward finalize when an env spans > 1 item)
 
+    state = {"skip": 0}
+
     def episode_step(i, **kw):
+        """One timestep.  When a whole episode lies ahead it is issued as ONE CUDA-graph launch (ipp_run_steps: the
+        same reset + 15 x (plan, map) kernels, captured once) and the next 14 calls have nothing left to issue."""
+        if state["skip"]:
+            state["skip"] -= 1
+            return
         if i % EP_LEN == 0:
+            if graphs and not kw and i + EP_LEN <= state["n_steps"]:
+                env.run_steps(reset=True)
+                counts["n"] += 2 + EP_LEN * per_step
+                state["skip"] = EP_LEN - 1
+                return
             env.reset()
             counts["n"] += 2
         env.step(**kw)
@@ -263,8 +275,12 @@ def time_env_shape(torch, dist, dev, world, rank, params, B, A, G, steps, warmup
             dist.barrier()
             torch.cuda.synchronize()
 
+    if graphs:
+        env.run_steps(reset=True)  # set-up, not a warm-up step: captures the episode graph (like a JIT / autotune pass)
+    state["n_steps"] = max(warmup, 3)
     for i in range(max(warmup, 3)):
         episode_step(i)
+    state["skip"], state["n_steps"] = 0, steps
     counts["n"] = 0
     sampler = None
     if clocks_index is not None:

@@ -169,6 +169,20 @@ int ipp_reset(ipp_handle* h, const ipp_state* st, int32_t* pos_out, void* stream
 int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream);
 
 /*
+ * n_steps consecutive timesteps t0 .. t0 + n_steps - 1 — optionally preceded by ipp_reset (with_reset != 0, start
+ * positions to reset_pos_out) — as ONE launch: exactly the kernels that the same sequence of ipp_reset / ipp_step
+ * calls would launch, captured once into a CUDA graph that the handle keeps and replays on every later call with the
+ * same arguments (same state buffers, same ios[i] contents, same t0 / n_steps / with_reset).  ios [n_steps] host
+ * array; for a whole episode pass its budget + 1 structs, ios[i].pos_in = ios[i - 1].pos_out.  The policy inputs of
+ * ios (actions_in / probs_in) are device pointers like in ipp_step and are read when the graph runs; results of
+ * every step go where its ios[i] points, so give each step its own reward / action rows to keep them all.
+ * Saves the per-launch host cost and the gaps between the 2 .. 3 kernels of a step (missions/episode_generator.py:
+ * 49-79 is one such loop over the budget).
+ */
+int ipp_run_steps(ipp_handle* h, const ipp_state* st, int32_t with_reset, int32_t* reset_pos_out, int32_t t0,
+                  int32_t n_steps, const ipp_step_io* ios, void* stream);
+
+/*
  * ipp_step for a policy that lives on the HOST: copies the step's policy output from host memory to the device,
  * runs the timestep and copies its results back, all asynchronously on `stream` (one call, no host work between the
  * copies and the two launches).  probs_host [n_envs, n_agents, 6] float32 or actions_host [n_envs, n_agents] int32

@@ -53,7 +53,7 @@ class IppStepIO(C.Structure):
 EXPORTS = [
     "ipp_status_string", "ipp_last_error", "ipp_version", "ipp_create", "ipp_destroy", "ipp_scratch_bytes",
     "ipp_set_step_variant", "ipp_get_step_variant",
-    "ipp_reset", "ipp_step", "ipp_step_host", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_features_actor", "ipp_features_critic",
+    "ipp_reset", "ipp_step", "ipp_run_steps", "ipp_step_host", "ipp_step_phases", "ipp_observe", "ipp_act", "ipp_features_actor", "ipp_features_critic",
     "ipp_export_beliefs", "ipp_ig_plan", "ipp_eval_metrics", "ipp_project_fov", "ipp_measure", "ipp_update_cells",
     "ipp_shannon_entropy", "ipp_fuse_map", "ipp_utility_reward",
 ]
@@ -93,6 +93,7 @@ def load():
     lib.ipp_reset.argtypes = [vp, C.POINTER(IppState), vp, vp]
     for name in ("ipp_step", "ipp_observe", "ipp_act"):
         getattr(lib, name).argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp]
+    lib.ipp_run_steps.argtypes = [vp, C.POINTER(IppState), i32, vp, i32, i32, C.POINTER(IppStepIO), vp]
     lib.ipp_features_actor.argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp, vp]
     lib.ipp_features_critic.argtypes = [vp, C.POINTER(IppState), i32, vp, vp, vp, vp, vp]
     lib.ipp_step_host.argtypes = [vp, C.POINTER(IppState), i32, C.POINTER(IppStepIO), vp, vp, vp, vp, vp, vp]

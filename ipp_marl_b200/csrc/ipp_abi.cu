@@ -22,6 +22,12 @@ struct ipp_handle {
   float4* lut;          // [n_alt, 256] odds multipliers of a quad for every measurement code byte
   ipp::PoolTables pool; // cv2.INTER_AREA tap tables of the feature builders
   // facade scratch (grown on demand)
+  // CUDA graphs of ipp_run_steps, keyed by a hash of everything that is baked into them
+  struct GraphSlot {
+    uint64_t key;
+    cudaGraphExec_t exec;
+  } graphs[8];
+  int n_graphs;
   void* fbuf;
   size_t fbuf_bytes;
   int64_t scratch_bytes;
@@ -162,6 +168,10 @@ int ipp_create(const ipp_config* cfg, ipp_handle** out) {
   cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, h->device);
   h->tma = ipp::plan_tma(h->cfg, smem_optin);
   h->variant = h->tma.ok ? IPP_VARIANT_TMA : IPP_VARIANT_DIRECT;
+  if (ipp::configure_plan() != cudaSuccess || (h->tma.ok && ipp::configure_step_tma(h->cfg, h->tma) != cudaSuccess)) {
+    delete h;
+    return IPP_ERR_CUDA;
+  }
   if (const char* v = getenv("IPP_STEP_VARIANT")) {
     if (strcmp(v, "direct") == 0) h->variant = IPP_VARIANT_DIRECT;
     if (strcmp(v, "tma") == 0 && h->tma.ok) h->variant = IPP_VARIANT_TMA;
@@ -219,6 +229,7 @@ int ipp_destroy(ipp_handle* h) {
   if (h->lut) cudaFree(h->lut);
   ipp::free_pool_tables(&h->pool);
   if (h->fbuf) cudaFree(h->fbuf);
+  for (int i = 0; i < h->n_graphs; ++i) cudaGraphExecDestroy(h->graphs[i].exec);
   delete h;
   return IPP_OK;
 }
@@ -268,6 +279,64 @@ int ipp_step_phases(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_ste
 
 int ipp_step(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, void* stream) {
   return ipp_step_phases(h, st, t, io, IPP_PHASE_MOVE | IPP_PHASE_MAPS, stream);
+}
+
+int ipp_run_steps(ipp_handle* h, const ipp_state* st, int32_t with_reset, int32_t* reset_pos_out, int32_t t0,
+                  int32_t n_steps, const ipp_step_io* ios, void* stream) {
+  DeviceGuard on_device(h);
+  if (h == nullptr || ios == nullptr || n_steps < 1 || n_steps > 4096 || (with_reset && reset_pos_out == nullptr))
+    return IPP_ERR_INVALID_ARG;
+  int rc = check_state(st);
+  if (rc != IPP_OK) return rc;
+  // everything that is baked into the graph: the state and io pointers, the timesteps, the kernel variant
+  uint64_t key = 1469598103934665603ull;
+  auto mix = [&key](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) key = (key ^ b[i]) * 1099511628211ull;
+  };
+  mix(st, sizeof(*st));
+  mix(ios, sizeof(ipp_step_io) * (size_t)n_steps);
+  mix(&with_reset, sizeof(with_reset));
+  mix(&reset_pos_out, sizeof(reset_pos_out));
+  mix(&t0, sizeof(t0));
+  mix(&n_steps, sizeof(n_steps));
+  mix(&h->variant, sizeof(h->variant));
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < h->n_graphs; ++i)
+    if (h->graphs[i].key == key) {
+      IPP_CUDA(h, cudaGraphLaunch(h->graphs[i].exec, s));
+      return IPP_OK;
+    }
+  // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured)
+  cudaStream_t cs = nullptr;
+  IPP_CUDA(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    if (with_reset) rc = ipp_reset(h, st, reset_pos_out, cs);
+    for (int32_t i = 0; rc == IPP_OK && i < n_steps; ++i) rc = ipp_step(h, st, t0 + i, &ios[i], cs);
+    e = cudaStreamEndCapture(cs, &graph);
+  }
+  cudaStreamDestroy(cs);
+  if (rc != IPP_OK) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail_cuda(h, e, "ipp_run_steps: stream capture");
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail_cuda(h, e, "cudaGraphInstantiate");
+  if (h->n_graphs == 8) {  // evict the oldest
+    cudaGraphExecDestroy(h->graphs[0].exec);
+    for (int i = 1; i < 8; ++i) h->graphs[i - 1] = h->graphs[i];
+    h->n_graphs = 7;
+  }
+  h->graphs[h->n_graphs].key = key;
+  h->graphs[h->n_graphs].exec = exec;
+  ++h->n_graphs;
+  IPP_CUDA(h, cudaGraphLaunch(exec, s));
+  return IPP_OK;
 }
 
 int ipp_step_host(ipp_handle* h, const ipp_state* st, int32_t t, const ipp_step_io* io, const float* probs_host,

@@ -566,26 +566,38 @@ __global__ void __launch_bounds__(256)
 // randint() draws 32-bit words, masks them and rejects values above the range.
 // =================================================================================================
 constexpr int MT_DRAWS = 40;
+constexpr int RESET_PREP_THREADS = 128;
 
+// The first MT_DRAWS outputs of MT19937 need mt[0 .. MT_DRAWS] and mt[397 .. 397 + MT_DRAWS - 1] of the seeded state.
+// They live in SHARED memory, one column per thread ([word][thread]: conflict-free) — as per-thread local arrays
+// with a run-time index they were the whole cost of this kernel (32 us for 41 k streams).
 struct MtStream {
-  uint32_t lo[MT_DRAWS + 1];  // mt[0 .. MT_DRAWS]
-  uint32_t hi[MT_DRAWS];      // mt[397 .. 397 + MT_DRAWS - 1]
+  uint32_t* lo;  // lo[i * RESET_PREP_THREADS] = mt[i],        i = 0 .. MT_DRAWS
+  uint32_t* hi;  // hi[i * RESET_PREP_THREADS] = mt[397 + i],  i = 0 .. MT_DRAWS - 1
   int32_t next;
   __device__ void seed(uint32_t s) {
     uint32_t v = s;
     lo[0] = v;
-    for (int32_t i = 1; i < 397 + MT_DRAWS; ++i) {
+#pragma unroll 4
+    for (int32_t i = 1; i <= MT_DRAWS; ++i) {
       v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
-      if (i <= MT_DRAWS) lo[i] = v;
-      if (i >= 397) hi[i - 397] = v;
+      lo[i * RESET_PREP_THREADS] = v;
+    }
+#pragma unroll 4
+    for (int32_t i = MT_DRAWS + 1; i < 397; ++i) v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+#pragma unroll 4
+    for (int32_t i = 397; i < 397 + MT_DRAWS; ++i) {
+      v = 1812433253u * (v ^ (v >> 30)) + (uint32_t)i;
+      hi[(i - 397) * RESET_PREP_THREADS] = v;
     }
     next = 0;
   }
   __device__ uint32_t draw() {
     const int32_t k = min(next, MT_DRAWS - 1);
     ++next;
-    const uint32_t y = (lo[k] & 0x80000000u) | (lo[k + 1] & 0x7FFFFFFFu);
-    uint32_t v = hi[k] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+    const uint32_t a = lo[k * RESET_PREP_THREADS], b = lo[(k + 1) * RESET_PREP_THREADS];
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7FFFFFFFu);
+    uint32_t v = hi[k * RESET_PREP_THREADS] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
     v ^= v >> 11;
     v ^= (v << 7) & 0x9D2C5680u;
     v ^= (v << 15) & 0xEFC60000u;
@@ -610,17 +622,20 @@ struct MtStream {
 };
 
 // thread (b, a): a < A -> start position of agent a; a == A -> ground-truth parameters
-__global__ void __launch_bounds__(128) reset_prep_kernel(const __grid_constant__ ipp_config cfg,
+__global__ void __launch_bounds__(RESET_PREP_THREADS) reset_prep_kernel(const __grid_constant__ ipp_config cfg,
                                                          const uint32_t* __restrict__ episodes,
                                                          int32_t* __restrict__ pos_out,
                                                          int32_t* __restrict__ gt_params,
                                                          uint32_t* __restrict__ flags) {
+  __shared__ uint32_t s_mt[(2 * MT_DRAWS + 1) * RESET_PREP_THREADS];
   const int32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t A = cfg.n_agents;
   if (idx >= cfg.n_envs * (A + 1)) return;
   const int32_t b = idx / (A + 1), a = idx % (A + 1);
   const uint32_t ep = episodes[b];
   MtStream mt;
+  mt.lo = s_mt + threadIdx.x;
+  mt.hi = s_mt + (MT_DRAWS + 1) * RESET_PREP_THREADS + threadIdx.x;
   if (a < A) {
     // RandomState(seed = seed * episode * agent_id): state_space.py:29 (numpy rejects seeds >= 2^32;
     // we wrap, documented in DESIGN.md)
@@ -756,6 +771,18 @@ cudaError_t launch_export_beliefs(const float* src, float* dst, int64_t n_floats
     default: return cudaErrorInvalidValue;    \
   }
 
+// function attributes of the plan kernel on the current device (idempotent; called from ipp_create so that no
+// attribute has to be set while a stream is being captured into a CUDA graph)
+cudaError_t configure_plan() {
+  static PerDevice attr_set;
+  if (!attr_set.cur()) {
+    cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set.cur() = 1;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_step_io& io, int32_t t, int do_comm,
                         int do_move, uint32_t* step_meta, const int32_t* gt_params, cudaStream_t s) {
   // ground truth + new code row of one env per warp in shared memory (falls back to global for big grids)
@@ -766,11 +793,9 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
   static const int dbg_env = getenv("IPP_PLAN_DEBUG") ? atoi(getenv("IPP_PLAN_DEBUG")) & 6 : 0;
   dbg = dbg_env;
 #endif
-  static PerDevice attr_set;
-  if (!attr_set.cur()) {
-    cudaError_t e = cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  {
+    cudaError_t e = configure_plan();
     if (e != cudaSuccess) return e;
-    attr_set.cur() = 1;
   }
   // Envs per block: two 80 KB blocks fit an SM, so the GPU runs 2 * n_sm blocks at a time.  When the batch needs
   // more than one such wave of 16-env blocks but fits ONE wave of <= 32-env blocks, use the larger blocks: the
@@ -786,6 +811,11 @@ cudaError_t launch_plan(const ipp_config& cfg, const ipp_state& st, const ipp_st
   int epb = PLAN_ENVS;
   if ((cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS > n_slots && (cfg.n_envs + n_slots - 1) / n_slots <= PLAN_MAX_ENVS)
     epb = (cfg.n_envs + n_slots - 1) / n_slots;
+  // a small batch does not fill the GPU with 16-env blocks: fewer envs per block so that every SM gets work
+  if ((cfg.n_envs + PLAN_ENVS - 1) / PLAN_ENVS < n_slots / 2) {
+    epb = (cfg.n_envs + n_slots - 1) / n_slots;
+    if (epb < 2) epb = 2;
+  }
 #ifdef IPP_PLAN_TIMING_KNOBS
   static const int epb_env = getenv("IPP_PLAN_EPB") ? atoi(getenv("IPP_PLAN_EPB")) : 0;  // A/B aid
   if (epb_env >= 1 && epb_env <= PLAN_MAX_ENVS) epb = epb_env;
@@ -833,7 +863,7 @@ cudaError_t launch_own_update(const ipp_config& cfg, const ipp_state& st, const 
 
 cudaError_t launch_reset(const ipp_config& cfg, const ipp_state& st, const float4* lut, const LaunchPlan& plan,
                          int32_t* pos_out, int32_t* gt_params, cudaStream_t s) {
-  const int threads = 128;
+  const int threads = RESET_PREP_THREADS;
   const int n = cfg.n_envs * (cfg.n_agents + 1);
   reset_prep_kernel<<<(n + threads - 1) / threads, threads, 0, s>>>(cfg, st.episodes, pos_out, gt_params,
                                                                     st.map_flags);

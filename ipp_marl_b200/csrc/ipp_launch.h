@@ -36,6 +36,8 @@ struct TmaPlan {
 };
 
 TmaPlan plan_tma(const ipp_config& cfg, int max_smem_optin);
+cudaError_t configure_step_tma(const ipp_config& cfg, const TmaPlan& plan);
+cudaError_t configure_plan();
 
 // cv2.INTER_AREA tap tables of the feature builders (device memory, owned by the handle)
 struct PoolTables {

@@ -390,12 +390,11 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
                                 int n_sm, const uint32_t* step_meta, int32_t t, float* reward_rel, float* reward_abs,
                                 double* partials, cudaStream_t s) {
   auto kern = step_tma_kernel<A, DO_OWN>;
-  static PerDevice configured;  // per template instantiation and device; grows to the largest plan seen
-  int& configured_bytes = configured.cur();
-  if (plan.smem_bytes > configured_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  static PerDevice configured;  // per template instantiation and device (normally done by configure_step_tma)
+  if (!configured.cur()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured_bytes = plan.smem_bytes;
+    configured.cur() = 1;
   }
   const int n_items = cfg.n_envs * plan.n_chunks;
   const int grid = n_items < n_sm ? n_items : n_sm;
@@ -407,6 +406,30 @@ static cudaError_t launch_tma_t(const ipp_config& cfg, const ipp_state& st, cons
   kern<<<grid, tma_threads(A), plan.smem_bytes, s>>>(cfg, st, lut, step_meta, t, reward_rel, reward_abs, partials,
                                                    plan.n_chunks, n_items, plan.slot_bytes, plan.env_bytes, dbg);
   return cudaGetLastError();
+}
+
+// dynamic shared-memory limit of both instantiations (with / without the own update) for this shape on the current
+// device; called from ipp_create so that nothing has to be configured while a stream is being captured
+template <int A>
+static cudaError_t configure_tma_t(const TmaPlan& plan) {
+  cudaError_t e = cudaFuncSetAttribute(step_tma_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  (void)plan;
+  return cudaFuncSetAttribute(step_tma_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+cudaError_t configure_step_tma(const ipp_config& cfg, const TmaPlan& plan) {
+  switch (cfg.n_agents) {
+    case 1: return configure_tma_t<1>(plan);
+    case 2: return configure_tma_t<2>(plan);
+    case 3: return configure_tma_t<3>(plan);
+    case 4: return configure_tma_t<4>(plan);
+    case 5: return configure_tma_t<5>(plan);
+    case 6: return configure_tma_t<6>(plan);
+    case 7: return configure_tma_t<7>(plan);
+    case 8: return configure_tma_t<8>(plan);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_step_tma(const ipp_config& cfg, const ipp_state& st, const float4* lut, const TmaPlan& plan,

@@ -60,6 +60,8 @@ class BatchedIPPEnv:
         self._folded = False
         self._ig_actions = None
         self._ios = {}
+        self._hist = None
+        self._default_episodes = False
 
     # ---- views in the reference's array convention: [.., gx, gy], first axis = world x ----------
     def _view(self, flat):
@@ -131,17 +133,28 @@ class BatchedIPPEnv:
     # ---- episode reset ------------------------------------------------------------------------
     def reset(self, episodes=None):
         """Start episode ``episodes[b]`` in env b (default: global env index + 1)."""
-        if episodes is None:
-            ep = torch.arange(self.B, dtype=torch.int64) + (self.env_id_base + 1)
-        else:
-            ep = torch.as_tensor(episodes, dtype=torch.int64).reshape(self.B)
-        ep32 = torch.where(ep >= 2**31, ep - 2**32, ep).to(torch.int32)
-        self.episodes.copy_(ep32, non_blocking=True)
+        self._set_episodes(episodes)
         self.t = 0
         self._observed = False
         self._folded = False
         rc = self.lib.ipp_reset(self._h, C.byref(self._state), _ptr(self.positions[0]), self._stream())
         N.check(self.lib, self._h, rc, "ipp_reset")
+
+    def _set_episodes(self, episodes):
+        """Episode number of every env (device buffer read by ipp_reset).  The default numbering (global env index + 1,
+        SURVEY.md 8d/8e) is uploaded once; a repeated default reset costs no host-to-device copy."""
+        if episodes is None:
+            if self._default_episodes:
+                return
+            ep = torch.arange(self.B, dtype=torch.int64) + (self.env_id_base + 1)
+            self._default_episodes = True
+        else:
+            if torch.is_tensor(episodes) and episodes.is_cuda:
+                ep = episodes.to(torch.int64).reshape(self.B)
+            else:
+                ep = torch.as_tensor(episodes, dtype=torch.int64).reshape(self.B)
+            self._default_episodes = False
+        self.episodes.copy_(torch.where(ep >= 2**31, ep - 2**32, ep).to(torch.int32), non_blocking=True)
 
     def _io(self, actions, probs, greedy):
         io = N.IppStepIO()
@@ -190,6 +203,46 @@ class BatchedIPPEnv:
         done = self.t == self.tables.budget  # coma_wrapper.py:163-164
         self.t += 1
         return self.reward_rel, self.reward_abs, done
+
+    # ---- a whole episode (or any run of timesteps) as ONE launch -------------------------------
+    def run_steps(self, n_steps=None, reset=False, episodes=None):
+        """``n_steps`` timesteps of the uniform masked policy from the current timestep — preceded by the episode reset
+        when ``reset`` — as ONE CUDA-graph launch (C ABI ``ipp_run_steps``; captured once, then replayed).  Default:
+        the rest of the episode.  The results of every step are kept: ``reward_hist`` [T, 2, B] (relative, absolute),
+        ``action_hist`` / ``mask_hist`` [T, B, A]; ``reward_rel`` / ``reward_abs`` / ``actions`` / ``masks`` keep their
+        meaning "of the last ipp_step call" and are NOT written by this path.  Returns ``done``."""
+        if reset:
+            self._set_episodes(episodes)
+            self.t = 0
+            self._observed = False
+            self._folded = False
+        if n_steps is None:
+            n_steps = self.T - self.t
+        if n_steps < 1 or self.t + n_steps > self.T:
+            raise N.IppError("run_steps: %d steps from t = %d do not fit the episode (T = %d)" % (n_steps, self.t, self.T))
+        if self._hist is None:
+            dev = self.device
+            self.reward_hist = torch.zeros((self.T, 2, self.B), dtype=torch.float32, device=dev)
+            self.action_hist = torch.zeros((self.T, self.B, self.A), dtype=torch.int32, device=dev)
+            self.mask_hist = torch.zeros((self.T, self.B, self.A), dtype=torch.uint8, device=dev)
+            ios = (N.IppStepIO * self.T)()
+            keep, self.t = self.t, 0
+            for t in range(self.T):
+                self.t = t
+                io = self._io(None, None, False)
+                io.reward_rel = _ptr(self.reward_hist[t, 0])
+                io.reward_abs = _ptr(self.reward_hist[t, 1])
+                io.actions_out = _ptr(self.action_hist[t])
+                io.mask_out = _ptr(self.mask_hist[t])
+                ios[t] = io
+            self.t = keep
+            self._hist = ios
+        first = C.cast(C.byref(self._hist, self.t * C.sizeof(N.IppStepIO)), C.POINTER(N.IppStepIO))
+        rc = self.lib.ipp_run_steps(self._h, C.byref(self._state), 1 if reset else 0, _ptr(self.positions[0]), self.t,
+                                    n_steps, first, self._stream())
+        N.check(self.lib, self._h, rc, "ipp_run_steps")
+        self.t += n_steps
+        return self.t == self.T
 
     def host_results(self):
         """Pinned host buffers (reward_rel [B], reward_abs [B], actions [B, A]) carved out of ONE block, so that

@@ -237,7 +237,8 @@ def test_full_size_properties():
     # a random subsample of envs is bit-exact against the kernel model
     from oracle import kernel_model as km
 
-    pick = np.array([0, 17, 4095, 8191])
+    rng = np.random.default_rng(8192)
+    pick = np.unique(np.concatenate([[0, 17, 4095, 8191], rng.choice(B, 64, replace=False)]))  # >= 64 random envs
     model = km.KernelModelEnv(params, pick + 1)
     for t in range(env.T):
         model.step()
@@ -278,3 +279,43 @@ def test_step_host_matches_device_step():
     assert torch.equal(a.local_odds, b.local_odds) and torch.equal(a.global_odds, b.global_odds)
     with pytest.raises(Exception):
         b.step_host(probs, None, rel_h, abs_h, act_h)  # episode finished
+
+
+def test_run_steps_graph_equals_eager_steps():
+    """ipp_run_steps (one CUDA-graph launch per episode, captured once and replayed) == the same ipp_reset / ipp_step
+    calls one by one: bit-identical maps, positions, per-step rewards, actions and masks — on the first (capturing)
+    call, on the replay of a second episode, and for a partial run from the middle of an episode."""
+    import torch
+    from ipp_marl_b200 import BatchedIPPEnv
+
+    params = load_kats()["synthetic50"]["params"]
+    params["experiment"]["missions"]["n_agents"] = 3
+    B = 37
+    a = BatchedIPPEnv(params, B, device="cuda:0")
+    b = BatchedIPPEnv(params, B, device="cuda:0")
+    for ep0 in (1, 500):
+        eps = torch.arange(B) + ep0
+        a.reset(eps)
+        rel, ab, act, msk = [], [], [], []
+        for t in range(a.T):
+            r, q, _ = a.step()
+            rel.append(r.clone()); ab.append(q.clone()); act.append(a.actions.clone()); msk.append(a.masks.clone())
+        assert b.run_steps(reset=True, episodes=eps) is True
+        torch.cuda.synchronize()
+        assert torch.equal(a._local, b._local) and torch.equal(a._glob, b._glob) and torch.equal(a._flags, b._flags)
+        assert torch.equal(a.positions, b.positions)
+        assert torch.equal(torch.stack(rel), b.reward_hist[:, 0]) and torch.equal(torch.stack(ab), b.reward_hist[:, 1])
+        assert torch.equal(torch.stack(act), b.action_hist) and torch.equal(torch.stack(msk), b.mask_hist)
+    # partial: eager reset + 4 steps, then the rest of the episode as one launch
+    eps = torch.arange(B) + 77
+    a.reset(eps)
+    b.reset(eps)
+    for t in range(a.T):
+        a.step()
+    for t in range(4):
+        b.step()
+    assert b.run_steps() is True
+    torch.cuda.synchronize()
+    assert torch.equal(a._local, b._local) and torch.equal(a._glob, b._glob) and torch.equal(a.positions, b.positions)
+    with pytest.raises(Exception):
+        b.run_steps()  # episode finished

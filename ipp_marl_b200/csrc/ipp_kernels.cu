@@ -325,7 +325,7 @@ constexpr int PLAN_MAX_ENVS = 32;  // most envs per block (the launcher picks: s
 // SHARED memory next to a staged copy of the ground truth and written out with coalesced 16-byte stores:
 // scattering one byte per (quad, agent) straight to global memory costs one L2 write transaction per byte
 // (7.4 M per launch at 8192 envs — that, not the arithmetic, bounded earlier versions of this kernel).
-__global__ void __launch_bounds__(PLAN_WARPS * 32)
+__global__ void __launch_bounds__(PLAN_WARPS * 32, 2)  // two 93 KB blocks per SM (more do not fit: measured no gain)
     plan_kernel(const __grid_constant__ ipp_config cfg, const ipp_state st, const ipp_step_io io, const int32_t t,
                 const int32_t do_comm, const int32_t do_move, const int32_t stage, uint32_t* __restrict__ step_meta,
                 const int32_t epb, const int32_t* __restrict__ gt_params) {
@@ -702,28 +702,42 @@ __global__ void __launch_bounds__(STEP_THREADS)
   constexpr int AP = A <= 4 ? 4 : 8;
   uint8_t* codes = st.meas_codes + code_row_offset(cfg, 0, b);  // half 0
   const int32_t q_end = min((chunk + 1) * quads_per_chunk, n_quads);
+  const float4 prior4 = make_float4(prior, prior, prior, prior);
   for (int32_t q = chunk * quads_per_chunk + tid; q < q_end; q += STEP_THREADS) {
     const int32_t c0 = q << 2;
+    const int32_t x0 = c0 / cfg.gy, y0 = c0 - x0 * cfg.gy;  // first cell of the quad; it wraps into row x0 + 1 after n0
+    const int32_t n0 = min(4, cfg.gy - y0);
+    const int32_t left = n_cells - c0;
+    const uint32_t valid = left >= 4 ? 0xFu : ((1u << max(left, 0)) - 1u);
     uint32_t g4 = 0;
     {
-      int32_t x = c0 / cfg.gy, y = c0 - x * cfg.gy;
+      int32_t x = x0, y = y0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int32_t v = (split < 2) ? x : y;
-        if (c0 + c < n_cells && v >= lo && v < hi) g4 |= 1u << (8 * c);
+        if (((valid >> c) & 1u) && v >= lo && v < hi) g4 |= 1u << (8 * c);
         if (++y == cfg.gy) { y = 0; ++x; }
       }
     }
     *reinterpret_cast<uint32_t*>(st.ground_truth + (int64_t)b * cfg.gt_stride + c0) = g4;
-    *reinterpret_cast<float4*>(st.global_map + (int64_t)b * stride + c0) = make_float4(prior, prior, prior, prior);
+    __stcs(reinterpret_cast<float4*>(st.global_map + (int64_t)b * stride + c0), prior4);
     uint32_t cw[2] = {0u, 0u};
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      const uint32_t byte = (c0 < n_cells) ? meas_code_byte(cfg, s_m[i], c0, g4) : 0u;
-      cw[i >> 2] |= byte << (8 * (i & 3));
-      F4 pv = f4_splat(prior);
-      if (byte & 0xFu) pv = f4_select(byte & 0xFu, f4_mul(o_prior, f4_from(lut[s_row[i] + byte])), pv);
-      *reinterpret_cast<float4*>(st.local_maps + ((int64_t)b * A + i) * stride + c0) = f4_to(pv);
+      const Meas& m = s_m[i];
+      // most quads lie in no footprint row of agent i: one range test, prior odds, nothing else
+      const uint32_t rows = (uint32_t)(m.xr - m.xl);
+      const bool near = (uint32_t)(x0 - m.xl) < rows || (n0 < 4 && (uint32_t)(x0 + 1 - m.xl) < rows);
+      float4 out = prior4;
+      if (near) {
+        const uint32_t in = rect_mask4(m, x0, y0, n0) & valid;
+        if (in != 0u) {
+          const uint32_t byte = in | ((seen_mask4(m.key, m.thresh, c0, g4) & in) << 4);
+          cw[i >> 2] |= byte << (8 * (i & 3));
+          out = f4_to(f4_select(in, f4_mul(o_prior, f4_from(lut[s_row[i] + byte])), f4_splat(prior)));
+        }
+      }
+      __stcs(reinterpret_cast<float4*>(st.local_maps + ((int64_t)b * A + i) * stride + c0), out);
     }
     if ((int64_t)q * AP < cfg.code_stride) {
       if (AP == 4) reinterpret_cast<uint32_t*>(codes)[q] = cw[0];

@@ -1,23 +1,24 @@
-"""Timing of the plan kernel and its phases (IPP_PLAN_DEBUG: 2 = no planning (agents stay), 4 = no code generation)."""
+"""Plan kernel timed alone (development aid): CUDA-event bracket of IPP_PHASE_MOVE over a few episodes."""
 import json, os, sys
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 from ipp_marl_b200 import BatchedIPPEnv
-params = json.load(open(os.path.join(sys.path[0], "tests/golden/kats.json")))["synthetic50"]["params"]
-params["experiment"]["missions"]["n_agents"] = 4
-env = BatchedIPPEnv(params, 8192, device="cuda:0")
-for dbg in sys.argv[1:] or ["0", "4", "2"]:
-    if dbg.startswith("e"):  # e16 / e28: envs per block override
-        os.environ["IPP_PLAN_EPB"] = dbg[1:]
-        dbg = "0"
-    os.environ["IPP_PLAN_DEBUG"] = dbg
+kats = json.load(open(os.path.join(ROOT, "tests/golden/kats.json")))
+for s in [a for a in sys.argv[1:] if "x" in a] or ["8192x4x50"]:
+    B, A, G = (int(v) for v in s.split("x"))
+    params = kats["synthetic100" if G == 100 else "synthetic50"]["params"]
+    params["experiment"]["missions"]["n_agents"] = A
+    env = BatchedIPPEnv(params, B, device="cuda:0")
+    env.reset()
+    for _ in range(15): env.step()
     evs = []
     def hook(phase, before):
         if phase == 1:
             ev = torch.cuda.Event(enable_timing=True); ev.record(); evs.append(ev)
-    for ep in range(8):
+    for ep in range(6):
         env.reset()
         for _ in range(15): env.step(_phase_hook=hook)
     torch.cuda.synchronize()
-    ms = [evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(30, len(evs) // 2)]
-    print("IPP_PLAN_DEBUG=%s EPB=%s plan kernel mean %.1f us" % (dbg, os.environ.get("IPP_PLAN_EPB", "auto"), sum(ms) / len(ms) * 1e3))
+    ms = [evs[2 * i].elapsed_time(evs[2 * i + 1]) for i in range(len(evs) // 2)]
+    print("%s plan kernel mean %.1f us (event bracket)" % (s, 1e3 * sum(ms) / len(ms)), flush=True)

@@ -263,7 +263,15 @@ __device__ __forceinline__ void write_all_codes(const ipp_config& cfg, const Mea
   }
 }
 
-// One warp writes the ItemRec of every segment of one env (ipp_cell.cuh): lane t looks at tile t of the segment.
+// bits of the tiles [t0, t0 + nt) of a map segment that lie inside the packed tile range r (bit 0 = tile t0; nt <= 32)
+__device__ __forceinline__ uint32_t range_bits(uint32_t r, int32_t t0, int32_t nt) {
+  const int32_t lo = max((int32_t)(r & 0xFFFFu), t0) - t0, hi = min((int32_t)(r >> 16), t0 + nt - 1) - t0;
+  return hi < lo ? 0u : ((2u << hi) - (1u << lo));
+}
+
+// One warp writes the ItemRec of every segment of one env (ipp_cell.cuh).  Lane i < A works on agent / local map i
+// with whole-segment tile masks (a footprint's tiles are one run of bits), lane t < ITEM_TILES then assembles the
+// facts of tile t from the A masks.
 // rec = the env's words from plan_moves_group: comm | comm4 | lut_prev | lut_next | rng_prev | rng_next (A each).
 __device__ void build_item_records(const ipp_config& cfg, const ipp_state& st, const int32_t b, const int lane,
                                    const uint32_t* rec, const bool have_next, uint32_t* __restrict__ step_meta) {
@@ -271,42 +279,31 @@ __device__ void build_item_records(const ipp_config& cfg, const ipp_state& st, c
   const int rw = rec_words(A);
   const bool kout_one = (cfg.k_out == 1.0f);
   const int32_t n_quads = (cfg.gx * cfg.gy + 3) >> 2;
-  const uint32_t all_agents = (1u << A) - 1u;
+  const bool agent = lane < A;
+  const uint32_t comm_i = agent ? rec[lane] : 0u;
+  const uint32_t rp = agent ? rec[4 * A + lane] : 1u, rn = (agent && have_next) ? rec[5 * A + lane] : 1u;
   for (int32_t c = 0; c < cfg.n_seg; ++c) {
     const int32_t nq = min(IPP_FLAG_QUADS, n_quads - c * IPP_FLAG_QUADS);
     const int32_t nt = (nq + 31) >> 5;
-    const bool tvalid = lane < nt;
-    const uint32_t tl = (uint32_t)(c * ITEM_TILES + lane);  // this lane's tile, numbered through the whole map
-    const uint32_t my_flags = lane < A ? st.map_flags[((int64_t)b * cfg.n_seg + c) * 8 + lane] : 0u;
-    uint32_t tch = 0, ownb = 0;
+    const uint32_t tiles = nt >= 32 ? 0xFFFFFFFFu : ((1u << nt) - 1u);
+    const uint32_t flags = agent ? st.map_flags[((int64_t)b * cfg.n_seg + c) * 8 + lane] & tiles : 0u;
+    // lane i: tiles agent i's communicated footprint reaches; tiles that must be clamped as a whole; tiles with work
+    uint32_t touch = agent ? (kout_one ? range_bits(rp, c * ITEM_TILES, nt) : tiles) : 0u;
+    const uint32_t dirty = comm_i != 0u ? (kout_one ? flags : tiles) : 0u;
+    uint32_t need = dirty | range_bits(rn, c * ITEM_TILES, nt);
+    uint32_t tch = 0, drt = 0;  // lane t: bit j / i of tile t
     for (int j = 0; j < A; ++j) {
-      const uint32_t rp = rec[4 * A + j];
-      tch |= (tl >= (rp & 0xFFFFu) && tl <= (rp >> 16) ? 1u : 0u) << j;
-      if (have_next) {
-        const uint32_t rn = rec[5 * A + j];
-        ownb |= (tl >= (rn & 0xFFFFu) && tl <= (rn >> 16) ? 1u : 0u) << j;
-      }
+      const uint32_t touch_j = __shfl_sync(0xFFFFFFFFu, touch, j);
+      const uint32_t dirty_j = __shfl_sync(0xFFFFFFFFu, dirty, j);
+      if ((comm_i >> j) & 1u) need |= touch_j;
+      tch |= ((touch_j >> lane) & 1u) << j;
+      drt |= ((dirty_j >> lane) & 1u) << j;
     }
-    if (!kout_one) tch = all_agents;  // every pass multiplies every cell
-    uint32_t drt = 0, needb = 0;
-    for (int i = 0; i < A; ++i) {
-      const uint32_t comm_i = rec[i];
-      const uint32_t fl = __shfl_sync(0xFFFFFFFFu, my_flags, i);
-      const bool d = comm_i != 0u && (((fl >> lane) & 1u) != 0u || !kout_one);
-      drt |= (d ? 1u : 0u) << i;
-      needb |= ((d || ((ownb >> i) & 1u) != 0u || (comm_i & tch) != 0u) ? 1u : 0u) << i;
-    }
-    if (!tvalid) needb = 0u, tch = 0u, drt = 0u;
     uint32_t* out = step_meta + ((int64_t)b * cfg.n_seg + c) * rw;
-    uint32_t my_need = 0;
-    for (int i = 0; i < A; ++i) {
-      const uint32_t mask_i = __ballot_sync(0xFFFFFFFFu, (needb >> i) & 1u);
-      if (lane == i) my_need = mask_i;
-    }
     for (int w = lane; w < 4 * A; w += 32) out[w] = rec[w];
-    if (lane < A) {
-      out[4 * A + lane] = my_need;
-      out[5 * A + lane] = my_flags & ((nt >= 32) ? 0xFFFFFFFFu : ((1u << nt) - 1u));
+    if (agent) {
+      out[4 * A + lane] = need;
+      out[5 * A + lane] = flags;
     }
     // tile bytes, two tiles per word: lanes 0, 2, 4 .. write (own | neighbour << 16)
     const uint32_t tb = tch | (drt << 8);

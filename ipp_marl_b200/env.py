@@ -16,6 +16,13 @@ from . import _native as N
 from .geometry import HostTables, make_config
 
 
+def default_episode_ids(n_envs, env_id_base=0):
+    """Episode number of env b of a shard that starts at global env index ``env_id_base``: global index + 1
+    (SURVEY.md 8d/8e).  Rank r of a sharded job passes ``env_id_base = r * n_envs``; all random streams are keyed on the
+    episode number, so the results do not depend on how the batch is cut into shards."""
+    return torch.arange(int(n_envs), dtype=torch.int64) + (int(env_id_base) + 1)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -146,7 +153,7 @@ class BatchedIPPEnv:
         if episodes is None:
             if self._default_episodes:
                 return
-            ep = torch.arange(self.B, dtype=torch.int64) + (self.env_id_base + 1)
+            ep = default_episode_ids(self.B, self.env_id_base)
             self._default_episodes = True
         else:
             if torch.is_tensor(episodes) and episodes.is_cuda:

@@ -47,6 +47,15 @@ class HostTables:
             raise ValueError("only the 6-action space (params.yaml default) is implemented on the GPU path")
         self.n_agents = int(params["experiment"]["missions"]["n_agents"])
         self.prior = float(params["mapping"]["prior"])
+        if self.prior != 0.5:
+            import warnings
+
+            # DESIGN.md section 2, deviation (1): with prior != 0.5 every pass multiplies every cell (k_out != 1), the
+            # unobserved cells drift and saturate, and the entropy-reduction reward becomes a difference of O(1e-3)
+            # float32-vs-float64 rounding terms: belief maps still meet the 1e-5 gate, rewards only 2e-2.
+            warnings.warn("mapping.prior = %g != 0.5: the batched path's belief maps match the reference to 1e-5, but its "
+                          "rewards only to 2e-2 (DESIGN.md section 2); the footprint-sparse fast path is off (every tile "
+                          "is processed every step)" % self.prior, RuntimeWarning, stacklevel=3)
         self.comm_range = float(params["experiment"]["uav"]["communication_range"])
         self.failure_rate = float(params["experiment"]["uav"]["failure_rate"])
         ax = sen["field_of_view"]["angle_x"]

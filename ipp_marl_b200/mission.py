@@ -100,6 +100,13 @@ def load_actor_state(path, map_location="cpu"):
     return {k: v for k, v in obj.items()}
 
 
+def next_episode_ids(n_envs, next_episode, world):
+    """Episode numbers of this rank's next rollout and the rank's counter after it: every rollout of the job consumes
+    ``n_envs * world`` consecutive numbers, rank r's block starts at ``env_id_base + 1 = r * n_envs + 1``."""
+    ids = torch.arange(int(n_envs), dtype=torch.int64) + int(next_episode)
+    return ids, int(next_episode) + int(n_envs) * int(world)
+
+
 def _stats(log, prefix, values, step):
     v = values.double().flatten()
     log.add_scalar(prefix + "/mean", v.mean(), step)
@@ -138,8 +145,7 @@ class COMAMission:
             self.log.add_scalar("%sAltitudes/%d" % (mode, z), (alt == z).sum(), step)
 
     def _episodes(self):
-        ids = torch.arange(self.env.B, dtype=torch.int64) + self._next_episode
-        self._next_episode += self.env.B * self._world()
+        ids, self._next_episode = next_episode_ids(self.env.B, self._next_episode, self._world())
         return ids
 
     @staticmethod

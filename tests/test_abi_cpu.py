@@ -83,9 +83,10 @@ def test_invalid_configs_are_rejected():
 
 
 def test_sharding_is_partition_invariant_gloo(tmp_path):
-    """world_size-2 gloo run of the host-side sharding logic bench.py uses: rank r owns global envs
-    [r*B, (r+1)*B) (episode = global index + 1) and the job metric is the sum over ranks divided by
-    the max-over-ranks time.  No data-path collective exists on the env path (envs are independent)."""
+    """world_size-2 gloo run of the repo's host-side sharding logic: `env.default_episode_ids` (rank r owns global
+    envs [r*B, (r+1)*B), episode = global index + 1), `mission.next_episode_ids` (successive rollouts of a sharded
+    training job never reuse an episode number) and the job metric of bench.py (sum over ranks / max-over-ranks
+    time).  No data-path collective exists on the env path (envs are independent)."""
     script = tmp_path / "w.py"
     script.write_text(r"""
 import os, sys, json
@@ -93,14 +94,24 @@ import torch, torch.distributed as dist
 sys.path.insert(0, %r)
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
+from ipp_marl_b200.env import default_episode_ids
+from ipp_marl_b200.mission import next_episode_ids
 B = 6
-ep = torch.arange(B, dtype=torch.int64) + (rank * B + 1)          # BatchedIPPEnv.reset default with env_id_base=rank*B
+ep = default_episode_ids(B, rank * B)                              # BatchedIPPEnv.reset default with env_id_base=rank*B
 gathered = [torch.zeros_like(ep) for _ in range(world)]
 dist.all_gather(gathered, ep)
+nxt = rank * B + 1                                                 # COMAMission._next_episode at construction
+seen = []
+for rollout in range(3):
+    ids, nxt = next_episode_ids(B, nxt, world)
+    allr = [torch.zeros_like(ids) for _ in range(world)]
+    dist.all_gather(allr, ids)
+    seen += torch.cat(allr).tolist()
 ms = torch.tensor([10.0 + rank], dtype=torch.float64)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"episodes": torch.cat(gathered).tolist(), "ms": ms.item(), "value": world * B / (ms.item() * 1e-3)}))
+    print(json.dumps({"episodes": torch.cat(gathered).tolist(), "ms": ms.item(), "value": world * B / (ms.item() * 1e-3),
+                      "rollouts": sorted(seen)}))
 dist.destroy_process_group()
 """ % ROOT)
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
@@ -113,3 +124,18 @@ dist.destroy_process_group()
     out = json.loads(line)
     assert out["episodes"] == list(range(1, 13))  # ranks tile the global episode range without overlap
     assert out["ms"] == 11.0 and abs(out["value"] - 12 / 0.011) < 1e-6
+    assert out["rollouts"] == list(range(1, 37))  # 3 rollouts x 2 ranks x 6 envs: every episode number exactly once
+
+
+def test_prior_other_than_half_warns():
+    """DESIGN.md section 2, deviation (1): rewards agree with the reference only to 2e-2 when mapping.prior != 0.5 —
+    HostTables says so loudly."""
+    import copy
+
+    from ipp_marl_b200.geometry import HostTables
+    from tests.helpers import load_kats
+
+    params = copy.deepcopy(load_kats()["synthetic50"]["params"])
+    params["mapping"]["prior"] = 0.4
+    with pytest.warns(RuntimeWarning, match="prior"):
+        HostTables(params)

@@ -141,6 +141,15 @@ __device__ __forceinline__ float from_odds(float o) {
   return (o < 1.0f) ? __fdiv_rn(o, d) : __fsub_rn(1.0f, __fdiv_rn(1.0f, d));
 }
 
+// The same within ~2 ulp from one MUFU.RCP instead of an IEEE division (26 instructions with its two-sided branch):
+// for consumers whose own tolerance is far above float32 rounding (the area-pooled network inputs; NOT the exported
+// beliefs, which are bit-exact against the kernel model).
+__device__ __forceinline__ float from_odds_fast(float o) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + o));
+  return (o < 1.0f) ? o * r : 1.0f - r;
+}
+
 // Weighted entropy terms of the reward (utils/state.py:53-76,118-121; utils/reward.py:68-82).
 __device__ __forceinline__ float shannon(const ipp_config& c, float p) {
   const float pc = clamp_p(c, p);

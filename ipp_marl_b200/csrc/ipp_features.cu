@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128)
             if (j != i && ((received >> j) & 1u) && (cw.byte(j) & bit)) o = 0.0f;
           if (cw.byte(i) & bit) o = 1.0f;
           const float wy = ty.weight(lj, k);
-          row_l += wy * from_odds(local[cell]);  // the maps hold odds
+          row_l += wy * from_odds_fast(local[cell]);  // the maps hold odds
           row_o += wy * o;
         }
         pl += wx * row_l;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(128)
         for (int j = 0; j < A; ++j)
           if (cw.byte(j) & bit) u = 1.0f;
         const float wy = ty.weight(lj, k);
-        row_g += wy * from_odds(glob[cell]);  // the maps hold odds
+        row_g += wy * from_odds_fast(glob[cell]);  // the maps hold odds
         row_u += wy * u;
       }
       pg += tx.weight(li, a) * row_g;
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(128, 9)
     const uint32_t own = cw.byte(i) & 0xFu, oth = fold_nibbles<A>(cw, others_mask) & ~own;
     reinterpret_cast<uint32_t*>(s_own)[q] = 0x01010101u + spread_nibble(own) - spread_nibble(oth);
     const float4 o4 = reinterpret_cast<float4*>(s_map)[q];  // the staged map holds odds: to probabilities, in place
-    reinterpret_cast<float4*>(s_map)[q] = make_float4(from_odds(o4.x), from_odds(o4.y), from_odds(o4.z), from_odds(o4.w));
+    reinterpret_cast<float4*>(s_map)[q] = make_float4(from_odds_fast(o4.x), from_odds_fast(o4.y), from_odds_fast(o4.z), from_odds_fast(o4.w));
   }
   {
     // footprint image, element (u, v) walked without per-element divisions
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(128)
     const uint32_t any = fold_nibbles<A>(load_code<A>(codes, q), all_mask);
     reinterpret_cast<uint32_t*>(s_uni)[q] = 0x01010101u + spread_nibble(any);
     const float4 o4 = reinterpret_cast<float4*>(s_map)[q];  // odds -> probabilities, in place
-    reinterpret_cast<float4*>(s_map)[q] = make_float4(from_odds(o4.x), from_odds(o4.y), from_odds(o4.z), from_odds(o4.w));
+    reinterpret_cast<float4*>(s_map)[q] = make_float4(from_odds_fast(o4.x), from_odds_fast(o4.y), from_odds_fast(o4.z), from_odds_fast(o4.w));
   }
   __syncthreads();
   pool_rows<MT>(tap_y, s_map, 1.0f, s_tg, cfg.gx, cfg.gy, cfg.py, rr, rpr, lj_r);

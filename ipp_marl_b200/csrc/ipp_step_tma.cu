@@ -44,6 +44,8 @@ __device__ __forceinline__ unsigned long long trace_now() {
   do { if (blockIdx.x == 0 && (k) < 64) atomicMin(&g_tma_trace[(k) * 8 + (e)], trace_now()); } while (0)
 #define IPP_TRACE_MAX(k, e) \
   do { if (blockIdx.x == 0 && (k) < 64) atomicMax(&g_tma_trace[(k) * 8 + (e)], trace_now()); } while (0)
+#define IPP_TRACE_ADD(k, e, v) \
+  do { if (blockIdx.x == 0 && (k) < 64) atomicAdd(&g_tma_trace[(k) * 8 + (e)], (unsigned long long)(v)); } while (0)
 extern "C" int ipp_debug_tma_trace(unsigned long long* out, int reset) {
   static unsigned long long init[64 * 8];
   if (reset) {
@@ -56,6 +58,7 @@ extern "C" int ipp_debug_tma_trace(unsigned long long* out, int reset) {
 #define IPP_TRACE_SET(k, e)
 #define IPP_TRACE_MIN(k, e)
 #define IPP_TRACE_MAX(k, e)
+#define IPP_TRACE_ADD(k, e, v)
 #endif
 
 namespace ipp {
@@ -262,7 +265,13 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     const uint32_t es = k & (TMA_D - 1), pe = (k / TMA_D) & 1u;
     // Tasks are handed out in item order and a slot is recycled only after all NT tiles of its item have arrived, so
     // a warp can never be two phases behind on these barriers.
+#ifdef IPP_TMA_TRACE
+    const unsigned long long tw0 = trace_now();
+#endif
     ptx::mbar_wait(rec_full + 8u * es, pe);
+#ifdef IPP_TMA_TRACE
+    if (lane == 0) IPP_TRACE_ADD(k, 6, trace_now() - tw0);
+#endif
     StageMeta<A>& sm = meta[es];
     const int32_t nq = sm.nq;  // (written by the producer before it armed rec_full)
     const int32_t ql = (int32_t)tile * 32 + lane;

@@ -19,7 +19,9 @@ lib.ipp_debug_tma_trace(buf, 1)
 env.step()
 torch.cuda.synchronize()
 lib.ipp_debug_tma_trace(buf, 0)
-a = np.array(buf[:], dtype=np.float64).reshape(64, 8)[:56, :6]
+raw = np.array(buf[:], dtype=np.float64).reshape(64, 8)
+print("ns waited for the record, summed over the item's 20 tile tasks:", raw[:56, 6].astype(int).tolist())
+a = raw[:56, :6]
 t0 = a[0, 0]
 a = (a - t0) / 1e3
 np.set_printoptions(precision=2, suppress=True, linewidth=200)

@@ -12,9 +12,10 @@
 //     code byte into the 4 odds multipliers with ONE 16-byte table load (lut[altitude][byte]);
 //   * the 4 cells of a quad are processed branch-free, the multiplies two cells per instruction with the
 //     sm_100 packed-float32 FMUL2 form (IEEE per lane => still bit-exact);
-//   * a local map whose range flag (ipp_state.map_flags) is clear lies inside [o_min, o_max], so the whole-map
-//     clamp of a fuse pass changes nothing outside the footprints: quads no footprint reaches are skipped
-//     (the TMA kernel: by one warp vote per (tile, map); the direct kernel: not even loaded from HBM);
+//   * a local-map tile whose range flag (ipp_state.map_flags) is clear lies inside [o_min, o_max], so the whole-map
+//     clamp of a fuse pass changes nothing outside the footprints: (tile, map) pairs no footprint reaches are
+//     neither loaded nor stored (the plan kernel's ItemRec says which have work), and inside a chain a clamp is
+//     executed only where the value may actually be out of range (fuse_chain);
 //   * only the reward needs more: H(p) of the global map's cells from their odds (1 MUFU.RCP + 2 MUFU.LG2).
 #pragma once
 #include "ipp_device.cuh"

@@ -15,6 +15,11 @@ for k in step_tma reset_fill plan_kernel; do
   echo "== ncu full $k"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -f -o $OUT/r02_prof_$k $B > $OUT/r02_ncu_$k.log 2>&1
 done
+for k in features_actor features_critic eval_metrics; do
+  echo "== ncu full $k"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $OUT/r02_prof_$k python scripts/split_loop.py > $OUT/r02_ncu_$k.log 2>&1
+done
 python scripts/kernel_times.py 2>&1 | grep tma | tee $OUT/r02_kernel_times.log
+python scripts/split_times.py 2>&1 | tail -1 | tee $OUT/r02_split_times.log
 tail -c 300 $OUT/r02_bench.err
 ls -la $OUT | tail -12

@@ -7,7 +7,8 @@
 //   * bulk copies (cp.async.bulk, SASS UBLKCP) into shared memory for what every tile task of an item needs: the
 //     item's record from the plan kernel (ItemRec: which tiles of which local map have work), its two measurement-
 //     code rows and its GLOBAL map — 8 item slots, three copies per item, issued by one producer lane;
-//   * plain streaming loads (ld.global.cs.v4) straight into registers for the LOCAL-map quads, issued by the tile
+//   * plain loads (ld.global.cg.v4: L2 only — with the evict-first hint of ld.global.cs the lines the producer had
+//     prefetched into L2 were gone again too often: 118 -> 115 us) straight into registers for the LOCAL-map quads, issued by the tile
 //     task itself as soon as the item's record has landed and BEFORE it waits for the item's bulk data, so that
 //     their latency overlaps that wait; (tile, map) pairs without work are not loaded at all.
 // Roles (no block-wide barrier after start-up; mbarriers do all the synchronisation):
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     if (kWide) {
 #pragma unroll
       for (int i = 0; i < A; ++i)
-        if ((work >> i) & 1u) l4[i] = __ldcs(out_l + i * stride4);  // warp-uniform branch
+        if ((work >> i) & 1u) l4[i] = __ldcg(out_l + i * stride4);  // warp-uniform branch
     }
     ptx::mbar_wait(env_full + 8u * es, pe);
     if (lane == 0) IPP_TRACE_MIN(k, 3);
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
 #pragma unroll
     for (int i = 0; i < A; ++i) {
       if (!((work >> i) & 1u)) continue;  // warp-uniform: no work for this (tile, map); it was not loaded
-      if (!kWide) l4[i] = __ldcs(out_l + i * stride4);  // A > 4: one map at a time
+      if (!kWide) l4[i] = __ldcg(out_l + i * stride4);  // A > 4: one map at a time
       const bool tile_dirty = ((dirty >> i) & 1u) != 0u;
       const bool b_i = local_quad<A, DO_OWN>(cfg, sm.rec.env, sm.rec.env.comm[i], touch, tile_dirty, i, cw,
                                              DO_OWN ? nw.byte(i) : 0u, lut, l4[i]);

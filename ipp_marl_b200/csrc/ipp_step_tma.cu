@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(tma_threads(A), 1)
     // destination) while the tasks are still D items away — their plain loads then see L2, not DRAM, latency
     // (same-box A/B at 8192 x 4 x 50x50: 117.7 us with, 122.0 us without).  Measured alternatives that were slower:
     // a single barrier per item (122 us), tile tasks of 2 / 4 tiles (131 / 134 us), a static deal of the tasks
-    // (135 us), 4 or 12 item slots (120 / 133 us), all maps through the bulk-copy engine (130 .. 150 us: the engine
+    // (135 us), 4 or 12 item slots (120 / 133 us), an evict-first L2 hint on the bulk copies of the global map and the
+    // code rows (118.7 vs 114.6 us), all maps through the bulk-copy engine (130 .. 150 us: the engine
     // moves ~20 bytes per clock and SM, and a bulk copy costs the issuing lane ~0.13 us; scripts/trace_tma.py).
     auto fetch_rec = [&](uint32_t kk) {
       const int32_t item = (int32_t)blockIdx.x + (int32_t)kk * (int32_t)gridDim.x;

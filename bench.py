@@ -423,11 +423,13 @@ def train_leg(torch, dist, dev, world, rank, params, B, iters, bf16):
             dist.barrier()
             torch.cuda.synchronize()
 
-    tr.rollout()
-    tr.update()  # warm-up: cuDNN algorithm selection, allocator, the one-piece first all-reduce
+    for it in range(2):  # warm-up: cuDNN algorithm selection, allocator growth, the one-piece first all-reduce
+        tr.rollout(episodes=torch.arange(B) + (rank * B + 1))
+        tr.update()
     sync()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     t_roll = t_upd = 0.0
+    per_iter = []
     for it in range(iters):
         base = (it + 1) * world * B + rank * B + 1
         e[0].record()
@@ -438,6 +440,7 @@ def train_leg(torch, dist, dev, world, rank, params, B, iters, bf16):
         sync()
         t_roll += e[0].elapsed_time(e[1])
         t_upd += e[1].elapsed_time(e[2])
+        per_iter.append([round(e[0].elapsed_time(e[1]), 2), round(e[1].elapsed_time(e[2]), 2)])
     # the collective alone: both networks' flat gradient buffers, bucket by bucket, nothing to overlap with
     ar_ms = 0.0
     n_opt = tr.optimizer_steps_per_update()
@@ -461,7 +464,8 @@ def train_leg(torch, dist, dev, world, rank, params, B, iters, bf16):
     out = {"workload": "COMA rollout + update, %d envs/GPU x %d UAVs, 50x50, %d GPU(s)" % (B, env.A, world),
            "value": steps / ((t_roll + t_upd) * 1e-3), "unit": UNIT,
            "rollout_env_steps_per_sec": steps / (t_roll * 1e-3), "ms_rollout_per_iter": t_roll / iters,
-           "ms_update_per_iter": t_upd / iters, "iters": iters, "data_passes": 1, "minibatch": 16384,
+           "ms_update_per_iter": t_upd / iters, "iters": iters, "rank0_ms_rollout_update_per_iter": per_iter,
+           "data_passes": 1, "minibatch": 16384,
            "compute_dtype": "bf16 autocast" if bf16 else "fp32",
            "optimizer_steps_per_update": n_opt,
            "grad_allreduce": {"bytes_per_critic_plus_actor_step": grad_bytes if world > 1 else 0,
@@ -584,7 +588,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the COMA train leg (configs[2] / configs[3])")
     ap.add_argument("--no-extra", action="store_true", help="--impl reference: skip the extra reference shapes")
     ap.add_argument("--train-envs", type=int, default=8192, help="envs per GPU of the train leg")
-    ap.add_argument("--train-iters", type=int, default=1)
+    ap.add_argument("--train-iters", type=int, default=2)
     ap.add_argument("--train-bf16", action="store_true", help="train leg with bf16 autocast (default: fp32 like the reference)")
     args = ap.parse_args()
     if args.impl == "reference":

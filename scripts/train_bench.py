@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--passes", type=int, default=1)
     ap.add_argument("--minibatch", type=int, default=16384)
-    ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--bf16", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -34,7 +34,7 @@ def main():
     params["experiment"]["missions"]["n_agents"] = args.agents
     env = BatchedIPPEnv(params, args.envs, device=dev, env_id_base=rank * args.envs)
     tr = COMATrainer(env, params, minibatch=args.minibatch, data_passes=args.passes,
-                     compute_dtype=torch.float32 if args.fp32 else torch.bfloat16)
+                     compute_dtype=torch.bfloat16 if args.bf16 else torch.float32)
     def sync():
         torch.cuda.synchronize()
         if world > 1: dist.barrier(); torch.cuda.synchronize()
@@ -51,6 +51,7 @@ def main():
         stats = tr.update()
         e[2].record()
         sync()
+        print("rank %d iter %d: rollout %.1f ms update %.1f ms" % (rank, it, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])), flush=True)
         t_roll += e[0].elapsed_time(e[1]); t_upd += e[1].elapsed_time(e[2])
     tt = torch.tensor([t_roll, t_upd], device=dev, dtype=torch.float64)
     if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -62,7 +63,7 @@ def main():
             "rollout_env_steps_per_sec": steps / (t_roll * 1e-3), "n_gpus": world, "envs_per_gpu": args.envs,
             "agents": args.agents, "iters": args.iters, "data_passes": args.passes, "minibatch": args.minibatch,
             "ms_rollout_per_iter": t_roll / args.iters, "ms_update_per_iter": t_upd / args.iters,
-            "compute_dtype": "fp32" if args.fp32 else "bf16 autocast", "mean_return": float(torch.stack(rets).mean()),
+            "compute_dtype": "bf16 autocast" if args.bf16 else "fp32", "mean_return": float(torch.stack(rets).mean()),
             "critic_loss": float(stats["critic_loss"]), "actor_loss": float(stats["actor_loss"]),
             "model_tflops": tr.flops_per_update() * args.iters / ((t_roll + t_upd) * 1e-3) / 1e12 * world,
             "grad_allreduce_bytes_per_step": 4 * (2275846 + 2307846) if world > 1 else 0}))

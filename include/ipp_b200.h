@@ -145,7 +145,8 @@ int ipp_destroy(ipp_handle* h);
 int ipp_set_step_variant(ipp_handle* h, int32_t variant);
 int ipp_get_step_variant(const ipp_handle* h);
 
-/* Bytes of device scratch held by the handle (reward partials, reset parameters). */
+/* Bytes of device scratch held by the handle (reward partials, reset parameters, the per-step item records that the
+ * plan kernel hands to the map kernel: 144 bytes per env and map segment at 4 agents). */
 int64_t ipp_scratch_bytes(const ipp_handle* h);
 
 /*

@@ -386,6 +386,47 @@ class SparseKernelModelEnv(KernelModelEnv):
             flat = np.concatenate([flat, np.zeros(flat.shape[:-1] + (pad,), bool)], -1)
         return flat.reshape(flat.shape[:-1] + (self.n_tiles, self.TILE_CELLS)).any(-1)
 
+    def _cells_of_tiles(self, tmask):
+        """[..., n_tiles] -> [..., gx, gy] (every cell of a selected tile)."""
+        n_cells = self.tab.gx * self.tab.gy
+        cells = np.repeat(tmask, self.TILE_CELLS, axis=-1)[..., :n_cells]
+        return cells.reshape(cells.shape[:-1] + (self.tab.gx, self.tab.gy))
+
+    def _tile_range(self, inr):
+        """[B, gx, gy] footprint mask -> [B, n_tiles]: the tiles between the footprint's first and last cell — what the
+        plan kernel's `tile_range` hands to the map kernel (a superset of the tiles the footprint really reaches)."""
+        flat = inr.reshape(inr.shape[0], -1)
+        some = flat.any(1)
+        first = flat.argmax(1) // self.TILE_CELLS
+        last = (flat.shape[1] - 1 - flat[:, ::-1].argmax(1)) // self.TILE_CELLS
+        t = np.arange(self.n_tiles)[None]
+        return some[:, None] & (t >= first[:, None]) & (t <= last[:, None])
+
+    def _apply_bookkept(self, o, passes, tile_oor, own=None):
+        """csrc/ipp_cell.cuh::fuse_chain + local_quad restated: the passes of the ENABLED agents in id order; a pass
+        whose footprint misses a tile multiplies its cells by exactly 1 (k_out == 1) and is not executed there, and a
+        clamp is executed exactly where the value may lie outside [o_min, o_max] — `tile_oor` [B, n_tiles]: the tile's
+        range flag to begin with, then "a multiply happened since the last clamp".  passes: (in_rect, k, enabled[B])."""
+        tab = self.tab
+        kout_one = bool(tab.k_out == F32(1))
+        o = o.astype(F32, copy=True)
+        oor = tile_oor.copy()
+        for inr, k, en in passes:
+            en_t = np.broadcast_to(en[:, None], oor.shape)
+            clamp_here = self._cells_of_tiles(en_t & oor)
+            o = np.where(clamp_here, np.minimum(np.maximum(o, tab.o_min), tab.o_max), o).astype(F32)
+            oor = oor & ~en_t
+            touch = self._tile_range(inr) if kout_one else np.ones_like(oor)
+            mul_here = self._cells_of_tiles(en_t & touch)
+            kk = np.where(inr, k, tab.k_out).astype(F32)
+            o = np.where(mul_here, o * kk, o).astype(F32)
+            oor = oor | (en_t & touch)
+        if own is not None:
+            inr, k = own
+            oc = np.minimum(np.maximum(o, tab.o_min), tab.o_max)
+            o = np.where(inr, oc * k, o).astype(F32)
+        return o
+
     def _cells_of_quads(self, qmask):
         """[..., n_quads] -> [..., gx, gy] (every cell of a selected quad)."""
         n_cells = self.tab.gx * self.tab.gy
@@ -399,13 +440,17 @@ class SparseKernelModelEnv(KernelModelEnv):
         new_pos, masks, acts = self._choose_and_move(actions)
         new = [self._k_of(new_pos[:, i], i, self.t + 1) for i in range(A)]
         last = self.glob_o
-        self.glob_o = self._apply(last, [(prev[j][0], prev[j][1], True) for j in range(A)])  # global map: dense
+        # global map: every cell is clamped first (the reward needs the clamped odds anyway), then the bookkept chain
+        all_on = np.ones(self.B, bool)
+        g0 = np.minimum(np.maximum(last, self.tab.o_min), self.tab.o_max).astype(F32)
+        self.glob_o = self._apply_bookkept(g0, [(prev[j][0], prev[j][1], all_on) for j in range(A)],
+                                           np.zeros((self.B, self.n_tiles), bool))
         rel, ab = self._reward(last, self.glob_o)
         kout_one = bool(self.tab.k_out == F32(1))
         quads_per_tile = self.TILE_CELLS // 4
         for i in range(A):
-            passes = [(prev[j][0], prev[j][1], True, comm[:, i, j]) for j in range(A) if j != i]
-            dense = self._apply(self.local_o[:, i], passes + [(new[i][0], new[i][1], False)])
+            passes = [(prev[j][0], prev[j][1], comm[:, i, j]) for j in range(A) if j != i]
+            dense = self._apply_bookkept(self.local_o[:, i], passes, self.flags[:, i], own=(new[i][0], new[i][1]))
             en = np.zeros(self.B, bool)
             touched = new[i][0].copy()
             for j in range(A):

@@ -76,6 +76,12 @@ def test_invalid_configs_are_rejected():
         rc = lib.ipp_create(C.byref(cfg), C.byref(h))
         assert rc in (-1, -2), (field, rc)
     assert lib.ipp_create(None, C.byref(h)) == -1
+    # entry points reject a missing handle / io before they touch the device
+    st, io = _native.IppState(), _native.IppStepIO()
+    assert lib.ipp_step(None, C.byref(st), 0, C.byref(io), None) == -1
+    assert lib.ipp_run_steps(None, C.byref(st), 1, None, 0, 15, C.byref(io), None) == -1
+    assert lib.ipp_reset(None, C.byref(st), None, None) == -1
+    assert lib.ipp_status_string(-1) == b"invalid argument" and lib.ipp_version() >= 210
     params = load_kats()["synthetic50"]["params"]
     params["experiment"]["constraints"]["num_actions"] = 9
     with pytest.raises(ValueError):

@@ -309,6 +309,7 @@ __device__ void build_item_records(const ipp_config& cfg, const ipp_state& st, c
     const uint32_t tb = tch | (drt << 8);
     const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, tb, 1);
     if (lane < ITEM_TILES && (lane & 1) == 0) out[6 * A + (lane >> 1)] = tb | (nb << 16);
+    if (lane < rw - (6 * A + ITEM_TILES / 2)) out[6 * A + ITEM_TILES / 2 + lane] = 0u;  // the record's padding words
   }
 }
 

@@ -70,7 +70,10 @@ constexpr int TMA_PF = 16;            // producer's ring of prefetched item reco
 
 template <int A>
 struct alignas(16) StageMeta {
-  ItemRec<A> rec;   // bulk-copied: the item's record written by the plan kernel
+  union {
+    ItemRec<A> rec;                  // bulk-copied: the item's record written by the plan kernel
+    uint32_t rec_raw[rec_words(A)];  // (the copy brings the record's padding words along: they must land in here)
+  };
   uint32_t bad[8];  // per local map, the tiles whose results left [o_min, o_max] in this step
   int32_t b, chunk, nq, pad;
 };

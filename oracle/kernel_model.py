@@ -284,7 +284,10 @@ class KernelModelEnv:
     # ---- reward -------------------------------------------------------------------------------
     def _reward(self, last, nxt):
         """utils/reward.py:68-82 on odds maps: float32 per-cell terms and float64 sums.  H of the clamped odds
-        (p = o/(1+o), q = 1/(1+o)); the weights compare the NEXT odds with 0.501/0.499 and 0.499/0.501."""
+        (p = o/(1+o), q = 1/(1+o)); the weights compare the NEXT odds with 0.501/0.499 and 0.499/0.501.
+        The reward is NOT part of the bit-exact specification (only the belief maps are): the kernel evaluates the
+        same H as lg(1+o) - p lg(o) with the approximate MUFU reciprocal / log2 and sums per warp in float32, and is
+        compared with this model — and with the reference's golden rewards — at rtol = atol = 1e-5."""
         tab = self.tab
 
         def H(o):
